@@ -1,0 +1,246 @@
+/* modle_b200 -- C ABI of the B200-native loop-extrusion hot path.
+ *
+ * Drop-in boundary for ONE path of paulsengroup/modle (reference paths are relative to the
+ * reference checkout): the per-(interval, cell) loop Simulation::simulate_one_cell
+ * (src/libmodle/cpu/simulation.cpp:896-986) plus the contact registration it calls
+ * (src/libmodle/cpu/register_contacts.cpp:93-232), i.e. what a worker thread does between popping
+ * a Task and pushing it back as COMPLETED (src/libmodle/cpu/scheduler_simulate.cpp:220-261).
+ * The reference has no FFI layer; the seam is the C++ class modle::Simulation
+ * (src/libmodle/cpu/include/modle/simulation.hpp:45-151). INTEGRATION.md shows the binding a
+ * maintainer would add inside Simulation::run_simulate.
+ *
+ * Everything is plain C: POD structs, pointers and sizes. All functions return 0 on success or a
+ * negative modle_b200_status; modle_b200_last_error() returns a thread-local message. There is no
+ * CPU fallback: every compute entry point fails with MODLE_B200_ERR_NO_DEVICE without a CUDA GPU.
+ */
+#ifndef MODLE_B200_H
+#define MODLE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MODLE_B200_ABI_VERSION 1
+
+typedef enum modle_b200_status {
+  MODLE_B200_OK = 0,
+  MODLE_B200_ERR_INVALID_ARGUMENT = -1,
+  MODLE_B200_ERR_NO_DEVICE = -2,
+  MODLE_B200_ERR_CUDA = -3,
+  MODLE_B200_ERR_UNSUPPORTED = -4, /* e.g. interval does not fit the shared-memory-resident kernel */
+  MODLE_B200_ERR_DEVICE_FAULT = -5 /* kernel-side invariant violated (reported, never ignored) */
+} modle_b200_status;
+
+/* dna::Direction values (src/common/include/modle/common/dna.hpp:77-80). A barrier stores its
+ * BLOCKING direction: motif '+' blocks REV-moving units, '-' blocks FWD-moving units
+ * (src/libmodle/internal/extrusion_barriers_impl.hpp:61-72). */
+enum { MODLE_B200_DIR_REV = 1, MODLE_B200_DIR_FWD = 2 };
+
+/* Config::ContactSamplingStrategy bits (simulation_config.hpp:33-38) */
+enum {
+  MODLE_B200_SAMPLE_NOISIFY = 1,
+  MODLE_B200_SAMPLE_TAD = 2,
+  MODLE_B200_SAMPLE_LOOP = 4
+};
+
+/* Config::StoppingCriterion (simulation_config.hpp:29) */
+enum { MODLE_B200_STOP_CONTACT_DENSITY = 0, MODLE_B200_STOP_SIMULATION_EPOCHS = 1 };
+
+/* The fields of modle::Config the path reads (simulation_config.hpp:53-113), holding the values
+ * AFTER Cli::transform_args (src/modle/cli.cpp:993-1016). modle_b200_default_params() +
+ * modle_b200_transform_params() reproduce that arithmetic. Same names as the reference. */
+typedef struct modle_b200_sim_params {
+  uint64_t bin_size;
+  uint64_t diagonal_width;
+  uint64_t rev_extrusion_speed;
+  uint64_t fwd_extrusion_speed;
+  uint64_t rev_extrusion_speed_burnin;
+  uint64_t fwd_extrusion_speed_burnin;
+  double rev_extrusion_speed_std;
+  double fwd_extrusion_speed_std;
+  double prob_of_lef_release;
+  double prob_of_lef_release_burnin;
+  double hard_stall_lef_stability_multiplier;
+  double soft_stall_lef_stability_multiplier;
+  double probability_of_extrusion_unit_bypass;
+  double lef_bar_major_collision_pblock;
+  double lef_bar_minor_collision_pblock;
+  double tad_to_loop_contact_ratio;
+  double genextreme_mu;
+  double genextreme_sigma;
+  double genextreme_xi;
+  double number_of_lefs_per_mbp;
+  double target_contact_density;
+  uint64_t target_simulation_epochs;
+  uint64_t contact_sampling_interval;
+  uint64_t avg_lef_processivity;
+  uint64_t probability_normalization_factor;
+  double extrusion_barrier_occupancy;
+  double barrier_occupied_stp;
+  double barrier_not_occupied_stp;
+  double burnin_speed_coefficient;
+  uint64_t burnin_history_length;
+  uint64_t burnin_smoothing_window_size;
+  uint64_t min_burnin_epochs;
+  uint64_t max_burnin_epochs;
+  uint64_t burnin_target_epochs_for_lef_activation;
+  uint64_t num_cells;
+  uint64_t seed;
+  uint32_t contact_sampling_strategy; /* MODLE_B200_SAMPLE_* bits */
+  uint32_t stopping_criterion;        /* MODLE_B200_STOP_* */
+  uint32_t track_1d_lef_position;
+  uint32_t skip_burnin;
+  uint32_t normalize_probabilities;
+  uint32_t override_extrusion_barrier_occupancy;
+  uint64_t debug_max_epochs; /* not in the reference: stop every cell after this many epochs
+                                (UINT64_MAX = off); used by the parity tests to bisect */
+} modle_b200_sim_params;
+
+/* GenomicInterval geometry (src/libmodle/internal/include/modle/genome.hpp:125-195). */
+typedef struct modle_b200_interval {
+  uint64_t chrom_size;
+  uint64_t start; /* simulated range is [start, end) */
+  uint64_t end;
+  uint64_t num_lefs; /* Simulation::compute_num_lefs (simulation.cpp:1086-1090) */
+} modle_b200_interval;
+
+/* One extrusion barrier (ExtrusionBarrier, extrusion_barriers.hpp:32-60); array sorted by pos. */
+typedef struct modle_b200_barrier {
+  uint64_t pos;
+  double stp_active;
+  double stp_inactive;
+  uint32_t blocking_direction; /* MODLE_B200_DIR_* */
+  uint32_t reserved_;
+} modle_b200_barrier;
+
+/* Simulation::Task minus the interval pointer (simulation.hpp:59-69). rng_state is the serialised
+ * xoshiro256++ state the reference copies into the task (scheduler_simulate.cpp:143-158). */
+typedef struct modle_b200_cell_task {
+  uint64_t cell_id;
+  uint64_t num_target_epochs;
+  uint64_t num_target_contacts;
+  uint64_t rng_state[4];
+} modle_b200_cell_task;
+
+/* What the reference only logs per task (scheduler_simulate.cpp:246-251) plus bookkeeping. */
+typedef struct modle_b200_cell_stats {
+  uint64_t num_contacts;
+  uint64_t num_epochs;
+  uint64_t num_burnin_epochs;
+  uint64_t num_lef_updates; /* sum over simulated epochs of the number of active LEFs */
+  uint64_t num_rng_draws;   /* raw 64-bit draws consumed from the cell's stream */
+  uint64_t device_fault;    /* 0, or a kernel-side fault code */
+} modle_b200_cell_stats;
+
+/* Snapshot of one cell (debug/parity aid; arrays sized num_lefs / num_barriers by the caller). */
+typedef struct modle_b200_cell_snapshot {
+  uint64_t* rev_pos;       /* UINT64_MAX when unbound */
+  uint64_t* fwd_pos;
+  uint64_t* binding_epoch; /* UINT64_MAX when unbound */
+  uint64_t* rev_ranks;
+  uint64_t* fwd_ranks;
+  uint8_t* barrier_active;
+  uint64_t num_active_lefs;
+  uint64_t burnin_completed;
+} modle_b200_cell_snapshot;
+
+typedef struct modle_b200_context modle_b200_context;
+
+/* ---- host-only helpers (no GPU needed) ------------------------------------------------- */
+
+int modle_b200_abi_version(void);
+const char* modle_b200_last_error(void);
+
+/* Config{} defaults (simulation_config.hpp:53-113), untransformed. */
+void modle_b200_default_params(modle_b200_sim_params* p);
+/* Cli::transform_args (cli.cpp:886-1016). `*_given` say which CLI options were passed explicitly
+ * (the reference asks CLI11 for that): rev/fwd speed and --extrusion-barrier-occupancy. */
+int modle_b200_transform_params(modle_b200_sim_params* p, int rev_speed_given, int fwd_speed_given,
+                                int barrier_occupancy_given);
+
+/* Simulation::compute_num_lefs / compute_contacts_per_epoch (simulation.cpp:1076-1090). */
+uint64_t modle_b200_compute_num_lefs(const modle_b200_sim_params* p, uint64_t interval_size_bp);
+uint64_t modle_b200_compute_contacts_per_epoch(const modle_b200_sim_params* p, uint64_t num_lefs);
+/* ContactMatrixDense geometry (contact_matrix_dense_impl.hpp:39-50): nrows, ncols; the band
+ * buffer holds nrows*ncols+1 uint32 with pixel (i=|b1-b2|, j=max(b1,b2)) at j*nrows+i. */
+void modle_b200_band_shape(const modle_b200_sim_params* p, uint64_t interval_size_bp,
+                           uint64_t* nrows, uint64_t* ncols);
+
+/* GenomicInterval::hash with Config::seed (genome.cpp:201-224): XXH3-64(seed) over
+ * name || u64 chrom_size || u64 start || u64 end. */
+int modle_b200_interval_hash(const char* chrom_name, size_t name_len, uint64_t chrom_size,
+                             uint64_t start, uint64_t end, uint64_t seed, uint64_t* out);
+/* random::PRNG(seed) (common/random.hpp:26-30) and Xoshiro256PlusPlus::jump(). */
+void modle_b200_rng_seed(uint64_t seed, uint64_t state[4]);
+uint64_t modle_b200_rng_next(uint64_t state[4]);
+void modle_b200_rng_jump(uint64_t state[4]);
+
+/* Barrier self-transition probabilities from a BED score (genome.cpp:255-271) and
+ * the occupancy <-> stp identities (extrusion_barriers_impl.hpp:106-128). */
+double modle_b200_stp_active_from_occupancy(double stp_inactive, double occupancy);
+double modle_b200_occupancy_from_stp(double stp_active, double stp_inactive);
+
+/* The per-interval task fan-out of Simulation::run_simulate (scheduler_simulate.cpp:104-160):
+ * engine = PRNG(interval hash), per-cell targets (:129-141), one jump() per cell (:158).
+ * Fills tasks[0..num_cells). */
+int modle_b200_make_cell_tasks(const modle_b200_sim_params* p, const char* chrom_name,
+                               size_t name_len, const modle_b200_interval* interval,
+                               modle_b200_cell_task* tasks);
+
+/* ---- device path ------------------------------------------------------------------------ */
+
+/* Binds a context to CUDA device `device`; fails without a GPU (no CPU fallback). */
+int modle_b200_init(modle_b200_context** ctx, int device);
+void modle_b200_destroy(modle_b200_context* ctx);
+
+/* Simulates `num_cells` cells of one interval: the GPU replacement for popping num_cells Tasks
+ * and running simulate_one_cell on each. HOST buffers in, HOST buffers out (copies included):
+ *   band_out   nrows*ncols+1 uint32, ADDED to (caller zero-initialises; reference layout)
+ *   occ1d_out  ncols uint64 or NULL, ADDED to (GenomicInterval::lef_1d_occupancy)
+ *   stats_out  num_cells entries or NULL
+ *   missed_updates_out  ContactMatrixDense::_updates_missed increment, or NULL            */
+int modle_b200_simulate_interval(modle_b200_context* ctx, const modle_b200_sim_params* params,
+                                 const modle_b200_interval* interval,
+                                 const modle_b200_barrier* barriers, size_t num_barriers,
+                                 const modle_b200_cell_task* tasks, size_t num_cells,
+                                 uint32_t* band_out, uint64_t* occ1d_out,
+                                 modle_b200_cell_stats* stats_out, uint64_t* missed_updates_out);
+
+/* Same, with every buffer already resident in device memory (d_* are device pointers in the
+ * context's device; cuda_stream is a cudaStream_t or NULL for the context's own stream). The call
+ * is asynchronous; d_missed_updates (1 uint64) and d_stats accumulate on the device.            */
+int modle_b200_simulate_interval_device(modle_b200_context* ctx,
+                                        const modle_b200_sim_params* params,
+                                        const modle_b200_interval* interval,
+                                        const modle_b200_barrier* d_barriers, size_t num_barriers,
+                                        const modle_b200_cell_task* d_tasks, size_t num_cells,
+                                        uint32_t* d_band, uint64_t* d_occ1d,
+                                        modle_b200_cell_stats* d_stats, uint64_t* d_missed_updates,
+                                        void* cuda_stream);
+int modle_b200_synchronize(modle_b200_context* ctx);
+
+/* Runs one cell for params->debug_max_epochs epochs and returns its state (parity bisection). */
+int modle_b200_snapshot_cell(modle_b200_context* ctx, const modle_b200_sim_params* params,
+                             const modle_b200_interval* interval,
+                             const modle_b200_barrier* barriers, size_t num_barriers,
+                             const modle_b200_cell_task* task, modle_b200_cell_snapshot* snapshot,
+                             modle_b200_cell_stats* stats_out);
+
+/* Contact-register kernel in isolation (register_contacts.cpp:149-152 + ContactMatrixDense::
+ * increment, contact_matrix_dense_safe_impl.hpp:54-89): scatters n (bin1, bin2) pairs held in
+ * device memory into the device band; used to replay a contact stream for the roofline run. */
+int modle_b200_register_contacts_device(modle_b200_context* ctx, const uint32_t* d_bin1,
+                                        const uint32_t* d_bin2, size_t n, uint64_t nrows,
+                                        uint64_t ncols, uint32_t* d_band,
+                                        uint64_t* d_missed_updates, void* cuda_stream);
+
+/* Number of kernels this library has launched on the context so far (bench bookkeeping). */
+uint64_t modle_b200_kernel_launches(const modle_b200_context* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MODLE_B200_H */

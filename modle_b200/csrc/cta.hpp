@@ -1,0 +1,317 @@
+// CTA abstraction shared by the CUDA kernel and the host-side emulation used by the CPU tests.
+//
+// The per-cell simulation (sim_core.hpp) is written in bulk-synchronous style: a sequence of
+// "thread regions" (every thread of the CTA runs the body once) separated by CTA-wide barriers,
+// plus a handful of block-wide primitives (scans over one value per thread). On the device a
+// region body runs once per hardware thread; in the emulation (MODLE_B200_EMU, plain g++) the
+// region is a loop over virtual thread ids, so the same source is exercised on the CPU with any
+// virtual CTA width. The emulation is TEST INFRASTRUCTURE (it lives behind tests/emu) and is
+// never linked into the product library.
+#pragma once
+#include <cstdint>
+
+#if defined(__CUDACC__) && !defined(MODLE_B200_EMU)
+#define MB_DEVICE_BUILD 1
+#define MB_FN __device__ __forceinline__
+#define MB_HD __host__ __device__ __forceinline__
+#define MB_FN_NOINLINE __device__ __noinline__
+#else
+#define MB_DEVICE_BUILD 0
+#define MB_FN inline
+#define MB_HD inline
+#define MB_FN_NOINLINE inline
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#endif
+
+namespace modle_b200 {
+
+using u8 = std::uint8_t;
+using u16 = std::uint16_t;
+using u32 = std::uint32_t;
+using u64 = std::uint64_t;
+using i32 = std::int32_t;
+using i64 = std::int64_t;
+
+constexpr int kMaxThreads = 1024;
+constexpr int kMaxWarps = kMaxThreads / 32;
+
+// Scratch the block-wide primitives need (lives in shared memory on the device).
+struct CtaScratch {
+  u64 warp_u64[kMaxWarps];
+  u64 warp_u64b[kMaxWarps];
+  double warp_f64[kMaxWarps];
+  u64 bcast_u64;
+  double bcast_f64;
+};
+
+// "Affine-min" element x -> min(a, x + b) over signed 64-bit; closed under composition. Used for
+// the neighbour scans (adjust_moves, secondary collisions). `a` large = no cap.
+struct MinPlus {
+  i64 a;
+  i64 b;
+};
+constexpr i64 kMinPlusInf = (i64(1) << 60);
+MB_FN MinPlus minplus_identity() { return MinPlus{kMinPlusInf, 0}; }
+// b == kMinPlusInf marks a constant map x -> a (used to restart a scan at a segment head).
+MB_FN MinPlus minplus_const(i64 a) { return MinPlus{a, kMinPlusInf}; }
+// apply `first`, then `second`
+MB_FN MinPlus minplus_then(const MinPlus& first, const MinPlus& second) {
+  if (second.b >= kMinPlusInf) return second;
+  MinPlus r;
+  const i64 a1b2 = first.a >= kMinPlusInf ? kMinPlusInf : first.a + second.b;
+  r.a = second.a < a1b2 ? second.a : a1b2;
+  r.b = first.b >= kMinPlusInf ? kMinPlusInf : first.b + second.b;
+  if (r.a > kMinPlusInf) r.a = kMinPlusInf;
+  return r;
+}
+MB_FN i64 minplus_apply(const MinPlus& f, i64 x) {
+  if (f.b >= kMinPlusInf) return f.a;
+  const i64 y = x + f.b;
+  return f.a < y ? f.a : y;
+}
+
+// One value per thread that survives across regions: a register on the device, an array indexed
+// by the virtual thread id in the emulation.
+template <class T>
+struct PerThread {
+#if MB_DEVICE_BUILD
+  T val;
+  MB_FN explicit PerThread(int) : val() {}
+  MB_FN T& operator[](int) { return val; }
+  MB_FN const T& operator[](int) const { return val; }
+#else
+  T vals[kMaxThreads];
+  explicit PerThread(int n) {
+    for (int i = 0; i < n; ++i) vals[i] = T();
+  }
+  T& operator[](int t) { return vals[t]; }
+  const T& operator[](int t) const { return vals[t]; }
+#endif
+};
+
+#if MB_DEVICE_BUILD
+
+struct Cta {
+  CtaScratch* scr;
+  MB_FN int nt() const { return static_cast<int>(blockDim.x); }
+  MB_FN int first() const { return static_cast<int>(threadIdx.x); }
+  MB_FN int step() const { return static_cast<int>(blockDim.x); }
+  MB_FN bool leader(int tid) const { return tid == 0; }
+  MB_FN void sync() const { __syncthreads(); }
+
+  // exclusive prefix sum of one u64 per thread; *total receives the CTA-wide sum
+  MB_FN u64 exscan_sum(int tid, u64 v, u64* total) const {
+    const int lane = tid & 31, warp = tid >> 5, nw = (nt() + 31) >> 5;
+    u64 inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const u64 o = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += o;
+    }
+    if (lane == 31) scr->warp_u64[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      u64 w = lane < nw ? scr->warp_u64[lane] : 0;
+      u64 winc = w;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const u64 o = __shfl_up_sync(0xffffffffu, winc, d);
+        if (lane >= d) winc += o;
+      }
+      if (lane < nw) scr->warp_u64[lane] = winc - w;
+      if (lane == 31) scr->bcast_u64 = winc;
+    }
+    __syncthreads();
+    const u64 res = scr->warp_u64[warp] + inc - v;
+    if (total) *total = scr->bcast_u64;
+    __syncthreads();
+    return res;
+  }
+
+  MB_FN u64 reduce_max(int tid, u64 v) const {
+    const int lane = tid & 31, warp = tid >> 5, nw = (nt() + 31) >> 5;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      const u64 o = __shfl_xor_sync(0xffffffffu, v, d);
+      v = o > v ? o : v;
+    }
+    if (lane == 0) scr->warp_u64[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+      u64 w = lane < nw ? scr->warp_u64[lane] : 0;
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+        const u64 o = __shfl_xor_sync(0xffffffffu, w, d);
+        w = o > w ? o : w;
+      }
+      if (lane == 0) scr->bcast_u64 = w;
+    }
+    __syncthreads();
+    const u64 r = scr->bcast_u64;
+    __syncthreads();
+    return r;
+  }
+  MB_FN u64 reduce_min(int tid, u64 v) const { return ~reduce_max(tid, ~v); }
+  MB_FN u64 reduce_sum(int tid, u64 v) const {
+    u64 total;
+    exscan_sum(tid, v, &total);
+    return total;
+  }
+
+  // Sum of one double per thread in a FIXED order: lanes pairwise (xor butterfly is symmetric, so
+  // every lane ends with the same value), then warps 0..nw-1 left to right.
+  MB_FN double reduce_sum_f64(int tid, double v) const {
+    const int lane = tid & 31, warp = tid >> 5, nw = (nt() + 31) >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) v = v + __shfl_xor_sync(0xffffffffu, v, d);
+    if (lane == 0) scr->warp_f64[warp] = v;
+    __syncthreads();
+    if (tid == 0) {
+      double acc = 0.0;
+      for (int w = 0; w < nw; ++w) acc = acc + scr->warp_f64[w];
+      scr->bcast_f64 = acc;
+    }
+    __syncthreads();
+    const double r = scr->bcast_f64;
+    __syncthreads();
+    return r;
+  }
+
+  // Exclusive scan of MinPlus elements in thread order: returns the composition of the elements
+  // of all lower-numbered threads (applied lowest thread first).
+  MB_FN MinPlus exscan_minplus(int tid, MinPlus v) const {
+    const int lane = tid & 31, warp = tid >> 5, nw = (nt() + 31) >> 5;
+    MinPlus inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      MinPlus o;
+      o.a = __shfl_up_sync(0xffffffffu, inc.a, d);
+      o.b = __shfl_up_sync(0xffffffffu, inc.b, d);
+      if (lane >= d) inc = minplus_then(o, inc);
+    }
+    if (lane == 31) {
+      scr->warp_u64[warp] = static_cast<u64>(inc.a);
+      scr->warp_u64b[warp] = static_cast<u64>(inc.b);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      MinPlus acc = minplus_identity();
+      for (int w = 0; w < nw; ++w) {
+        const MinPlus cur{static_cast<i64>(scr->warp_u64[w]), static_cast<i64>(scr->warp_u64b[w])};
+        scr->warp_u64[w] = static_cast<u64>(acc.a);
+        scr->warp_u64b[w] = static_cast<u64>(acc.b);
+        acc = minplus_then(acc, cur);
+      }
+    }
+    __syncthreads();
+    const MinPlus wprefix{static_cast<i64>(scr->warp_u64[warp]),
+                          static_cast<i64>(scr->warp_u64b[warp])};
+    // exclusive within the warp: shift the inclusive value up by one lane
+    MinPlus ex;
+    ex.a = __shfl_up_sync(0xffffffffu, inc.a, 1);
+    ex.b = __shfl_up_sync(0xffffffffu, inc.b, 1);
+    if (lane == 0) ex = minplus_identity();
+    const MinPlus res = minplus_then(wprefix, ex);
+    __syncthreads();
+    return res;
+  }
+
+  // ---- collectives over PerThread values (uniform results returned to every thread) ----
+  MB_FN u64 exscan_sum(PerThread<u64>& v) const {
+    u64 total;
+    v.val = exscan_sum(first(), v.val, &total);
+    return total;
+  }
+  MB_FN u64 reduce_max(const PerThread<u64>& v) const { return reduce_max(first(), v.val); }
+  MB_FN u64 reduce_min(const PerThread<u64>& v) const { return reduce_min(first(), v.val); }
+  MB_FN u64 reduce_sum(const PerThread<u64>& v) const { return reduce_sum(first(), v.val); }
+  MB_FN double reduce_sum_f64(const PerThread<double>& v) const {
+    return reduce_sum_f64(first(), v.val);
+  }
+  MB_FN void exscan_minplus(PerThread<MinPlus>& v) const { v.val = exscan_minplus(first(), v.val); }
+};
+
+#define MB_ATOMIC_MAX_U32(ptr, val) atomicMax((ptr), (val))
+#define MB_ATOMIC_OR_U32(ptr, val) atomicOr((ptr), (val))
+#define MB_ATOMIC_ADD_U32(ptr, val) atomicAdd((ptr), (val))
+#define MB_ATOMIC_ADD_U64(ptr, val) \
+  atomicAdd(reinterpret_cast<unsigned long long*>(ptr), static_cast<unsigned long long>(val))
+#define MB_U64_TO_F64(x) __ull2double_rn(x)
+
+#else  // ---------------------------------------------------------------- emulation
+
+struct Cta {
+  CtaScratch* scr;
+  int nthreads;
+  // The emulation runs a region as a loop over virtual threads, so "one value per thread"
+  // primitives are split in two halves: put(tid, v) inside one region, get(tid) in a later one.
+  int nt() const { return nthreads; }
+  int first() const { return 0; }
+  int step() const { return 1; }
+  bool leader(int tid) const { return tid == 0; }
+  void sync() const {}
+
+  u64 exscan_sum(PerThread<u64>& v) const {
+    u64 acc = 0;
+    for (int t = 0; t < nthreads; ++t) {
+      const u64 x = v[t];
+      v[t] = acc;
+      acc += x;
+    }
+    return acc;
+  }
+  u64 reduce_max(const PerThread<u64>& v) const {
+    u64 m = 0;
+    for (int t = 0; t < nthreads; ++t) m = std::max(m, v[t]);
+    return m;
+  }
+  u64 reduce_min(const PerThread<u64>& v) const {
+    u64 m = ~u64(0);
+    for (int t = 0; t < nthreads; ++t) m = std::min(m, v[t]);
+    return m;
+  }
+  u64 reduce_sum(const PerThread<u64>& v) const {
+    u64 acc = 0;
+    for (int t = 0; t < nthreads; ++t) acc += v[t];
+    return acc;
+  }
+  // same association order as the device: xor-butterfly inside each group of 32, then groups
+  // left to right
+  double reduce_sum_f64(const PerThread<double>& v) const {
+    double total = 0.0;
+    for (int w = 0; w * 32 < nthreads; ++w) {
+      double lane[32];
+      for (int l = 0; l < 32; ++l) lane[l] = (w * 32 + l < nthreads) ? v[w * 32 + l] : 0.0;
+      for (int d = 1; d < 32; d <<= 1) {
+        double nxt[32];
+        for (int l = 0; l < 32; ++l) nxt[l] = lane[l] + lane[l ^ d];
+        for (int l = 0; l < 32; ++l) lane[l] = nxt[l];
+      }
+      total = total + lane[0];
+    }
+    return total;
+  }
+  void exscan_minplus(PerThread<MinPlus>& v) const {
+    MinPlus acc = minplus_identity();
+    for (int t = 0; t < nthreads; ++t) {
+      const MinPlus x = v[t];
+      v[t] = acc;
+      acc = minplus_then(acc, x);
+    }
+  }
+};
+
+#define MB_ATOMIC_MAX_U32(ptr, val) (*(ptr) = std::max<u32>(*(ptr), (val)))
+#define MB_ATOMIC_OR_U32(ptr, val) (*(ptr) |= (val))
+#define MB_ATOMIC_ADD_U32(ptr, val) (*(ptr) += (val))
+#define MB_ATOMIC_ADD_U64(ptr, val) (*(ptr) += (val))
+#define MB_U64_TO_F64(x) static_cast<double>(x)
+
+#endif
+
+// A region: every thread of the CTA executes the body once, then the CTA synchronises.
+#define MB_REGION(cta, tid) for (int tid = (cta).first(); tid < (cta).nt(); tid += (cta).step())
+
+}  // namespace modle_b200

@@ -1,0 +1,491 @@
+// Device half of the C ABI (include/modle_b200.h): CUDA kernels for sm_100a and their launchers.
+//
+//   k_simulate_cells      persistent CTAs; each CTA pops cells from a device-side queue and runs
+//                         the whole per-cell loop (sim_core.hpp) with the cell's LEF / barrier
+//                         state resident in shared memory. Replaces the reference worker's
+//                         simulate_one_cell (src/libmodle/cpu/simulation.cpp:896-986).
+//   k_register_contacts   the contact-register step in isolation: scatters (bin1, bin2) pairs
+//                         into the banded matrix with red.global.add.u32
+//                         (ContactMatrixDense::increment, contact_matrix_dense_safe_impl.hpp:54-89).
+//
+// There is no CPU fallback: without a CUDA device every entry point fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/modle_b200.h"
+#include "launch_prep.hpp"
+#include "sim_core.hpp"
+#include "status.hpp"
+
+namespace modle_b200 {
+
+struct LaunchArgs {
+  KernelParams kp;
+  IntervalData D;
+  Sinks K;
+  const modle_b200_cell_task* tasks;
+  modle_b200_cell_stats* stats;  // may be null
+  u32 num_cells;
+  u32* queue;       // device counter
+  u64* ring_pool;   // grid * 2W
+  u64* state_pool;  // grid * 4G
+  // optional snapshot of cell 0 (debug)
+  u64* snap_u64;  // 5 * n_lefs + 2
+  u8* snap_bar;   // n_bar
+};
+
+__global__ void __launch_bounds__(512, 1) k_simulate_cells(const __grid_constant__ LaunchArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  CellShared& S = *reinterpret_cast<CellShared*>(smem);
+  CellArrays A = carve_cell_arrays(smem + ((sizeof(CellShared) + 15) / 16) * 16, a.kp.n_lefs,
+                                   a.kp.n_bar);
+  A.rng_ring = a.ring_pool + size_t(blockIdx.x) * 2 * a.kp.rng_window;
+  A.rng_state = a.state_pool + size_t(blockIdx.x) * 4 * a.kp.rng_gen_threads;
+  __shared__ u32 s_cell;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_cell = atomicAdd(a.queue, 1u);
+    __syncthreads();
+    const u32 cell = s_cell;
+    if (cell >= a.num_cells) break;
+    const modle_b200_cell_task t = a.tasks[cell];
+    const bool has_work = a.kp.stop_on_epochs || t.num_target_contacts != 0;
+    CellTaskDev td;
+    td.cell_id = t.cell_id;
+    td.target_epochs = t.num_target_epochs;
+    td.target_contacts = t.num_target_contacts;
+    for (int i = 0; i < 4; ++i) td.rng_state[i] = t.rng_state[i];
+    if (has_work) {
+      Cta cta{&S.scratch};
+      CellSim sim{a.kp, a.D, A, S, a.K, cta, td};
+      sim.run();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && a.stats) {
+      modle_b200_cell_stats st;
+      st.num_contacts = has_work ? S.num_contacts : 0;
+      st.num_epochs = has_work ? S.epoch : 0;
+      st.num_burnin_epochs = has_work ? S.num_burnin_epochs : 0;
+      st.num_lef_updates = has_work ? S.lef_updates : 0;
+      st.num_rng_draws = has_work ? S.rng_pos : 0;
+      st.device_fault = has_work ? S.fault : 0;
+      a.stats[cell] = st;
+    }
+    if (a.snap_u64 && cell == 0 && has_work) {
+      const u32 n = a.kp.n_lefs;
+      for (u32 i = threadIdx.x; i < n; i += blockDim.x) {
+        a.snap_u64[i] = A.rev[i] == kUnbound ? ~u64(0) : u64(A.rev[i]);
+        a.snap_u64[n + i] = A.fwd[i] == kUnbound ? ~u64(0) : u64(A.fwd[i]);
+        a.snap_u64[2 * n + i] = A.ep[i] == kUnbound ? ~u64(0) : u64(A.ep[i]);
+        a.snap_u64[3 * n + i] = A.rr[i];
+        a.snap_u64[4 * n + i] = A.fr[i];
+      }
+      for (u32 i = threadIdx.x; i < a.kp.n_bar; i += blockDim.x) a.snap_bar[i] = A.bar_active[i];
+      if (threadIdx.x == 0) {
+        a.snap_u64[5 * size_t(n)] = S.num_active;
+        a.snap_u64[5 * size_t(n) + 1] = S.burnin_completed;
+      }
+    }
+  }
+}
+
+// Contact register: one (bin1, bin2) pair per thread, grid-stride. Out-of-band pairs are counted
+// once per warp (warp-aggregated) into *missed.
+__global__ void __launch_bounds__(256) k_register_contacts(const u32* __restrict__ bin1,
+                                                           const u32* __restrict__ bin2, size_t n,
+                                                           u32 nrows, u32* __restrict__ band,
+                                                           u64* __restrict__ missed) {
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  u32 my_missed = 0;
+  for (size_t e = size_t(blockIdx.x) * blockDim.x + threadIdx.x; e < n; e += stride) {
+    const u32 b1 = __ldcs(bin1 + e), b2 = __ldcs(bin2 + e);
+    const u32 i = b1 > b2 ? b1 - b2 : b2 - b1;
+    const u32 j = b1 > b2 ? b1 : b2;
+    if (i >= nrows) {
+      ++my_missed;
+    } else {
+      atomicAdd(band + (size_t(j) * nrows + i), 1u);  // result unused -> RED.E.ADD
+    }
+  }
+  const u32 warp_missed = __reduce_add_sync(0xffffffffu, my_missed);
+  if ((threadIdx.x & 31) == 0 && warp_missed)
+    atomicAdd(reinterpret_cast<unsigned long long*>(missed),
+              static_cast<unsigned long long>(warp_missed));
+}
+
+}  // namespace modle_b200
+
+using namespace modle_b200;
+
+namespace {
+
+#define CUDA_TRY(expr)                                                                   \
+  do {                                                                                   \
+    const cudaError_t e_ = (expr);                                                       \
+    if (e_ != cudaSuccess)                                                               \
+      return modle_b200::fail(MODLE_B200_ERR_CUDA,                                       \
+                              std::string(#expr) + ": " + cudaGetErrorString(e_));       \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    const cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+};
+
+}  // namespace
+
+struct modle_b200_context {
+  int device = 0;
+  int num_sms = 0;
+  size_t max_smem_optin = 0;
+  cudaStream_t stream = nullptr;
+  bool jump_uploaded[kJumpSlots] = {false, false};
+  ZigguratTables zig;
+  DevBuf d_zig;                                    // nx, ny, ex, ey
+  DevBuf d_args, d_queue, d_rings, d_states;       // launch scratch
+  DevBuf d_bar_pos, d_bar_dir, d_stp_a, d_stp_i, d_occ;  // per-interval arrays
+  DevBuf d_barriers, d_tasks, d_band, d_occ1d, d_stats, d_missed, d_snap_u64, d_snap_bar;
+  uint64_t launches = 0;
+};
+
+extern "C" {
+
+int modle_b200_init(modle_b200_context** out, int device) {
+  if (!out) return fail(MODLE_B200_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  *out = nullptr;
+  int count = 0;
+  const cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(MODLE_B200_ERR_NO_DEVICE,
+                std::string("no CUDA device available (modle_b200 has no CPU fallback): ") +
+                    cudaGetErrorString(e));
+  if (device < 0 || device >= count)
+    return fail(MODLE_B200_ERR_INVALID_ARGUMENT, "device index out of range");
+  CUDA_TRY(cudaSetDevice(device));
+  auto* ctx = new modle_b200_context();
+  ctx->device = device;
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  ctx->num_sms = prop.multiProcessorCount;
+  ctx->max_smem_optin = prop.sharedMemPerBlockOptin;
+  CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CUDA_TRY(ctx->d_zig.reserve(sizeof(double) * (129 * 2 + 257 * 2)));
+  double* z = static_cast<double*>(ctx->d_zig.p);
+  CUDA_TRY(cudaMemcpy(z, ctx->zig.nx, sizeof(double) * 129, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(z + 129, ctx->zig.ny, sizeof(double) * 129, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(z + 258, ctx->zig.ex, sizeof(double) * 257, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(z + 515, ctx->zig.ey, sizeof(double) * 257, cudaMemcpyHostToDevice));
+  *out = ctx;
+  return MODLE_B200_OK;
+}
+
+void modle_b200_destroy(modle_b200_context* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+uint64_t modle_b200_kernel_launches(const modle_b200_context* ctx) {
+  return ctx ? ctx->launches : 0;
+}
+
+int modle_b200_synchronize(modle_b200_context* ctx) {
+  if (!ctx) return fail(MODLE_B200_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return MODLE_B200_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+// Shared implementation of the two simulate entry points. All pointers are device pointers.
+int launch_simulate(modle_b200_context* ctx, const modle_b200_sim_params* params,
+                    const modle_b200_interval* interval, const modle_b200_barrier* h_barriers,
+                    size_t num_barriers, const modle_b200_cell_task* d_tasks, size_t num_cells,
+                    u32* d_band, u64* d_occ1d, modle_b200_cell_stats* d_stats, u64* d_missed,
+                    cudaStream_t stream, u64* d_snap_u64, u8* d_snap_bar) {
+  const StagingConfig sc =
+      pick_staging(static_cast<u32>(interval->num_lefs), static_cast<u32>(num_barriers));
+  KernelParams kp;
+  IntervalHostData hd;
+  const std::string err =
+      prepare_interval(*params, *interval, h_barriers, num_barriers, sc, &kp, &hd);
+  if (!err.empty()) return fail(MODLE_B200_ERR_UNSUPPORTED, err);
+  const size_t smem = ((sizeof(CellShared) + 15) / 16) * 16 + cell_array_bytes(kp.n_lefs, kp.n_bar);
+  if (smem > ctx->max_smem_optin)
+    return fail(MODLE_B200_ERR_UNSUPPORTED,
+                "interval needs " + std::to_string(smem) +
+                    " bytes of shared memory per cell; the device offers " +
+                    std::to_string(ctx->max_smem_optin));
+  if (num_cells == 0) return MODLE_B200_OK;
+  if (num_cells > 0x7FFFFFFFull) return fail(MODLE_B200_ERR_INVALID_ARGUMENT, "too many cells");
+
+  if (!ctx->jump_uploaded[sc.jump_slot]) {
+    std::vector<u64> table(1024);
+    build_jump_table(sc.window, table.data());
+    CUDA_TRY(cudaMemcpyToSymbol(c_jump, table.data(), sizeof(u64) * 1024,
+                                sizeof(u64) * 1024 * sc.jump_slot, cudaMemcpyHostToDevice));
+    ctx->jump_uploaded[sc.jump_slot] = true;
+  }
+  // per-interval arrays (pageable host -> device; small)
+  const size_t nb = num_barriers;
+  CUDA_TRY(ctx->d_bar_pos.reserve(sizeof(u32) * (nb + 1)));
+  CUDA_TRY(ctx->d_bar_dir.reserve(sizeof(u32) * hd.bar_dir_rev.size()));
+  CUDA_TRY(ctx->d_stp_a.reserve(sizeof(double) * (nb + 1)));
+  CUDA_TRY(ctx->d_stp_i.reserve(sizeof(double) * (nb + 1)));
+  CUDA_TRY(ctx->d_occ.reserve(sizeof(double) * (nb + 1)));
+  // the previous launch on this context may still read these buffers
+  CUDA_TRY(cudaStreamSynchronize(stream));
+  if (stream != ctx->stream) CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  if (nb) {
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_bar_pos.p, hd.bar_pos.data(), sizeof(u32) * nb,
+                             cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_stp_a.p, hd.stp_active.data(), sizeof(double) * nb,
+                             cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_stp_i.p, hd.stp_inactive.data(), sizeof(double) * nb,
+                             cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_occ.p, hd.occupancy.data(), sizeof(double) * nb,
+                             cudaMemcpyHostToDevice, stream));
+  }
+  CUDA_TRY(cudaMemcpyAsync(ctx->d_bar_dir.p, hd.bar_dir_rev.data(),
+                           sizeof(u32) * hd.bar_dir_rev.size(), cudaMemcpyHostToDevice, stream));
+
+  // grid: persistent CTAs, as many as fit
+  CUDA_TRY(cudaFuncSetAttribute(k_simulate_cells, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(smem)));
+  int per_sm = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_simulate_cells,
+                                                         static_cast<int>(sc.cta_threads), smem));
+  if (per_sm < 1) return fail(MODLE_B200_ERR_UNSUPPORTED, "kernel does not fit on an SM");
+  const u32 grid = static_cast<u32>(
+      std::min<size_t>(num_cells, size_t(per_sm) * static_cast<size_t>(ctx->num_sms)));
+  CUDA_TRY(ctx->d_rings.reserve(sizeof(u64) * 2 * size_t(sc.window) * grid));
+  CUDA_TRY(ctx->d_states.reserve(sizeof(u64) * 4 * size_t(sc.gen_threads) * grid));
+  CUDA_TRY(ctx->d_queue.reserve(sizeof(u32) * 4));
+  CUDA_TRY(cudaMemsetAsync(ctx->d_queue.p, 0, sizeof(u32) * 4, stream));
+
+  LaunchArgs a;
+  a.kp = kp;
+  const double* z = static_cast<const double*>(ctx->d_zig.p);
+  a.D.bar_pos = static_cast<const u32*>(ctx->d_bar_pos.p);
+  a.D.bar_dir_rev = static_cast<const u32*>(ctx->d_bar_dir.p);
+  a.D.bar_stp_active = static_cast<const double*>(ctx->d_stp_a.p);
+  a.D.bar_stp_inactive = static_cast<const double*>(ctx->d_stp_i.p);
+  a.D.bar_occupancy = static_cast<const double*>(ctx->d_occ.p);
+  a.D.zig_nx = z;
+  a.D.zig_ny = z + 129;
+  a.D.zig_ex = z + 258;
+  a.D.zig_ey = z + 515;
+  a.K.band = d_band;
+  a.K.occ1d = kp.track_1d ? d_occ1d : nullptr;
+  a.K.missed = d_missed;
+  a.tasks = d_tasks;
+  a.stats = d_stats;
+  a.num_cells = static_cast<u32>(num_cells);
+  a.queue = static_cast<u32*>(ctx->d_queue.p);
+  a.ring_pool = static_cast<u64*>(ctx->d_rings.p);
+  a.state_pool = static_cast<u64*>(ctx->d_states.p);
+  a.snap_u64 = d_snap_u64;
+  a.snap_bar = d_snap_bar;
+  k_simulate_cells<<<grid, sc.cta_threads, smem, stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  ++ctx->launches;
+  return MODLE_B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int modle_b200_simulate_interval_device(modle_b200_context* ctx,
+                                        const modle_b200_sim_params* params,
+                                        const modle_b200_interval* interval,
+                                        const modle_b200_barrier* barriers_host_or_dev,
+                                        size_t num_barriers, const modle_b200_cell_task* d_tasks,
+                                        size_t num_cells, uint32_t* d_band, uint64_t* d_occ1d,
+                                        modle_b200_cell_stats* d_stats, uint64_t* d_missed_updates,
+                                        void* cuda_stream) {
+  if (!ctx || !params || !interval || !d_tasks || !d_band || !d_missed_updates)
+    return fail(MODLE_B200_ERR_INVALID_ARGUMENT, "NULL argument");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  cudaStream_t stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
+  // barriers may live on either side: stage a host copy (the launcher validates and repacks them)
+  std::vector<modle_b200_barrier> hb(num_barriers);
+  if (num_barriers) {
+    cudaPointerAttributes attr;
+    const cudaError_t e = cudaPointerGetAttributes(&attr, barriers_host_or_dev);
+    if (e == cudaSuccess && attr.type == cudaMemoryTypeDevice) {
+      CUDA_TRY(cudaMemcpy(hb.data(), barriers_host_or_dev,
+                          sizeof(modle_b200_barrier) * num_barriers, cudaMemcpyDeviceToHost));
+    } else {
+      cudaGetLastError();
+      std::memcpy(hb.data(), barriers_host_or_dev, sizeof(modle_b200_barrier) * num_barriers);
+    }
+  }
+  return launch_simulate(ctx, params, interval, hb.data(), num_barriers, d_tasks, num_cells, d_band,
+                         d_occ1d, d_stats, d_missed_updates, stream, nullptr, nullptr);
+}
+
+int modle_b200_simulate_interval(modle_b200_context* ctx, const modle_b200_sim_params* params,
+                                 const modle_b200_interval* interval,
+                                 const modle_b200_barrier* barriers, size_t num_barriers,
+                                 const modle_b200_cell_task* tasks, size_t num_cells,
+                                 uint32_t* band_out, uint64_t* occ1d_out,
+                                 modle_b200_cell_stats* stats_out, uint64_t* missed_updates_out) {
+  if (!ctx || !params || !interval || !tasks || !band_out)
+    return fail(MODLE_B200_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (num_barriers && !barriers) return fail(MODLE_B200_ERR_INVALID_ARGUMENT, "barriers is NULL");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  u64 nrows = 0, ncols = 0;
+  modle_b200_band_shape(params, interval->end - interval->start, &nrows, &ncols);
+  const size_t npx = nrows * ncols + 1;
+  cudaStream_t s = ctx->stream;
+  CUDA_TRY(ctx->d_tasks.reserve(sizeof(modle_b200_cell_task) * std::max<size_t>(num_cells, 1)));
+  CUDA_TRY(ctx->d_band.reserve(sizeof(u32) * npx));
+  CUDA_TRY(ctx->d_occ1d.reserve(sizeof(u64) * std::max<u64>(ncols, 1)));
+  CUDA_TRY(ctx->d_stats.reserve(sizeof(modle_b200_cell_stats) * std::max<size_t>(num_cells, 1)));
+  CUDA_TRY(ctx->d_missed.reserve(sizeof(u64)));
+  CUDA_TRY(cudaMemcpyAsync(ctx->d_tasks.p, tasks, sizeof(modle_b200_cell_task) * num_cells,
+                           cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemsetAsync(ctx->d_band.p, 0, sizeof(u32) * npx, s));
+  CUDA_TRY(cudaMemsetAsync(ctx->d_occ1d.p, 0, sizeof(u64) * std::max<u64>(ncols, 1), s));
+  CUDA_TRY(cudaMemsetAsync(ctx->d_stats.p, 0,
+                           sizeof(modle_b200_cell_stats) * std::max<size_t>(num_cells, 1), s));
+  CUDA_TRY(cudaMemsetAsync(ctx->d_missed.p, 0, sizeof(u64), s));
+  const int rc = launch_simulate(
+      ctx, params, interval, barriers, num_barriers,
+      static_cast<const modle_b200_cell_task*>(ctx->d_tasks.p), num_cells,
+      static_cast<u32*>(ctx->d_band.p), static_cast<u64*>(ctx->d_occ1d.p),
+      static_cast<modle_b200_cell_stats*>(ctx->d_stats.p), static_cast<u64*>(ctx->d_missed.p), s,
+      nullptr, nullptr);
+  if (rc != MODLE_B200_OK) return rc;
+  // results are ADDED to the caller's buffers (the reference accumulates into a shared matrix)
+  std::vector<u32> h_band(npx);
+  std::vector<u64> h_occ(ncols);
+  std::vector<modle_b200_cell_stats> h_stats(num_cells);
+  u64 h_missed = 0;
+  CUDA_TRY(cudaMemcpyAsync(h_band.data(), ctx->d_band.p, sizeof(u32) * npx, cudaMemcpyDeviceToHost, s));
+  if (occ1d_out)
+    CUDA_TRY(cudaMemcpyAsync(h_occ.data(), ctx->d_occ1d.p, sizeof(u64) * ncols,
+                             cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(h_stats.data(), ctx->d_stats.p,
+                           sizeof(modle_b200_cell_stats) * num_cells, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(&h_missed, ctx->d_missed.p, sizeof(u64), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  for (size_t i = 0; i < npx; ++i) band_out[i] += h_band[i];
+  if (occ1d_out)
+    for (size_t i = 0; i < ncols; ++i) occ1d_out[i] += h_occ[i];
+  if (missed_updates_out) *missed_updates_out += h_missed;
+  u64 first_fault = 0;
+  for (size_t i = 0; i < num_cells; ++i) {
+    if (stats_out) stats_out[i] = h_stats[i];
+    if (!first_fault && h_stats[i].device_fault) first_fault = h_stats[i].device_fault;
+  }
+  if (first_fault)
+    return fail(MODLE_B200_ERR_DEVICE_FAULT,
+                "kernel reported fault code " + std::to_string(first_fault));
+  return MODLE_B200_OK;
+}
+
+int modle_b200_snapshot_cell(modle_b200_context* ctx, const modle_b200_sim_params* params,
+                             const modle_b200_interval* interval,
+                             const modle_b200_barrier* barriers, size_t num_barriers,
+                             const modle_b200_cell_task* task, modle_b200_cell_snapshot* snapshot,
+                             modle_b200_cell_stats* stats_out) {
+  if (!ctx || !params || !interval || !task || !snapshot)
+    return fail(MODLE_B200_ERR_INVALID_ARGUMENT, "NULL argument");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  u64 nrows = 0, ncols = 0;
+  modle_b200_band_shape(params, interval->end - interval->start, &nrows, &ncols);
+  const size_t npx = nrows * ncols + 1;
+  const size_t n = interval->num_lefs;
+  cudaStream_t s = ctx->stream;
+  CUDA_TRY(ctx->d_tasks.reserve(sizeof(modle_b200_cell_task)));
+  CUDA_TRY(ctx->d_band.reserve(sizeof(u32) * npx));
+  CUDA_TRY(ctx->d_occ1d.reserve(sizeof(u64) * std::max<u64>(ncols, 1)));
+  CUDA_TRY(ctx->d_stats.reserve(sizeof(modle_b200_cell_stats)));
+  CUDA_TRY(ctx->d_missed.reserve(sizeof(u64)));
+  CUDA_TRY(ctx->d_snap_u64.reserve(sizeof(u64) * (5 * n + 2)));
+  CUDA_TRY(ctx->d_snap_bar.reserve(num_barriers + 1));
+  modle_b200_cell_task t0 = *task;
+  CUDA_TRY(cudaMemcpyAsync(ctx->d_tasks.p, &t0, sizeof(t0), cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemsetAsync(ctx->d_band.p, 0, sizeof(u32) * npx, s));
+  CUDA_TRY(cudaMemsetAsync(ctx->d_occ1d.p, 0, sizeof(u64) * std::max<u64>(ncols, 1), s));
+  CUDA_TRY(cudaMemsetAsync(ctx->d_stats.p, 0, sizeof(modle_b200_cell_stats), s));
+  CUDA_TRY(cudaMemsetAsync(ctx->d_missed.p, 0, sizeof(u64), s));
+  CUDA_TRY(cudaMemsetAsync(ctx->d_snap_u64.p, 0xFF, sizeof(u64) * (5 * n + 2), s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  const int rc = launch_simulate(
+      ctx, params, interval, barriers, num_barriers,
+      static_cast<const modle_b200_cell_task*>(ctx->d_tasks.p), 1, static_cast<u32*>(ctx->d_band.p),
+      static_cast<u64*>(ctx->d_occ1d.p), static_cast<modle_b200_cell_stats*>(ctx->d_stats.p),
+      static_cast<u64*>(ctx->d_missed.p), s, static_cast<u64*>(ctx->d_snap_u64.p),
+      static_cast<u8*>(ctx->d_snap_bar.p));
+  if (rc != MODLE_B200_OK) return rc;
+  std::vector<u64> h(5 * n + 2);
+  modle_b200_cell_stats st{};
+  CUDA_TRY(cudaMemcpyAsync(h.data(), ctx->d_snap_u64.p, sizeof(u64) * h.size(),
+                           cudaMemcpyDeviceToHost, s));
+  if (num_barriers)
+    CUDA_TRY(cudaMemcpyAsync(snapshot->barrier_active, ctx->d_snap_bar.p, num_barriers,
+                             cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(&st, ctx->d_stats.p, sizeof(st), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  for (size_t i = 0; i < n; ++i) {
+    snapshot->rev_pos[i] = h[i];
+    snapshot->fwd_pos[i] = h[n + i];
+    snapshot->binding_epoch[i] = h[2 * n + i];
+    snapshot->rev_ranks[i] = h[3 * n + i];
+    snapshot->fwd_ranks[i] = h[4 * n + i];
+  }
+  snapshot->num_active_lefs = h[5 * n];
+  snapshot->burnin_completed = h[5 * n + 1];
+  if (stats_out) *stats_out = st;
+  if (st.device_fault)
+    return fail(MODLE_B200_ERR_DEVICE_FAULT,
+                "kernel reported fault code " + std::to_string(st.device_fault));
+  return MODLE_B200_OK;
+}
+
+int modle_b200_register_contacts_device(modle_b200_context* ctx, const uint32_t* d_bin1,
+                                        const uint32_t* d_bin2, size_t n, uint64_t nrows,
+                                        uint64_t ncols, uint32_t* d_band,
+                                        uint64_t* d_missed_updates, void* cuda_stream) {
+  if (!ctx || !d_bin1 || !d_bin2 || !d_band || !d_missed_updates)
+    return fail(MODLE_B200_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (nrows == 0 || nrows * ncols + 1 >= (u64(1) << 32))
+    return fail(MODLE_B200_ERR_UNSUPPORTED, "band matrix too large for 32-bit pixel index");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  cudaStream_t stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
+  if (n == 0) return MODLE_B200_OK;
+  const int threads = 256;
+  const size_t want = (n + threads - 1) / threads;
+  const u32 grid = static_cast<u32>(std::min<size_t>(want, size_t(ctx->num_sms) * 8));
+  k_register_contacts<<<grid, threads, 0, stream>>>(d_bin1, d_bin2, n, static_cast<u32>(nrows),
+                                                    d_band, d_missed_updates);
+  CUDA_TRY(cudaGetLastError());
+  ++ctx->launches;
+  return MODLE_B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,173 @@
+// Host-side preparation of one interval launch: translates the C-ABI structs into the kernel's
+// KernelParams / per-interval arrays, builds the ziggurat tables and the RNG jump matrices.
+// Pure host code (no CUDA calls) so that the CPU emulation of the kernel can reuse it.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/modle_b200.h"
+#include "host_rng.hpp"
+#include "sim_types.hpp"
+
+namespace modle_b200 {
+
+// Ziggurat tables of Boost.Random's unit normal (128 layers) and unit exponential (256 layers)
+// distributions, rebuilt from the standard construction (boost/random/normal_distribution.hpp
+// and exponential_distribution.hpp hold them as literals; those headers are not available here,
+// see DESIGN.md "third-party arithmetic").
+struct ZigguratTables {
+  double nx[129], ny[129], ex[257], ey[257];
+  ZigguratTables() {
+    {
+      const long double r = 3.442619855899L, v = 9.91256303526217e-3L;
+      long double x[129];
+      x[0] = v / std::exp(-0.5L * r * r);
+      x[1] = r;
+      for (int i = 2; i < 128; ++i)
+        x[i] = std::sqrt(-2.0L * std::log(v / x[i - 1] + std::exp(-0.5L * x[i - 1] * x[i - 1])));
+      x[128] = 0.0L;
+      for (int i = 0; i <= 128; ++i) {
+        nx[i] = static_cast<double>(x[i]);
+        ny[i] = static_cast<double>(std::exp(-0.5L * x[i] * x[i]));
+      }
+      ny[0] = 0.0;
+      ny[128] = 1.0;
+    }
+    {
+      const long double r = 7.69711747013104972L, v = 3.949659822581572e-3L;
+      long double x[257];
+      x[0] = v / std::exp(-r);
+      x[1] = r;
+      for (int i = 2; i < 256; ++i) x[i] = -std::log(v / x[i - 1] + std::exp(-x[i - 1]));
+      x[256] = 0.0L;
+      for (int i = 0; i <= 256; ++i) {
+        ex[i] = static_cast<double>(x[i]);
+        ey[i] = static_cast<double>(std::exp(-x[i]));
+      }
+      ey[0] = 0.0;
+      ey[256] = 1.0;
+    }
+  }
+};
+
+// RNG staging configurations: (CTA threads, generator threads G, draws per generator per window l).
+struct StagingConfig {
+  u32 cta_threads, gen_threads, per_thread, window, jump_slot;
+};
+inline StagingConfig staging_large() { return StagingConfig{512, 512, 64, 512 * 64, 0}; }
+inline StagingConfig staging_small() { return StagingConfig{256, 64, 128, 64 * 128, 1}; }
+
+// Flattens T^window into the [256 columns][4 words] layout of c_jump.
+inline void build_jump_table(u32 window, u64* out /*1024*/) {
+  const host::StateMatrix m = host::StateMatrix::power(window);
+  for (int j = 0; j < 256; ++j)
+    for (int w = 0; w < 4; ++w) out[j * 4 + w] = m.col[j][w];
+}
+
+struct IntervalHostData {
+  std::vector<u32> bar_pos, bar_dir_rev;
+  std::vector<double> stp_active, stp_inactive, occupancy;
+};
+
+// Returns an empty string on success, else the reason the launch is not possible.
+inline std::string prepare_interval(const modle_b200_sim_params& p, const modle_b200_interval& iv,
+                                    const modle_b200_barrier* bars, size_t nb,
+                                    const StagingConfig& sc, KernelParams* kp,
+                                    IntervalHostData* hd) {
+  if (iv.end <= iv.start) return "empty interval";
+  if (iv.end >= 0xFFFFFFF0ull) return "interval end does not fit 32-bit device coordinates";
+  if (iv.num_lefs == 0 || iv.num_lefs >= 65535) return "num_lefs must be in [1, 65534]";
+  if (nb >= (1u << 24)) return "too many barriers";
+  if (p.bin_size == 0 || p.bin_size > 0xFFFFFFFFull) return "invalid bin_size";
+  if (p.burnin_history_length > kMaxBurninHistory ||
+      p.burnin_smoothing_window_size + 1 >= p.burnin_history_length)
+    return "burn-in history/window outside the supported range";
+  if (p.burnin_target_epochs_for_lef_activation == 0) return "burnin activation epochs is 0";
+  KernelParams k;
+  std::memset(&k, 0, sizeof(k));
+  k.start = static_cast<u32>(iv.start);
+  k.end = static_cast<u32>(iv.end);
+  k.n_lefs = static_cast<u32>(iv.num_lefs);
+  k.n_bar = static_cast<u32>(nb);
+  k.bin_size = static_cast<u32>(p.bin_size);
+  u64 nrows = 0, ncols = 0;
+  modle_b200_band_shape(&p, iv.end - iv.start, &nrows, &ncols);
+  if (nrows * ncols + 1 >= (u64(1) << 32)) return "band matrix too large for 32-bit pixel index";
+  k.nrows = static_cast<u32>(nrows);
+  k.ncols = static_cast<u32>(ncols);
+  k.rev_speed = static_cast<double>(p.rev_extrusion_speed);
+  k.fwd_speed = static_cast<double>(p.fwd_extrusion_speed);
+  k.rev_speed_burnin = static_cast<double>(p.rev_extrusion_speed_burnin);
+  k.fwd_speed_burnin = static_cast<double>(p.fwd_extrusion_speed_burnin);
+  k.rev_std = p.rev_extrusion_speed_std;
+  k.fwd_std = p.fwd_extrusion_speed_std;
+  k.p_release = p.prob_of_lef_release;
+  k.p_release_burnin = p.prob_of_lef_release_burnin;
+  k.hard_mult = p.hard_stall_lef_stability_multiplier;
+  k.soft_mult = p.soft_stall_lef_stability_multiplier;
+  k.p_bypass = p.probability_of_extrusion_unit_bypass;
+  k.pblock_major = p.lef_bar_major_collision_pblock;
+  k.pblock_minor = p.lef_bar_minor_collision_pblock;
+  k.tad_to_loop = p.tad_to_loop_contact_ratio;
+  k.gev_mu = p.genextreme_mu;
+  k.gev_sigma = p.genextreme_sigma;
+  k.gev_xi = p.genextreme_xi;
+  k.noisify = (p.contact_sampling_strategy & MODLE_B200_SAMPLE_NOISIFY) ? 1 : 0;
+  k.track_1d = p.track_1d_lef_position ? 1 : 0;
+  k.skip_burnin = p.skip_burnin ? 1 : 0;
+  k.stop_on_epochs = p.stopping_criterion == MODLE_B200_STOP_SIMULATION_EPOCHS ? 1 : 0;
+  const u64 cpe = modle_b200_compute_contacts_per_epoch(&p, iv.num_lefs);
+  if (cpe > 0x7FFFFFFFull) return "contacts per epoch too large";
+  k.contacts_per_epoch = static_cast<u32>(cpe);
+  k.burnin_history = static_cast<u32>(p.burnin_history_length);
+  k.burnin_window = static_cast<u32>(p.burnin_smoothing_window_size);
+  k.min_burnin_epochs = p.min_burnin_epochs;
+  k.max_burnin_epochs = p.max_burnin_epochs;
+  // simulate_one_cell, simulation.cpp:906-908
+  k.lef_binding_rate_burnin = static_cast<double>(iv.num_lefs) /
+                              static_cast<double>(p.burnin_target_epochs_for_lef_activation);
+  k.debug_max_epochs = p.debug_max_epochs;
+  k.rng_gen_threads = sc.gen_threads;
+  k.rng_per_thread = sc.per_thread;
+  k.rng_window = sc.window;
+  k.rng_jump_slot = sc.jump_slot;
+  // every phase must fit one staging window (largest consumer: 2 x the normal draws of a pass)
+  const u64 worst = u64(iv.num_lefs) + iv.num_lefs / 8 + 512;
+  if (worst > sc.window || nb + 64 > sc.window) return "interval too large for the RNG staging window";
+
+  hd->bar_pos.resize(nb);
+  hd->bar_dir_rev.assign((nb + 31) / 32 + 1, 0);
+  hd->stp_active.resize(nb);
+  hd->stp_inactive.resize(nb);
+  hd->occupancy.resize(nb);
+  for (size_t i = 0; i < nb; ++i) {
+    if (bars[i].pos < iv.start || bars[i].pos >= iv.end) return "barrier outside the interval";
+    if (i && bars[i].pos < bars[i - 1].pos) return "barriers are not sorted by position";
+    if (bars[i].blocking_direction != MODLE_B200_DIR_REV &&
+        bars[i].blocking_direction != MODLE_B200_DIR_FWD)
+      return "invalid barrier blocking direction";
+    hd->bar_pos[i] = static_cast<u32>(bars[i].pos);
+    if (bars[i].blocking_direction == MODLE_B200_DIR_REV)
+      hd->bar_dir_rev[i >> 5] |= 1u << (i & 31);
+    hd->stp_active[i] = bars[i].stp_active;
+    hd->stp_inactive[i] = bars[i].stp_inactive;
+    // ExtrusionBarriers::occupancy (extrusion_barriers.cpp:140-143)
+    hd->occupancy[i] = modle_b200_occupancy_from_stp(bars[i].stp_active, bars[i].stp_inactive);
+  }
+  *kp = k;
+  return std::string();
+}
+
+inline StagingConfig pick_staging(u32 n_lefs, u32 n_bar) {
+  // small intervals: several CTAs per SM, few generator threads each; large: one fat CTA per SM
+  const size_t bytes = cell_array_bytes(n_lefs, n_bar) + sizeof(CellShared);
+  const StagingConfig s = staging_small();
+  const u64 worst = u64(n_lefs) + n_lefs / 8 + 512;
+  if (bytes <= 100 * 1024 && worst <= s.window && u64(n_bar) + 64 <= s.window) return s;
+  return staging_large();
+}
+
+}  // namespace modle_b200

@@ -1,0 +1,1974 @@
+// Per-cell loop-extrusion simulation, one CTA per cell, state resident in shared memory.
+//
+// Data-parallel restatement of Simulation::simulate_one_cell
+// (reference: src/libmodle/cpu/simulation.cpp:896-986) and of everything it calls, preserving the
+// reference's sequential RNG draw order (one xoshiro256++ stream per cell). Written in the
+// bulk-synchronous style of cta.hpp so that the CUDA kernel and the CPU emulation used by the
+// tests compile from this one source. Each phase cites the reference routine it replaces.
+#pragma once
+#include "sim_types.hpp"
+
+namespace modle_b200 {
+
+// ---- jump-ahead matrices T^W (256 columns x 4 words), one slot per staging configuration -------
+constexpr int kJumpSlots = 2;
+#if MB_DEVICE_BUILD
+__constant__ u64 c_jump[kJumpSlots][1024];
+#define MB_JUMP(slot, idx) c_jump[slot][idx]
+#define MB_LDCG_U64(p) __ldcg(p)
+#define MB_ATOMIC_MIN_U32(ptr, val) atomicMin((ptr), (val))
+#else
+extern u64 g_emu_jump[kJumpSlots][1024];
+#define MB_JUMP(slot, idx) g_emu_jump[slot][idx]
+#define MB_LDCG_U64(p) (*(p))
+#define MB_ATOMIC_MIN_U32(ptr, val) (*(ptr) = std::min<u32>(*(ptr), (val)))
+#endif
+
+constexpr double kTwo64 = 18446744073709551616.0;
+#if !MB_DEVICE_BUILD
+using std::isfinite;
+#endif
+
+struct Xs {
+  u64 s0, s1, s2, s3;
+};
+MB_FN u64 rotl64(u64 x, int k) { return (x << k) | (x >> (64 - k)); }
+MB_FN u64 xs_next(Xs& g) {
+  const u64 r = rotl64(g.s0 + g.s3, 23) + g.s0;
+  const u64 t = g.s1 << 17;
+  g.s2 ^= g.s0;
+  g.s3 ^= g.s1;
+  g.s1 ^= g.s2;
+  g.s0 ^= g.s3;
+  g.s2 ^= t;
+  g.s3 = rotl64(g.s3, 45);
+  return r;
+}
+// g <- T^W g : 256 masked XORs of matrix columns
+MB_FN Xs xs_jump(const Xs& g, int slot) {
+  Xs r{0, 0, 0, 0};
+  const u64 w[4] = {g.s0, g.s1, g.s2, g.s3};
+#pragma unroll 1
+  for (int wi = 0; wi < 4; ++wi) {
+    const u64 word = w[wi];
+#pragma unroll 4
+    for (int b = 0; b < 64; ++b) {
+      const u64 m = u64(0) - ((word >> b) & 1);
+      const int c = (wi * 64 + b) * 4;
+      r.s0 ^= MB_JUMP(slot, c + 0) & m;
+      r.s1 ^= MB_JUMP(slot, c + 1) & m;
+      r.s2 ^= MB_JUMP(slot, c + 2) & m;
+      r.s3 ^= MB_JUMP(slot, c + 3) & m;
+    }
+  }
+  return r;
+}
+
+// ---- elementary Boost.Random pieces on a raw 64-bit draw (see oracle/oracle_rng.hpp notes) ------
+MB_FN bool bernoulli_raw(u64 u, double p) { return MB_U64_TO_F64(u) <= p * kTwo64; }
+MB_FN double canonical_raw(u64 u) {
+  double r = MB_U64_TO_F64(u) / kTwo64;
+  if (r == 1.0) r -= 2.220446049250313e-16 / 2;
+  return r;
+}
+MB_FN u64 uniform_int_bucket(u64 range) {
+  const u64 brange = ~u64(0);
+  u64 bucket = brange / (range + 1);
+  if (brange % (range + 1) == range) ++bucket;
+  return bucket;
+}
+// detail::generate_int_float_pair<double, 8>
+MB_FN double int_float_pair8(u64 u, int* bucket) {
+  *bucket = static_cast<int>(u & 0xFF);
+  u &= ~((u64(1) << 11) - 1);
+  return MB_U64_TO_F64(u >> 8) * (1.0 / 72057594037927936.0);
+}
+// genextreme_value_distribution (common/genextreme_value_distribution.hpp:87-105) on a canonical u
+MB_FN double gev_from_canonical(double u, double mu, double sigma, double xi) {
+  if (xi == 0.0) return (mu - sigma) * log(-log(u));
+  return mu + (sigma * (1.0 - pow(-log(u), xi))) / xi;
+}
+
+// The per-cell simulator. All member functions are CTA-collective unless noted.
+struct CellSim {
+  const KernelParams& P;
+  const IntervalData& D;
+  CellArrays A;
+  CellShared& S;
+  Sinks K;
+  Cta cta;
+  CellTaskDev task;
+
+  // ------------------------------------------------------------------------------ helpers
+  MB_FN void chunk(int tid, u32 n, u32* lo, u32* hi) const {
+    const u64 nt = static_cast<u64>(cta.nt());
+    *lo = static_cast<u32>(static_cast<u64>(n) * static_cast<u64>(tid) / nt);
+    *hi = static_cast<u32>(static_cast<u64>(n) * (static_cast<u64>(tid) + 1) / nt);
+  }
+  MB_FN void fault(u32 code) const {
+    if (S.fault == 0) S.fault = code;  // benign race: any code is reported
+  }
+  MB_FN u64 raw(u64 off) const { return MB_LDCG_U64(A.rng_ring + (off & (2 * u64(P.rng_window) - 1))); }
+
+  // A serial reader of the raw stream used by the few inherently sequential samplers.
+  struct Cursor {
+    const CellSim* sim;
+    u64 pos, limit;
+    bool overrun;
+    MB_FN u64 next() {
+      if (pos >= limit) {
+        overrun = true;
+        return 0;
+      }
+      return sim->raw(pos++);
+    }
+    MB_FN double uniform01() {  // boost::random::uniform_01<double>
+      for (;;) {
+        const double r = MB_U64_TO_F64(next()) * (1.0 / kTwo64);
+        if (r < 1.0 || overrun) return r;
+      }
+    }
+  };
+  MB_FN Cursor cursor(u64 pos, u64 limit) const { return Cursor{this, pos, limit, false}; }
+
+  // ------------------------------------------------------------------------------ RNG staging
+  // Makes raw(o) valid for every o in [S.rng_pos, need_end). The stream is produced window by
+  // window (W draws): generator thread g owns the l consecutive draws [g*l, (g+1)*l) of each
+  // window and hops to the next window with a precomputed GF(2) matrix (T^W).
+  MB_FN void rng_ensure(u64 need_end) {
+    if (need_end > S.rng_pos + P.rng_window) {
+      MB_REGION(cta, tid) {
+        if (cta.leader(tid)) fault(kFaultRngWindow);
+      }
+      cta.sync();
+      return;
+    }
+    while (S.rng_generated < need_end) {
+      const u64 wbase = S.rng_generated;
+      cta.sync();
+      MB_REGION(cta, tid) {
+        const u32 G = P.rng_gen_threads;
+        for (u32 gi = static_cast<u32>(tid); gi < G; gi += static_cast<u32>(cta.nt())) {
+          Xs g{A.rng_state[gi], A.rng_state[G + gi], A.rng_state[2 * G + gi],
+               A.rng_state[3 * G + gi]};
+          const Xs nxt = xs_jump(g, static_cast<int>(P.rng_jump_slot));
+          const u64 mask = 2 * u64(P.rng_window) - 1;
+          const u64 o0 = wbase + u64(gi) * P.rng_per_thread;
+          for (u32 i = 0; i < P.rng_per_thread; i += 2) {
+            const u64 a = xs_next(g);
+            const u64 b = xs_next(g);
+            u64* dst = A.rng_ring + ((o0 + i) & mask);
+#if MB_DEVICE_BUILD
+            *reinterpret_cast<ulonglong2*>(dst) = make_ulonglong2(a, b);
+#else
+            dst[0] = a;
+            dst[1] = b;
+#endif
+          }
+          A.rng_state[gi] = nxt.s0;
+          A.rng_state[G + gi] = nxt.s1;
+          A.rng_state[2 * G + gi] = nxt.s2;
+          A.rng_state[3 * G + gi] = nxt.s3;
+        }
+        if (cta.leader(tid)) S.rng_generated = wbase + P.rng_window;
+      }
+      cta.sync();
+    }
+  }
+
+  // Positions the G generator sub-streams at offsets g*l of the cell's stream (leader walks the
+  // stream once; W steps).
+  MB_FN void rng_bootstrap() {
+    MB_REGION(cta, tid) {
+      if (cta.leader(tid)) {
+        Xs g{task.rng_state[0], task.rng_state[1], task.rng_state[2], task.rng_state[3]};
+        const u32 G = P.rng_gen_threads;
+        for (u32 t = 0; t < G; ++t) {
+          A.rng_state[t] = g.s0;
+          A.rng_state[G + t] = g.s1;
+          A.rng_state[2 * G + t] = g.s2;
+          A.rng_state[3 * G + t] = g.s3;
+          for (u32 i = 0; i < P.rng_per_thread; ++i) xs_next(g);
+        }
+        S.rng_pos = 0;
+        S.rng_generated = 0;
+      }
+    }
+    cta.sync();
+  }
+
+  // ------------------------------------------------------------------------------ serial samplers
+  // boost::random::poisson_distribution<size_t,double> (inversion below 10, PTRD above)
+  MB_FN u64 poisson_serial(Cursor& c, double mean) const {
+    if (mean < 10) {
+      double p = exp(-mean);
+      u64 x = 0;
+      double u = c.uniform01();
+      while (u > p) {
+        u = u - p;
+        ++x;
+        p = mean * p / static_cast<double>(x);
+      }
+      return x;
+    }
+    const double log_fact[10] = {0.0,
+                                 0.0,
+                                 0.69314718055994529,
+                                 1.7917594692280550,
+                                 3.1780538303479458,
+                                 4.7874917427820458,
+                                 6.5792512120101012,
+                                 8.5251613610654147,
+                                 10.604602902745251,
+                                 12.801827480081469};
+    const double smu = sqrt(mean);
+    const double b = 0.931 + 2.53 * smu;
+    const double a = -0.059 + 0.02483 * b;
+    const double inv_alpha = 1.1239 + 1.1328 / (b - 3.4);
+    const double v_r = 0.9277 - 3.6224 / (b - 2);
+    for (;;) {
+      if (c.overrun) return 0;
+      double u;
+      double v = c.uniform01();
+      if (v <= 0.86 * v_r) {
+        u = v / v_r - 0.43;
+        return static_cast<u64>(floor((2 * a / (0.5 - fabs(u)) + b) * u + mean + 0.445));
+      }
+      if (v >= v_r) {
+        u = c.uniform01() - 0.5;
+      } else {
+        u = v / v_r - 0.93;
+        u = ((u < 0) ? -0.5 : 0.5) - u;
+        v = c.uniform01() * v_r;
+      }
+      const double us = 0.5 - fabs(u);
+      if (us < 0.013 && v > us) continue;
+      const double k = floor((2 * a / us + b) * u + mean + 0.445);
+      v = v * inv_alpha / (a / (us * us) + b);
+      const double log_sqrt_2pi = 0.91893853320467267;
+      if (k >= 10) {
+        if (log(v * smu) <= (k + 0.5) * log(mean / k) - mean - log_sqrt_2pi + k -
+                                (1 / 12. - (1 / 360. - 1 / (1260. * k * k)) / (k * k)) / k)
+          return static_cast<u64>(k);
+      } else if (k >= 0) {
+        if (log(v) <= k * log(mean) - mean - log_fact[static_cast<int>(k)])
+          return static_cast<u64>(k);
+      }
+    }
+  }
+
+  MB_FN static double binomial_fc(i64 k) {
+    const double tbl[10] = {0.08106146679532726, 0.04134069595540929, 0.02767792568499834,
+                            0.02079067210376509, 0.01664469118982119, 0.01387612882307075,
+                            0.01189670994589177, 0.01041126526197209, 0.009255462182712733,
+                            0.008330563433362871};
+    if (k < 10) return tbl[k];
+    const double ikp1 = 1.0 / static_cast<double>(k + 1);
+    return (1.0 / 12 - (1.0 / 360 - (1.0 / 1260) * (ikp1 * ikp1)) * (ikp1 * ikp1)) * ikp1;
+  }
+
+  // boost::random::binomial_distribution<ptrdiff_t,double> (inversion when (t+1)p < 11, else BTRD)
+  MB_FN i64 binomial_serial(Cursor& c, i64 t, double p_in) const {
+    const bool flip = 0.5 < p_in;
+    const double p = flip ? (1 - p_in) : p_in;
+    const i64 m = static_cast<i64>(static_cast<double>(t + 1) * p);
+    i64 res = 0;
+    if (m < 11) {
+      const double q_n = pow(1 - p, static_cast<double>(t));
+      const double q = 1 - p;
+      const double s = p / q;
+      const double a = static_cast<double>(t + 1) * s;
+      double r = q_n;
+      double u = c.uniform01();
+      i64 x = 0;
+      while (u > r) {
+        u = u - r;
+        ++x;
+        const double r1 = ((a / static_cast<double>(x)) - s) * r;
+        if (r1 < 2.220446049250313e-16 && r1 < r) break;
+        r = r1;
+      }
+      res = x;
+    } else {
+      const double td = static_cast<double>(t);
+      const double r = p / (1 - p);
+      const double nr = static_cast<double>(t + 1) * r;
+      const double npq = td * p * (1 - p);
+      const double sqrt_npq = sqrt(npq);
+      const double b = 1.15 + 2.53 * sqrt_npq;
+      const double a = -0.0873 + 0.0248 * b + 0.01 * p;
+      const double cc = td * p + 0.5;
+      const double alpha = (2.83 + 5.1 / b) * sqrt_npq;
+      const double v_r = 0.92 - 4.2 / b;
+      const double u_rv_r = 0.86 * v_r;
+      for (;;) {
+        if (c.overrun) return 0;
+        double u;
+        double v = c.uniform01();
+        if (v <= u_rv_r) {
+          u = v / v_r - 0.43;
+          res = static_cast<i64>(floor((2 * a / (0.5 - fabs(u)) + b) * u + cc));
+          break;
+        }
+        if (v >= v_r) {
+          u = c.uniform01() - 0.5;
+        } else {
+          u = v / v_r - 0.93;
+          u = ((u < 0) ? -0.5 : 0.5) - u;
+          v = c.uniform01() * v_r;
+        }
+        const double us = 0.5 - fabs(u);
+        const i64 k = static_cast<i64>(floor((2 * a / us + b) * u + cc));
+        if (k < 0 || k > t) continue;
+        v = v * alpha / (a / (us * us) + b);
+        const double km = static_cast<double>(k > m ? k - m : m - k);
+        if (km <= 15) {
+          double f = 1;
+          if (m < k) {
+            i64 i = m;
+            do {
+              ++i;
+              f = f * (nr / static_cast<double>(i) - r);
+            } while (i != k);
+          } else if (m > k) {
+            i64 i = k;
+            do {
+              ++i;
+              v = v * (nr / static_cast<double>(i) - r);
+            } while (i != m);
+          }
+          if (v <= f) {
+            res = k;
+            break;
+          }
+          continue;
+        }
+        v = log(v);
+        const double rho = (km / npq) * (((km / 3. + 0.625) * km + 1. / 6) / npq + 0.5);
+        const double tt = -km * km / (2 * npq);
+        if (v < tt - rho) {
+          res = k;
+          break;
+        }
+        if (v > tt + rho) continue;
+        const i64 nm = t - m + 1;
+        const double h = (static_cast<double>(m) + 0.5) *
+                             log(static_cast<double>(m + 1) / (r * static_cast<double>(nm))) +
+                         binomial_fc(m) + binomial_fc(t - m);
+        const i64 nk = t - k + 1;
+        if (v <= h +
+                     static_cast<double>(t + 1) *
+                         log(static_cast<double>(nm) / static_cast<double>(nk)) +
+                     (static_cast<double>(k) + 0.5) *
+                         log(static_cast<double>(nk) * r / static_cast<double>(k + 1)) -
+                     binomial_fc(k) - binomial_fc(t - k)) {
+          res = k;
+          break;
+        }
+      }
+    }
+    return flip ? t - res : res;
+  }
+
+  // detail::unit_exponential_distribution<double> (256-layer ziggurat)
+  MB_FN double unit_exponential_serial(Cursor& c) const {
+    const double* tx = D.zig_ex;
+    const double* ty = D.zig_ey;
+    double shift = 0;
+    for (;;) {
+      if (c.overrun) return 0;
+      int i;
+      const double u = int_float_pair8(c.next(), &i);
+      const double x = u * tx[i];
+      if (x < tx[i + 1]) return shift + x;
+      if (i == 0) {
+        shift += tx[1];
+      } else {
+        const double y01 = c.uniform01();
+        const double y = ty[i] + y01 * (ty[i + 1] - ty[i]);
+        const double y_above_ubound = (tx[i] - tx[i + 1]) * y01 - (tx[i] - x);
+        const double y_above_lbound = y - (ty[i + 1] + (tx[i + 1] - x) * ty[i + 1]);
+        if (y_above_ubound < 0 && (y_above_lbound < 0 || y < exp(-x))) return x + shift;
+      }
+    }
+  }
+
+  // Fast path of detail::unit_normal_distribution<double>: true when the draw is accepted at once.
+  MB_FN bool unit_normal_fast(u64 u, double* z) const {
+    int bits;
+    const double r = int_float_pair8(u, &bits);
+    const int sign = (bits & 1) * 2 - 1;
+    const int i = bits >> 1;
+    const double x = r * A.zig_nx[i];
+    *z = x * sign;
+    return x < A.zig_nx[i + 1];
+  }
+  // Full sampler from a cursor (the first draw is taken from the cursor as well).
+  MB_FN double unit_normal_serial(Cursor& c) const {
+    const double* tx = A.zig_nx;
+    const double* ty = D.zig_ny;
+    for (;;) {
+      if (c.overrun) return 0;
+      int bits;
+      const double r = int_float_pair8(c.next(), &bits);
+      const int sign = (bits & 1) * 2 - 1;
+      const int i = bits >> 1;
+      const double x = r * tx[i];
+      if (x < tx[i + 1]) return x * sign;
+      if (i == 0) {
+        const double tail_start = tx[1];
+        for (;;) {
+          if (c.overrun) return 0;
+          const double xx = unit_exponential_serial(c) / tail_start;
+          const double yy = unit_exponential_serial(c);
+          if (2 * yy > xx * xx) return (xx + tail_start) * sign;
+        }
+      }
+      const double y01 = c.uniform01();
+      const double y = ty[i] + y01 * (ty[i + 1] - ty[i]);
+      double y_above_ubound, y_above_lbound;
+      if (tx[i] >= 1) {
+        y_above_ubound = (tx[i] - tx[i + 1]) * y01 - (tx[i] - x);
+        y_above_lbound = y - (ty[i] + (tx[i] - x) * ty[i] * tx[i]);
+      } else {
+        y_above_lbound = (tx[i] - tx[i + 1]) * y01 - (tx[i] - x);
+        y_above_ubound = y - (ty[i] + (tx[i] - x) * ty[i] * tx[i]);
+      }
+      if (y_above_ubound < 0 && (y_above_lbound < 0 || y < exp(-(x * x / 2)))) return x * sign;
+    }
+  }
+
+  // ------------------------------------------------------------------------------ init
+  // State::operator=(Task) + reset_buffers (simulation.cpp:617-627,741-761) and
+  // ExtrusionBarriers::init_states (extrusion_barriers.cpp:219-230).
+  MB_FN void init_cell() {
+    MB_REGION(cta, tid) {
+      for (u32 i = tid; i < P.n_lefs; i += cta.nt()) {
+        A.rev[i] = kUnbound;
+        A.fwd[i] = kUnbound;
+        A.ep[i] = kUnbound;
+        A.rr[i] = static_cast<u16>(i);
+        A.fr[i] = static_cast<u16>(i);
+        A.rm[i] = 0;
+        A.fm[i] = 0;
+        A.rc[i] = 0;
+        A.fc[i] = 0;
+      }
+      for (u32 i = tid; i < P.n_bar; i += cta.nt()) A.bar_pos[i] = D.bar_pos[i];
+      for (u32 i = tid; i < 129; i += cta.nt()) A.zig_nx[i] = D.zig_nx[i];
+      if (cta.leader(tid)) {
+        S.epoch = 0;
+        S.num_burnin_epochs = 0;
+        S.num_contacts = 0;
+        S.lef_updates = 0;
+        S.num_active = 0;
+        S.burnin_completed = 0;
+        S.fault = 0;
+        S.hist_len = 0;
+        S.hist_head = 0;
+        S.done = 0;
+        if (P.burnin_history > kMaxBurninHistory || P.burnin_window + 1 >= P.burnin_history)
+          fault(kFaultBurninHistory);
+      }
+    }
+    cta.sync();
+    rng_bootstrap();
+
+    // init_states: one Bernoulli(occupancy) per barrier whose occupancy is not 0
+    rng_ensure(S.rng_pos + P.n_bar);
+    PerThread<u64> cnt(cta.nt());
+    MB_REGION(cta, tid) {
+      u32 lo, hi;
+      chunk(tid, P.n_bar, &lo, &hi);
+      u64 c = 0;
+      for (u32 i = lo; i < hi; ++i) c += D.bar_occupancy[i] != 0.0;
+      cnt[tid] = c;
+    }
+    const u64 total = cta.exscan_sum(cnt);
+    MB_REGION(cta, tid) {
+      u32 lo, hi;
+      chunk(tid, P.n_bar, &lo, &hi);
+      u64 o = S.rng_pos + cnt[tid];
+      for (u32 i = lo; i < hi; ++i) {
+        const double occ = D.bar_occupancy[i];
+        bool act = false;
+        if (occ != 0.0) act = bernoulli_raw(raw(o++), occ);
+        A.bar_active[i] = act ? 1 : 0;
+      }
+    }
+    cta.sync();
+    MB_REGION(cta, tid) {
+      if (cta.leader(tid)) {
+        S.rng_pos += total;
+        if (P.skip_burnin) {
+          S.num_active = P.n_lefs;
+          S.burnin_completed = 1;
+        }
+      }
+    }
+    cta.sync();
+  }
+
+  // ------------------------------------------------------------------------------ burn-in
+  // run_burnin (simulation.cpp:866-894), compute_loop_size_stats (:795-819),
+  // evaluate_burnin (:821-864).
+  MB_FN u32 count_dips(const double* hist, int tid) const {
+    // hist is a ring of length cap starting at S.hist_head
+    const u32 cap = P.burnin_history, w = P.burnin_window;
+    u32 n = 0;
+    for (u32 j = 1 + tid; j + w < cap; j += cta.nt()) {
+      double a1 = 0.0, a2 = 0.0;
+      for (u32 k = 0; k < w; ++k) a1 = a1 + hist[(S.hist_head + j - 1 + k) % cap];
+      for (u32 k = 0; k < w; ++k) a2 = a2 + hist[(S.hist_head + j + k) % cap];
+      const double n1 = a1 / static_cast<double>(w);
+      const double n2 = a2 / static_cast<double>(w);
+      n += n1 > n2;
+    }
+    return n;
+  }
+
+  MB_FN void burnin_step() {
+    for (;;) {
+      const bool activating = S.num_active != P.n_lefs;
+      cta.sync();
+      if (activating) {
+        rng_ensure(S.rng_pos + 256);
+        MB_REGION(cta, tid) {
+          if (cta.leader(tid)) {
+            ++S.num_burnin_epochs;
+            Cursor c = cursor(S.rng_pos, S.rng_pos + 256);
+            const u64 k = poisson_serial(c, P.lef_binding_rate_burnin);
+            if (c.overrun) fault(kFaultSerialDraws);
+            S.rng_pos = c.pos;
+            const u64 na = u64(S.num_active) + k;
+            S.num_active = na < P.n_lefs ? static_cast<u32>(na) : P.n_lefs;
+          }
+        }
+        cta.sync();
+      } else {
+        const u32 n = S.num_active;
+        // mean loop size: the integer sum is exact in double, so any order gives the reference's
+        // left-to-right result; the squared-deviation sum is reduced in a fixed tree order
+        // (DESIGN.md "burn-in statistics").
+        PerThread<u64> isum(cta.nt());
+        MB_REGION(cta, tid) {
+          u64 acc = 0;
+          for (u32 i = tid; i < n; i += cta.nt())
+            acc += (A.ep[i] != kUnbound) ? (A.fwd[i] - A.rev[i]) : 0u;
+          isum[tid] = acc;
+        }
+        const u64 tot = cta.reduce_sum(isum);
+        const double mean = static_cast<double>(tot) / static_cast<double>(n);
+        PerThread<double> dsum(cta.nt());
+        MB_REGION(cta, tid) {
+          double acc = 0.0;
+          for (u32 i = tid; i < n; i += cta.nt()) {
+            const u32 ls = (A.ep[i] != kUnbound) ? (A.fwd[i] - A.rev[i]) : 0u;
+            const double d = static_cast<double>(ls) - mean;
+            acc = acc + (d * d);
+          }
+          dsum[tid] = acc;
+        }
+        const double ssd = cta.reduce_sum_f64(dsum);
+        MB_REGION(cta, tid) {
+          if (cta.leader(tid)) {
+            ++S.num_burnin_epochs;
+            const double sd = sqrt(ssd / static_cast<double>(n));
+            const u32 cap = P.burnin_history;
+            if (S.hist_len == cap) {
+              S.hist_head = (S.hist_head + 1) % cap;
+              --S.hist_len;
+            }
+            const u32 slot = (S.hist_head + S.hist_len) % cap;
+            S.avg_hist[slot] = mean;
+            S.cv_hist[slot] = sd / mean;
+            ++S.hist_len;
+          }
+        }
+        cta.sync();
+        bool completed = false;
+        if (S.hist_len == P.burnin_history) {
+          const u32 cap = P.burnin_history, w = P.burnin_window;
+          PerThread<u64> dips(cta.nt());
+          MB_REGION(cta, tid) { dips[tid] = count_dips(S.cv_hist, tid); }
+          const u64 n1 = cta.reduce_sum(dips);
+          const double r1 = static_cast<double>(n1) / static_cast<double>(cap - w - n1);
+          if (r1 >= 0.95 && r1 <= 1.05) {
+            MB_REGION(cta, tid) { dips[tid] = count_dips(S.avg_hist, tid); }
+            const u64 n2 = cta.reduce_sum(dips);
+            const double r2 = static_cast<double>(n2) / static_cast<double>(cap - w - n2);
+            completed = r2 >= 0.95 && r2 <= 1.05;
+          }
+        }
+        completed = completed && (S.epoch > P.min_burnin_epochs);
+        bool force = false;
+        if (!completed && S.epoch >= P.max_burnin_epochs) force = true;
+        cta.sync();
+        MB_REGION(cta, tid) {
+          if (cta.leader(tid)) {
+            if (completed || force) S.burnin_completed = 1;
+            if (force) S.num_active = P.n_lefs;
+          }
+        }
+        cta.sync();
+      }
+      if (S.num_active != 0 || S.fault != 0) break;
+    }
+    cta.sync();
+  }
+
+  // ------------------------------------------------------------------------------ bind + rank
+  // select_lefs_to_bind + bind_lefs (simulation_impl.hpp:30-91)
+  MB_FN void bind_lefs() {
+    const u32 n = S.num_active;
+    const u64 range = u64(P.end - 1) - u64(P.start);
+    const u64 bucket = range ? uniform_int_bucket(range) : 1;
+    PerThread<u64> cnt(cta.nt());
+    MB_REGION(cta, tid) {
+      u32 lo, hi;
+      chunk(tid, n, &lo, &hi);
+      u64 c = 0;
+      for (u32 i = lo; i < hi; ++i) c += A.ep[i] == kUnbound;
+      cnt[tid] = c;
+    }
+    const u64 total = cta.exscan_sum(cnt);
+    if (total == 0) return;
+    if (range == 0) {
+      MB_REGION(cta, tid) {
+        for (u32 i = tid; i < n; i += cta.nt()) {
+          if (A.ep[i] == kUnbound) {
+            A.rev[i] = A.fwd[i] = P.start;
+            A.ep[i] = static_cast<u32>(S.epoch);
+          }
+        }
+      }
+      cta.sync();
+      return;
+    }
+    rng_ensure(S.rng_pos + total + 64);
+    MB_REGION(cta, tid) {
+      if (cta.leader(tid)) S.tmp_u32[0] = 0;
+    }
+    cta.sync();
+    MB_REGION(cta, tid) {
+      u32 lo, hi;
+      chunk(tid, n, &lo, &hi);
+      u64 o = S.rng_pos + cnt[tid];
+      bool rejected = false;
+      for (u32 i = lo; i < hi; ++i) {
+        if (A.ep[i] != kUnbound) continue;
+        const u64 r = raw(o++) / bucket;
+        if (r > range) rejected = true;
+        A.scratch[i] = static_cast<u32>(u64(P.start) + r);
+      }
+      if (rejected) S.tmp_u32[0] = 1;
+    }
+    cta.sync();
+    if (S.tmp_u32[0] != 0) {
+      // a uniform_int rejection shifts every later draw: redo the phase sequentially
+      cta.sync();
+      MB_REGION(cta, tid) {
+        if (cta.leader(tid)) {
+          Cursor c = cursor(S.rng_pos, S.rng_pos + total + 64);
+          for (u32 i = 0; i < n; ++i) {
+            if (A.ep[i] != kUnbound) continue;
+            u64 r;
+            do {
+              r = c.next() / bucket;
+            } while (r > range && !c.overrun);
+            A.scratch[i] = static_cast<u32>(u64(P.start) + r);
+          }
+          if (c.overrun) fault(kFaultSerialDraws);
+          S.tmp_u64[0] = c.pos;
+        }
+      }
+      cta.sync();
+    } else {
+      MB_REGION(cta, tid) {
+        if (cta.leader(tid)) S.tmp_u64[0] = S.rng_pos + total;
+      }
+      cta.sync();
+    }
+    MB_REGION(cta, tid) {
+      for (u32 i = tid; i < n; i += cta.nt()) {
+        if (A.ep[i] == kUnbound) {
+          A.rev[i] = A.fwd[i] = A.scratch[i];
+          A.ep[i] = static_cast<u32>(S.epoch);
+        }
+      }
+      if (cta.leader(tid)) S.rng_pos = S.tmp_u64[0];
+    }
+    cta.sync();
+  }
+
+  // rank_lefs (simulation.cpp:410-496): total order (pos, binding epoch asc/desc, previous slot).
+  template <bool kRev>
+  MB_FN bool rank_less(u32 a, u32 b, const u16* prev_slot) const {
+    const u32 pa = kRev ? A.rev[a] : A.fwd[a];
+    const u32 pb = kRev ? A.rev[b] : A.fwd[b];
+    if (pa != pb) return pa < pb;
+    const u32 ea = A.ep[a], eb = A.ep[b];
+    if (ea != eb) return kRev ? ea < eb : ea > eb;
+    return prev_slot[a] < prev_slot[b];
+  }
+
+  MB_FN void rank_lefs() {
+    const u32 n = S.num_active;
+    if (n < 2) return;
+    // scratch areas that are dead at this point of the epoch: moves and collision words
+    u16* prev_r = reinterpret_cast<u16*>(A.rc);  // previous slot of every LEF in the rev order
+    u16* prev_f = reinterpret_cast<u16*>(A.fc);
+    MB_REGION(cta, tid) {
+      for (u32 k = tid; k < n; k += cta.nt()) {
+        prev_r[A.rr[k]] = static_cast<u16>(k);
+        prev_f[A.fr[k]] = static_cast<u16>(k);
+      }
+    }
+    cta.sync();
+#if MB_DEVICE_BUILD
+    u32 npad = 1;
+    while (npad < n) npad <<= 1;
+    u16* kr = reinterpret_cast<u16*>(A.rm);  // npad <= 2n u16 fit in n u32
+    u16* kf = reinterpret_cast<u16*>(A.fm);
+    const int tid = cta.first();
+    for (u32 k = tid; k < npad; k += cta.nt()) {
+      kr[k] = k < n ? A.rr[k] : static_cast<u16>(0xFFFF);
+      kf[k] = k < n ? A.fr[k] : static_cast<u16>(0xFFFF);
+    }
+    __syncthreads();
+    for (u32 size = 2; size <= npad; size <<= 1) {
+      for (u32 stride = size >> 1; stride > 0; stride >>= 1) {
+        for (u32 t = tid; t < npad / 2; t += cta.nt()) {
+          const u32 lo = 2 * t - (t & (stride - 1));
+          const u32 hi = lo + stride;
+          const bool asc = (lo & size) == 0;
+          {
+            const u16 x = kr[lo], y = kr[hi];
+            // sentinel 0xFFFF sorts last
+            const bool y_lt_x = (y != 0xFFFF) && (x == 0xFFFF || rank_less<true>(y, x, prev_r));
+            const bool x_lt_y = (x != 0xFFFF) && (y == 0xFFFF || rank_less<true>(x, y, prev_r));
+            if (asc ? y_lt_x : x_lt_y) {
+              kr[lo] = y;
+              kr[hi] = x;
+            }
+          }
+          {
+            const u16 x = kf[lo], y = kf[hi];
+            const bool y_lt_x = (y != 0xFFFF) && (x == 0xFFFF || rank_less<false>(y, x, prev_f));
+            const bool x_lt_y = (x != 0xFFFF) && (y == 0xFFFF || rank_less<false>(x, y, prev_f));
+            if (asc ? y_lt_x : x_lt_y) {
+              kf[lo] = y;
+              kf[hi] = x;
+            }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    for (u32 k = tid; k < n; k += cta.nt()) {
+      A.rr[k] = kr[k];
+      A.fr[k] = kf[k];
+    }
+    __syncthreads();
+#else
+    std::sort(A.rr, A.rr + n, [&](u16 a, u16 b) { return rank_less<true>(a, b, prev_r); });
+    std::sort(A.fr, A.fr + n, [&](u16 a, u16 b) { return rank_less<false>(a, b, prev_f); });
+#endif
+  }
+
+  // ------------------------------------------------------------------------------ contacts
+  // ContactMatrixDense::increment (contact_matrix_dense_safe_impl.hpp:54-68,86-89)
+  MB_FN void band_increment(u32 b1, u32 b2) const {
+    const u32 i = b1 > b2 ? b1 - b2 : b2 - b1;
+    const u32 j = b1 > b2 ? b1 : b2;
+    if (i >= P.nrows) {
+      MB_ATOMIC_ADD_U64(K.missed, u64(1));
+      return;
+    }
+    MB_ATOMIC_ADD_U32(K.band + (size_t(j) * P.nrows + i), 1u);
+  }
+
+  // One sampling event starting at stream offset o (register_contacts.cpp:122-232).
+  // kind 0: loop contact, 1: TAD contact, 2: 1D occupancy. Returns the number of raw draws the
+  // event consumes; *b1/*b2 receive the two bins (or kUnbound when nothing is registered).
+  MB_FN u32 sampling_event(u64 o, int kind, u64 limit, u32* b1, u32* b2) const {
+    *b1 = kUnbound;
+    *b2 = kUnbound;
+    Cursor c = cursor(o, limit);
+    const u32 n = S.num_active;
+    u64 i = 0;
+    if (n > 1) {
+      const u64 range = n - 1;
+      const u64 bucket = uniform_int_bucket(range);
+      do {
+        i = c.next() / bucket;
+      } while (i > range && !c.overrun);
+    }
+    if (c.overrun) {
+      fault(kFaultSerialDraws);
+      return static_cast<u32>(c.pos - o);
+    }
+    const u64 sp = u64(P.start) + 1, ep = u64(P.end) - 1;
+    const u32 rev = A.rev[i], fwd = A.fwd[i];
+    const bool bound = A.ep[i] != kUnbound;
+    if (bound && rev > sp && rev < ep && fwd > sp && fwd < ep) {
+      double n1 = 0.0, n2 = 0.0;
+      if (P.noisify) {
+        n1 = gev_from_canonical(canonical_raw(c.next()), P.gev_mu, P.gev_sigma, P.gev_xi);
+        n2 = gev_from_canonical(canonical_raw(c.next()), P.gev_mu, P.gev_sigma, P.gev_xi);
+      }
+      const double a = static_cast<double>(rev) - n1;
+      const double b = static_cast<double>(fwd) + n2;
+      const double p1 = b < a ? b : a;
+      const double p2 = b < a ? a : b;
+      const double sd = static_cast<double>(sp), ed = static_cast<double>(ep);
+      if (p1 >= sd && p2 >= sd && p1 < ed && p2 < ed) {
+        u64 x1 = static_cast<u64>(p1), x2 = static_cast<u64>(p2);
+        if (kind == 1) {
+          const u64 range = x2 - x1;
+          u64 y1 = x1, y2 = x1;
+          if (range != 0) {
+            const u64 bucket = uniform_int_bucket(range);
+            u64 r;
+            do {
+              r = c.next() / bucket;
+            } while (r > range && !c.overrun);
+            y1 = x1 + r;
+            do {
+              r = c.next() / bucket;
+            } while (r > range && !c.overrun);
+            y2 = x1 + r;
+          }
+          x1 = y1;
+          x2 = y2;
+        }
+        *b1 = static_cast<u32>((x1 - sp) / P.bin_size);
+        *b2 = static_cast<u32>((x2 - sp) / P.bin_size);
+      }
+    }
+    if (c.overrun) fault(kFaultSerialDraws);
+    return static_cast<u32>(c.pos - o);
+  }
+
+  // Runs `n_events` events of one kind. Events are evaluated speculatively at their default
+  // stride; the first event that consumes a different number of draws re-bases the rest.
+  MB_FN void sampling_events(u32 n_events, int kind) {
+    if (n_events == 0) return;
+    const u32 n_act = S.num_active;
+    const u32 base_draws = n_act > 1 ? 1u : 0u;
+    const u32 stride = base_draws + (P.noisify ? 2u : 0u) + (kind == 1 ? 2u : 0u);
+    const u32 cap = ((P.n_lefs > P.n_bar ? P.n_lefs : P.n_bar) + 64) / 2;
+    u32 e0 = 0;
+    while (e0 < n_events) {
+      u32 batch = n_events - e0;
+      if (batch > cap) batch = cap;
+      const u32 max_by_window = (P.rng_window - 64) / (stride + 1);
+      if (batch > max_by_window) batch = max_by_window;
+      const u64 base = S.rng_pos;
+      const u64 limit = base + u64(batch) * stride + 48;
+      rng_ensure(limit);
+      MB_REGION(cta, tid) {
+        if (cta.leader(tid)) S.tmp_u32[0] = 0xFFFFFFFFu;
+      }
+      cta.sync();
+      MB_REGION(cta, tid) {
+        for (u32 e = tid; e < batch; e += cta.nt()) {
+          u32 b1, b2;
+          const u32 c = sampling_event(base + u64(e) * stride, kind, limit, &b1, &b2);
+          A.scratch[2 * e] = b1;
+          A.scratch[2 * e + 1] = b2;
+          if (c != stride) MB_ATOMIC_MIN_U32(&S.tmp_u32[0], (e << 8) | (c > 255 ? 255u : c));
+        }
+      }
+      cta.sync();
+      const u32 exc = S.tmp_u32[0];
+      const u32 valid = exc == 0xFFFFFFFFu ? batch : (exc >> 8) + 1;  // events final this round
+      cta.sync();
+      MB_REGION(cta, tid) {
+        u32 registered = 0;
+        for (u32 e = tid; e < valid; e += cta.nt()) {
+          const u32 b1 = A.scratch[2 * e], b2 = A.scratch[2 * e + 1];
+          if (b1 == kUnbound) continue;
+          if (kind == 2) {
+            if (K.occ1d) {
+              MB_ATOMIC_ADD_U64(K.occ1d + b1, u64(1));
+              MB_ATOMIC_ADD_U64(K.occ1d + b2, u64(1));
+            }
+          } else {
+            band_increment(b1, b2);
+            ++registered;
+          }
+        }
+        if (registered) MB_ATOMIC_ADD_U64(&S.tmp_u64[1], u64(registered));
+        if (cta.leader(tid)) {
+          u64 consumed = u64(valid) * stride;
+          if (exc != 0xFFFFFFFFu) {
+            if ((exc & 0xFF) == 255) fault(kFaultSerialDraws);
+            consumed = u64(valid - 1) * stride + (exc & 0xFF);
+          }
+          S.rng_pos = base + consumed;
+        }
+      }
+      cta.sync();
+      e0 += valid;
+    }
+  }
+
+  // sample_and_register_contacts (register_contacts.cpp:93-120)
+  MB_FN void sample_and_register_contacts() {
+    u64 nev = P.contacts_per_epoch;
+    if (!P.stop_on_epochs) {
+      const u64 left = task.target_contacts - S.num_contacts;
+      if (left < nev) nev = left;
+    }
+    if (nev == 0) return;
+    cta.sync();
+    const bool need_binomial = P.tad_to_loop != 0.0 && isfinite(P.tad_to_loop);
+    if (need_binomial) rng_ensure(S.rng_pos + 256);
+    MB_REGION(cta, tid) {
+      if (cta.leader(tid)) {
+        u64 nloop;
+        if (P.tad_to_loop == 0.0) {
+          nloop = nev;
+        } else if (!need_binomial) {
+          nloop = 0;
+        } else {
+          Cursor c = cursor(S.rng_pos, S.rng_pos + 256);
+          nloop = static_cast<u64>(
+              binomial_serial(c, static_cast<i64>(nev), 1.0 / (P.tad_to_loop + 1.0)));
+          if (c.overrun) fault(kFaultSerialDraws);
+          S.rng_pos = c.pos;
+        }
+        S.tmp_u32[1] = static_cast<u32>(nloop);
+        S.tmp_u64[1] = 0;
+      }
+    }
+    cta.sync();
+    const u32 nloop = S.tmp_u32[1];
+    const u32 ntad = static_cast<u32>(nev) - nloop;
+    sampling_events(nloop, 0);
+    sampling_events(ntad, 1);
+    if (P.track_1d) sampling_events(static_cast<u32>(nev), 2);
+    MB_REGION(cta, tid) {
+      if (cta.leader(tid)) S.num_contacts += S.tmp_u64[1];
+    }
+    cta.sync();
+  }
+
+  // ------------------------------------------------------------------------------ moves
+  // generate_moves_helper (simulation.cpp:272-297) for one direction: one Normal(speed, sd) per
+  // LEF in index order. The fast ziggurat path uses exactly one draw; the rare slow paths are
+  // evaluated speculatively and stitched into the stream by the leader.
+  MB_FN void generate_moves_dir(u32* moves, double speed, double sd) {
+    const u32 n = S.num_active;
+    if (sd == 0.0) {
+      const u32 mi = static_cast<u32>(round(speed));
+      MB_REGION(cta, tid) {
+        for (u32 i = tid; i < n; i += cta.nt()) moves[i] = mi;
+      }
+      cta.sync();
+      return;
+    }
+    const u32 slack = n / 8 + 64;
+    const u32 span = n + slack;  // offsets examined
+    const u64 base = S.rng_pos;
+    const u64 limit = base + span + 192;
+    rng_ensure(limit);
+    // exception records live in scratch: 4 words each {offset, draws consumed, z lo, z hi}
+    u32* ex = A.scratch;
+    const u32 ex_cap = ((P.n_lefs > P.n_bar ? P.n_lefs : P.n_bar) + 64) / 4;
+    PerThread<u64> cnt(cta.nt());
+    MB_REGION(cta, tid) {
+      u32 lo, hi;
+      chunk(tid, span, &lo, &hi);
+      u64 c = 0;
+      for (u32 o = lo; o < hi; ++o) {
+        double z;
+        c += !unit_normal_fast(raw(base + o), &z);
+      }
+      cnt[tid] = c;
+    }
+    const u64 n_exc = cta.exscan_sum(cnt);
+    if (n_exc > ex_cap) {
+      MB_REGION(cta, tid) {
+        if (cta.leader(tid)) fault(kFaultSerialDraws);
+      }
+      cta.sync();
+      return;
+    }
+    MB_REGION(cta, tid) {
+      u32 lo, hi;
+      chunk(tid, span, &lo, &hi);
+      u32 j = static_cast<u32>(cnt[tid]);
+      for (u32 o = lo; o < hi; ++o) {
+        double z;
+        if (!unit_normal_fast(raw(base + o), &z)) ex[4 * j++] = o;
+      }
+    }
+    cta.sync();
+    MB_REGION(cta, tid) {
+      for (u32 j = tid; j < n_exc; j += cta.nt()) {
+        Cursor c = cursor(base + ex[4 * j], limit);
+        const double z = unit_normal_serial(c);
+        ex[4 * j + 1] = static_cast<u32>(c.pos - (base + ex[4 * j]));
+        u64 zb;
+#if MB_DEVICE_BUILD
+        zb = static_cast<u64>(__double_as_longlong(z));
+#else
+        std::memcpy(&zb, &z, 8);
+#endif
+        ex[4 * j + 2] = static_cast<u32>(zb);
+        ex[4 * j + 3] = static_cast<u32>(zb >> 32);
+        if (c.overrun) fault(kFaultSerialDraws);
+      }
+    }
+    cta.sync();
+    // leader: keep the exceptions that start an item (not swallowed by an earlier slow path) and
+    // turn their offsets into item indices. Record j becomes {item, cumulative extra draws, z}.
+    MB_REGION(cta, tid) {
+      if (cta.leader(tid)) {
+        u32 covered = 0, shift = 0, kept = 0;
+        for (u32 j = 0; j < n_exc; ++j) {
+          const u32 off = ex[4 * j];
+          if (off < covered) continue;
+          const u32 item = off - shift;
+          if (item >= n) break;
+          const u32 c = ex[4 * j + 1];
+          covered = off + c;
+          shift += c - 1;
+          ex[4 * kept] = item;
+          ex[4 * kept + 1] = shift;
+          ex[4 * kept + 2] = ex[4 * j + 2];
+          ex[4 * kept + 3] = ex[4 * j + 3];
+          ++kept;
+        }
+        S.tmp_u32[2] = kept;
+        S.tmp_u32[3] = shift;
+        if (shift > slack) fault(kFaultRngWindow);
+      }
+    }
+    cta.sync();
+    const u32 kept = S.tmp_u32[2];
+    MB_REGION(cta, tid) {
+      u32 lo, hi;
+      chunk(tid, n, &lo, &hi);
+      // first kept exception with item >= lo
+      u32 a = 0, b = kept;
+      while (a < b) {
+        const u32 m = (a + b) >> 1;
+        if (ex[4 * m] < lo) {
+          a = m + 1;
+        } else {
+          b = m;
+        }
+      }
+      u32 e = a;
+      u32 shift = e ? ex[4 * (e - 1) + 1] : 0;
+      for (u32 i = lo; i < hi; ++i) {
+        double z;
+        if (e < kept && ex[4 * e] == i) {
+          const u64 zb = u64(ex[4 * e + 2]) | (u64(ex[4 * e + 3]) << 32);
+#if MB_DEVICE_BUILD
+          z = __longlong_as_double(static_cast<long long>(zb));
+#else
+          std::memcpy(&z, &zb, 8);
+#endif
+          shift = ex[4 * e + 1];  // later items start after this item's extra draws
+          ++e;
+        } else {
+          unit_normal_fast(raw(base + i + shift), &z);
+        }
+        const double v = z * sd + speed;
+        const double clamped = v < 0.0 ? 0.0 : v;  // std::max(0.0, v)
+        moves[i] = static_cast<u32>(round(clamped));
+      }
+    }
+    cta.sync();
+    MB_REGION(cta, tid) {
+      if (cta.leader(tid)) S.rng_pos = base + n + S.tmp_u32[3];
+    }
+    cta.sync();
+  }
+
+  // adjust_moves_of_consecutive_extr_units (simulation.cpp:350-407) + clamp_moves (:332-347).
+  // The two neighbour recurrences are min-plus prefix scans; the handful of units close enough
+  // to an interval end for the reference's "skip" rule to fire are finished serially.
+  MB_FN u32 count_rev_le(u64 thr) const {  // number of rev ranks with pos <= thr (binary search)
+    u32 a = 0, b = S.num_active;
+    while (a < b) {
+      const u32 m = (a + b) >> 1;
+      if (u64(A.rev[A.rr[m]]) <= thr) {
+        a = m + 1;
+      } else {
+        b = m;
+      }
+    }
+    return a;
+  }
+  MB_FN u32 count_fwd_lt(u64 thr) const {  // number of fwd ranks with pos < thr
+    u32 a = 0, b = S.num_active;
+    while (a < b) {
+      const u32 m = (a + b) >> 1;
+      if (u64(A.fwd[A.fr[m]]) < thr) {
+        a = m + 1;
+      } else {
+        b = m;
+      }
+    }
+    return a;
+  }
+
+  MB_FN void adjust_and_clamp_moves() {
+    const u32 n = S.num_active;
+    PerThread<u64> mx(cta.nt());
+    MB_REGION(cta, tid) {
+      u64 m = 0;
+      for (u32 i = tid; i < n; i += cta.nt()) {
+        const u64 a = A.rm[i], b = A.fm[i];
+        m = a > m ? a : m;
+        m = b > m ? b : m;
+      }
+      mx[tid] = m;
+    }
+    const u64 mmax = cta.reduce_max(mx);
+    if (n >= 2) {
+      // ---- rev units, walked 3'->5': q'[k-1] = min(q[k-1], q'[k] - 1)
+      const u32 k_near = count_rev_le(u64(P.start) + mmax + n);  // ranks < k_near: serial part
+      const u32 M = n - k_near;                                  // ranks [k_near, n) in parallel
+      PerThread<MinPlus> f(cta.nt());
+      MB_REGION(cta, tid) {
+        u32 lo, hi;
+        chunk(tid, M, &lo, &hi);
+        MinPlus acc = minplus_identity();
+        for (u32 m = lo; m < hi; ++m) {
+          const u32 idx = A.rr[n - 1 - m];
+          const i64 q = i64(A.rev[idx]) - i64(A.rm[idx]);
+          acc = minplus_then(acc, MinPlus{q, -1});
+        }
+        f[tid] = acc;
+      }
+      cta.exscan_minplus(f);
+      MB_REGION(cta, tid) {
+        u32 lo, hi;
+        chunk(tid, M, &lo, &hi);
+        i64 x = minplus_apply(f[tid], kMinPlusInf);
+        for (u32 m = lo; m < hi; ++m) {
+          const u32 idx = A.rr[n - 1 - m];
+          const i64 q = i64(A.rev[idx]) - i64(A.rm[idx]);
+          const i64 cap = x - 1;
+          x = q < cap ? q : cap;
+          A.rm[idx] = static_cast<u32>(i64(A.rev[idx]) - x);
+        }
+      }
+      cta.sync();
+      MB_REGION(cta, tid) {
+        if (cta.leader(tid)) {
+          for (u32 i = (k_near < n - 1 ? k_near : n - 1); i > 0; --i) {
+            const u32 i1 = A.rr[i - 1], i2 = A.rr[i];
+            if (u64(A.rev[i1]) <= u64(P.start) + A.rm[i1] ||
+                u64(A.rev[i2]) <= u64(P.start) + A.rm[i2])
+              continue;
+            const u32 p1 = A.rev[i1] - A.rm[i1];
+            const u32 p2 = A.rev[i2] - A.rm[i2];
+            if (p2 <= p1) A.rm[i1] += (p1 - p2) + 1;
+          }
+        }
+      }
+      cta.sync();
+      // ---- fwd units, walked 5'->3': q'[k] = max(q[k], q'[k-1] + 1)  (negated: min-plus)
+      const u64 far_thr = u64(P.end) - 1 > mmax + n ? u64(P.end) - 1 - mmax - n : 0;
+      const u32 k_far = count_fwd_lt(far_thr);  // ranks [0, k_far) in parallel
+      MB_REGION(cta, tid) {
+        u32 lo, hi;
+        chunk(tid, k_far, &lo, &hi);
+        MinPlus acc = minplus_identity();
+        for (u32 k = lo; k < hi; ++k) {
+          const u32 idx = A.fr[k];
+          const i64 q = i64(A.fwd[idx]) + i64(A.fm[idx]);
+          acc = minplus_then(acc, MinPlus{-q, -1});
+        }
+        f[tid] = acc;
+      }
+      cta.exscan_minplus(f);
+      MB_REGION(cta, tid) {
+        u32 lo, hi;
+        chunk(tid, k_far, &lo, &hi);
+        i64 x = minplus_apply(f[tid], kMinPlusInf);
+        for (u32 k = lo; k < hi; ++k) {
+          const u32 idx = A.fr[k];
+          const i64 nq = -(i64(A.fwd[idx]) + i64(A.fm[idx]));
+          const i64 cap = x - 1;
+          x = nq < cap ? nq : cap;
+          A.fm[idx] = static_cast<u32>(-x - i64(A.fwd[idx]));
+        }
+      }
+      cta.sync();
+      MB_REGION(cta, tid) {
+        if (cta.leader(tid)) {
+          for (u32 i = (k_far > 1 ? k_far : 1); i < n; ++i) {
+            const u32 i1 = A.fr[i - 1], i2 = A.fr[i];
+            if (u64(A.fwd[i1]) + A.fm[i1] > u64(P.end) - 1 ||
+                u64(A.fwd[i2]) + A.fm[i2] > u64(P.end) - 1)
+              continue;
+            const u32 p1 = A.fwd[i1] + A.fm[i1];
+            const u32 p2 = A.fwd[i2] + A.fm[i2];
+            if (p1 >= p2) A.fm[i2] += (p1 - p2) + 1;
+          }
+        }
+      }
+      cta.sync();
+    }
+    MB_REGION(cta, tid) {
+      for (u32 i = tid; i < n; i += cta.nt()) {
+        const u32 rcap = A.rev[i] - P.start;
+        const u32 fcap = P.end - A.fwd[i] - 1;
+        if (A.rm[i] > rcap) A.rm[i] = rcap;
+        if (A.fm[i] > fcap) A.fm[i] = fcap;
+      }
+    }
+    cta.sync();
+  }
+
+  // generate_moves (simulation.cpp:299-330)
+  MB_FN void generate_moves() {
+    const bool done = S.burnin_completed != 0;
+    generate_moves_dir(A.rm, done ? P.rev_speed : P.rev_speed_burnin, P.rev_std);
+    generate_moves_dir(A.fm, done ? P.fwd_speed : P.fwd_speed_burnin, P.fwd_std);
+    adjust_and_clamp_moves();
+  }
+
+  // ExtrusionBarriers::next_state (extrusion_barriers.cpp:145-161): one canonical per barrier
+  MB_FN void next_barrier_states() {
+    if (P.n_bar == 0) return;
+    rng_ensure(S.rng_pos + P.n_bar);
+    const u64 base = S.rng_pos;
+    MB_REGION(cta, tid) {
+      for (u32 i = tid; i < P.n_bar; i += cta.nt()) {
+        const double u = canonical_raw(raw(base + i));
+        const bool act = A.bar_active[i] != 0;
+        if (!act && u > D.bar_stp_inactive[i]) {
+          A.bar_active[i] = 1;
+        } else if (act && u > D.bar_stp_active[i]) {
+          A.bar_active[i] = 0;
+        }
+      }
+      if (cta.leader(tid)) S.rng_pos = base + P.n_bar;
+    }
+    cta.sync();
+  }
+
+  MB_FN bool bar_blocks_rev(u32 b) const { return (D.bar_dir_rev[b >> 5] >> (b & 31)) & 1u; }
+
+  // ------------------------------------------------------------------------------ collisions
+  // detect_units_at_interval_boundaries (simulation_detect_collisions.cpp:25-120); leader only.
+  MB_FN void detect_boundaries_leader() {
+    const u32 n = S.num_active;
+    u32 n5 = 0, n3 = 0;
+    const u32 first_fwd_pos = A.fwd[A.fr[0]];
+    const u32 last_rev_pos = A.rev[A.rr[n - 1]];
+    for (u32 i = 0; i < n; ++i) {
+      const u32 idx = A.rr[i];
+      const u32 pos = A.rev[idx];
+      if (pos == P.start) {
+        ++n5;
+        A.rc[idx] = coll_make(5, kEvCollision | kEvChromBoundary);
+      } else if (pos > first_fwd_pos) {
+        break;
+      } else if (pos - A.rm[idx] == P.start) {
+        A.rc[idx] = coll_make(5, kEvCollision | kEvChromBoundary);
+        ++n5;
+        break;
+      }
+    }
+    for (u32 i = n - 1; i > 0; --i) {
+      const u32 idx = A.fr[i];
+      const u32 pos = A.fwd[idx];
+      if (pos == P.end - 1) {
+        ++n3;
+        A.fc[idx] = coll_make(3, kEvCollision | kEvChromBoundary);
+      } else if (pos < last_rev_pos) {
+        break;
+      } else if (pos + A.fm[idx] == P.end - 1) {
+        A.fc[idx] = coll_make(3, kEvCollision | kEvChromBoundary);
+        ++n3;
+        break;
+      }
+    }
+    S.n5 = n5;
+    S.n3 = n3;
+  }
+
+  // detect_lef_bar_collisions (simulation_detect_collisions.cpp:123-247). Every active barrier
+  // tests exactly one unit: the first rev unit downstream of it / the last fwd unit upstream of
+  // it; the closest successful barrier wins. Bernoulli draws (fractional pblock only) are taken
+  // in barrier order, rev pass (ascending) then fwd pass (descending).
+  MB_FN bool lef_bar_candidate_rev(u32 b, u32 j0, u32* unit) const {
+    const u32 n = S.num_active;
+    const u32 bp = A.bar_pos[b];
+    u32 j = count_rev_le(bp);  // first rank with pos > bp
+    if (j < j0) j = j0;
+    if (j >= n) return false;
+    const u32 idx = A.rr[j];
+    const u32 pos = A.rev[idx];
+    if (pos <= bp) return false;
+    *unit = idx;
+    return pos - bp <= A.rm[idx];
+  }
+  MB_FN bool lef_bar_candidate_fwd(u32 b, u32 jend, u32* unit) const {
+    const u32 bp = A.bar_pos[b];
+    const u32 c = count_fwd_lt(bp);  // ranks [0, c) have pos < bp
+    if (c == 0) return false;
+    u32 j = c - 1;
+    if (j > jend) j = jend;
+    const u32 idx = A.fr[j];
+    const u32 pos = A.fwd[idx];
+    if (pos >= bp) return false;
+    *unit = idx;
+    return bp - pos <= A.fm[idx];
+  }
+
+  MB_FN void detect_lef_bar_collisions() {
+    const u32 n = S.num_active, nb = P.n_bar;
+    if (nb == 0) return;
+    const u32 j0 = S.n5 ? S.n5 - 1 : 0;
+    const u32 sat3 = S.n3 ? S.n3 - 1 : 0;
+    const u32 jend = n - sat3 - 1;
+    const double pmaj = P.pblock_major, pmin = P.pblock_minor;
+    const bool frac_maj = pmaj != 0.0 && pmaj != 1.0;
+    const bool frac_min = pmin != 0.0 && pmin != 1.0;
+    const u32 tmp_ev = kEvTmp | kEvCollision | kEvLefBar;
+    if (!frac_maj && !frac_min) {
+      MB_REGION(cta, tid) {
+        for (u32 b = tid; b < nb; b += cta.nt()) {
+          if (!A.bar_active[b]) continue;
+          const bool brev = bar_blocks_rev(b);
+          u32 unit;
+          if ((brev ? pmaj : pmin) == 1.0 && lef_bar_candidate_rev(b, j0, &unit))
+            MB_ATOMIC_MAX_U32(&A.rc[unit], coll_make(b, tmp_ev));
+          if ((brev ? pmin : pmaj) == 1.0 && lef_bar_candidate_fwd(b, jend, &unit))
+            MB_ATOMIC_MAX_U32(&A.fc[unit], coll_make(nb - 1 - b, tmp_ev));
+        }
+      }
+      cta.sync();
+    } else {
+      // general case: count the trials that need a draw, prefix-sum, then run them in order
+      PerThread<u64> cnt(cta.nt());
+      for (int pass = 0; pass < 2; ++pass) {  // 0: rev (ascending b), 1: fwd (descending b)
+        MB_REGION(cta, tid) {
+          u32 lo, hi;
+          chunk(tid, nb, &lo, &hi);
+          u64 c = 0;
+          for (u32 t = lo; t < hi; ++t) {
+            const u32 b = pass == 0 ? t : nb - 1 - t;
+            if (!A.bar_active[b]) continue;
+            const bool brev = bar_blocks_rev(b);
+            const double pb = (pass == 0) == brev ? pmaj : pmin;
+            u32 unit;
+            const bool cand = pass == 0 ? lef_bar_candidate_rev(b, j0, &unit)
+                                        : lef_bar_candidate_fwd(b, jend, &unit);
+            if (cand && pb != 0.0 && pb != 1.0) ++c;
+          }
+          cnt[tid] = c;
+        }
+        const u64 total = cta.exscan_sum(cnt);
+        rng_ensure(S.rng_pos + total);
+        MB_REGION(cta, tid) {
+          u32 lo, hi;
+          chunk(tid, nb, &lo, &hi);
+          u64 o = S.rng_pos + cnt[tid];
+          for (u32 t = lo; t < hi; ++t) {
+            const u32 b = pass == 0 ? t : nb - 1 - t;
+            if (!A.bar_active[b]) continue;
+            const bool brev = bar_blocks_rev(b);
+            const double pb = (pass == 0) == brev ? pmaj : pmin;
+            u32 unit;
+            const bool cand = pass == 0 ? lef_bar_candidate_rev(b, j0, &unit)
+                                        : lef_bar_candidate_fwd(b, jend, &unit);
+            if (!cand) continue;
+            bool hit;
+            if (pb == 1.0) {
+              hit = true;
+            } else if (pb == 0.0) {
+              hit = false;
+            } else {
+              hit = bernoulli_raw(raw(o++), pb);
+            }
+            if (hit) {
+              if (pass == 0) {
+                MB_ATOMIC_MAX_U32(&A.rc[unit], coll_make(b, tmp_ev));
+              } else {
+                MB_ATOMIC_MAX_U32(&A.fc[unit], coll_make(nb - 1 - b, tmp_ev));
+              }
+            }
+          }
+        }
+        cta.sync();
+        MB_REGION(cta, tid) {
+          if (cta.leader(tid)) S.rng_pos += total;
+        }
+        cta.sync();
+      }
+    }
+    // strip the temporary marker (it made LEF-BAR hits win over boundary marks in atomicMax)
+    MB_REGION(cta, tid) {
+      for (u32 i = tid; i < n; i += cta.nt()) {
+        const u32 r = A.rc[i], f = A.fc[i];
+        if (r & 0x80000000u) A.rc[i] = coll_make(coll_index(r), kEvCollision | kEvLefBar);
+        if (f & 0x80000000u)
+          A.fc[i] = coll_make(nb - 1 - coll_index(f), kEvCollision | kEvLefBar);
+      }
+    }
+    cta.sync();
+  }
+
+  // compute_lef_lef_collision_pos (simulation.cpp:523-551) -> rev / fwd collision positions
+  MB_FN static void lef_lef_collision_pos(u32 rev_pos, u32 fwd_pos, u32 rev_move, u32 fwd_move,
+                                          u32* cp_rev, u32* cp_fwd) {
+    const u64 rel = u64(rev_move) + u64(fwd_move);
+    const double t = static_cast<double>(rev_pos - fwd_pos) / static_cast<double>(rel);
+    const u32 cp = fwd_pos + static_cast<u32>(round(static_cast<double>(fwd_move) * t));
+    if (cp == fwd_pos) {
+      *cp_rev = cp + 1;
+      *cp_fwd = cp;
+    } else {
+      *cp_rev = cp;
+      *cp_fwd = cp - 1;
+    }
+  }
+
+  // detect_primary_lef_lef_collisions (simulation_detect_collisions.cpp:250-397). The tested
+  // pairs are the places of the merged 5'->3' order where a fwd unit is directly followed by a
+  // rev unit; pairs are disjoint, so they are resolved independently. Bernoulli(1-bypass) draws
+  // go to the geometrically colliding pairs in ascending order.
+  MB_FN bool primary_pair(u32 j, u32 n5, u32 i2, u32* r_out, u32* f_out) const {
+    const u32 r = A.rr[j];
+    const u32 rp = A.rev[r];
+    // first fwd rank in [0, i2) with pos >= rp
+    u32 a = 0, b = i2;
+    while (a < b) {
+      const u32 m = (a + b) >> 1;
+      if (A.fwd[A.fr[m]] < rp) {
+        a = m + 1;
+      } else {
+        b = m;
+      }
+    }
+    if (a == i2 || a == 0) return false;
+    const u32 f = A.fr[a - 1];
+    if (j > n5 && A.rev[A.rr[j - 1]] > A.fwd[f]) return false;
+    const u32 delta = rp - A.fwd[f];
+    if (!(u64(delta) < u64(A.rm[r]) + u64(A.fm[f]))) return false;
+    *r_out = r;
+    *f_out = f;
+    return true;
+  }
+
+  MB_FN void primary_apply(u32 r, u32 f) const {
+    u32 cp_rev, cp_fwd;
+    lef_lef_collision_pos(A.rev[r], A.fwd[f], A.rm[r], A.fm[f], &cp_rev, &cp_fwd);
+    const u32 rcol = A.rc[r], fcol = A.fc[f];
+    const u32 hit_r = coll_make(f, kEvCollision | kEvPrimary);
+    const u32 hit_f = coll_make(r, kEvCollision | kEvPrimary);
+    if (!coll_occurred(rcol) && !coll_occurred(fcol)) {
+      A.rc[r] = hit_r;
+      A.fc[f] = hit_f;
+    } else if (coll_occurred(rcol) && !coll_occurred(fcol)) {
+      // the reference asserts LEF_BAR here; a boundary mark has index 5/3 and is read the same way
+      const u32 barrier_pos = A.bar_pos[coll_index(rcol)];
+      if (cp_fwd > barrier_pos) {
+        A.rc[r] = hit_r;
+        A.fc[f] = hit_f;
+      } else {
+        A.fc[f] = hit_f;
+      }
+    } else if (!coll_occurred(rcol) && coll_occurred(fcol)) {
+      const u32 barrier_pos = A.bar_pos[coll_index(fcol)];
+      A.rc[r] = hit_r;
+      if (cp_rev < barrier_pos) A.fc[f] = hit_f;
+    }
+  }
+
+  MB_FN void detect_primary_lef_lef_collisions() {
+    const u32 n = S.num_active;
+    const u32 n5 = S.n5, n3 = S.n3;
+    if (n5 == n || n3 == n) return;
+    const u32 i2 = n - (n3 ? n3 - 1 : 0);
+    const u32 M = n - n5;
+    const bool draws = P.p_bypass != 0.0;
+    PerThread<u64> cnt(cta.nt());
+    u64 total = 0;
+    if (draws) {
+      MB_REGION(cta, tid) {
+        u32 lo, hi;
+        chunk(tid, M, &lo, &hi);
+        u64 c = 0;
+        for (u32 m = lo; m < hi; ++m) {
+          u32 r, f;
+          c += primary_pair(n5 + m, n5, i2, &r, &f);
+        }
+        cnt[tid] = c;
+      }
+      total = cta.exscan_sum(cnt);
+      rng_ensure(S.rng_pos + total);
+    }
+    MB_REGION(cta, tid) {
+      u32 lo, hi;
+      chunk(tid, M, &lo, &hi);
+      u64 o = S.rng_pos + (draws ? cnt[tid] : 0);
+      for (u32 m = lo; m < hi; ++m) {
+        u32 r, f;
+        if (!primary_pair(n5 + m, n5, i2, &r, &f)) continue;
+        if (draws && !bernoulli_raw(raw(o++), 1.0 - P.p_bypass)) continue;
+        primary_apply(r, f);
+      }
+    }
+    cta.sync();
+    if (draws) {
+      MB_REGION(cta, tid) {
+        if (cta.leader(tid)) S.rng_pos += total;
+      }
+      cta.sync();
+    }
+  }
+
+  // correct_moves_for_lef_bar_collisions (simulation_correct_moves.cpp:19-50)
+  // correct_moves_for_primary_lef_lef_collisions (:53-121)
+  MB_FN void correct_moves() {
+    const u32 n = S.num_active;
+    MB_REGION(cta, tid) {
+      for (u32 i = tid; i < n; i += cta.nt()) {
+        if (coll_is(A.rc[i], kEvLefBar)) A.rm[i] = (A.rev[i] - A.bar_pos[coll_index(A.rc[i])]) - 1;
+        if (coll_is(A.fc[i], kEvLefBar)) A.fm[i] = (A.bar_pos[coll_index(A.fc[i])] - A.fwd[i]) - 1;
+      }
+    }
+    cta.sync();
+    MB_REGION(cta, tid) {
+      for (u32 r = tid; r < n; r += cta.nt()) {
+        if (!coll_is(A.rc[r], kEvPrimary)) continue;
+        const u32 f = coll_index(A.rc[r]);
+        if (coll_is(A.fc[f], kEvPrimary)) {
+          u32 p1, p2;
+          lef_lef_collision_pos(A.rev[r], A.fwd[f], A.rm[r], A.fm[f], &p1, &p2);
+          A.rm[r] = A.rev[r] - p1;
+          A.fm[f] = p2 - A.fwd[f];
+        } else if (coll_is(A.fc[f], kEvLefBar)) {
+          A.rm[r] = A.rev[r] - (A.fwd[f] + A.fm[f]) - 1;
+        }
+      }
+    }
+    cta.sync();
+    MB_REGION(cta, tid) {
+      for (u32 f = tid; f < n; f += cta.nt()) {
+        if (!coll_is(A.fc[f], kEvPrimary)) continue;
+        const u32 r = coll_index(A.fc[f]);
+        if (coll_is(A.rc[r], kEvLefBar)) A.fm[f] = (A.rev[r] - A.rm[r]) - A.fwd[f] - 1;
+      }
+    }
+    cta.sync();
+  }
+
+  // process_secondary_lef_lef_collisions (simulation_detect_collisions.cpp:400-515), one
+  // direction. Scan position m = 0..M-1 maps to rank `first + m` (rev pass, values as they are)
+  // or `first - m` (fwd pass, values negated) so that both passes read: a stalled unit at m-1
+  // stalls the free unit at m when  q[m] <= v[m-1],  after which  v[m] = min(pos[m], v[m-1]+1).
+  template <bool kRevPass>
+  MB_FN u32 sec_idx(u32 first, u32 m) const {
+    return kRevPass ? A.rr[first + m] : A.fr[first - m];
+  }
+  template <bool kRevPass>
+  MB_FN i64 sec_pos(u32 idx) const {
+    return kRevPass ? i64(A.rev[idx]) : -i64(A.fwd[idx]);
+  }
+  template <bool kRevPass>
+  MB_FN i64 sec_q(u32 idx) const {  // position after the unit's current move
+    return kRevPass ? i64(A.rev[idx]) - i64(A.rm[idx]) : -(i64(A.fwd[idx]) + i64(A.fm[idx]));
+  }
+
+  template <bool kRevPass>
+  MB_FN void secondary_pass(u32 first, u32 M) {
+    if (M < 2) return;
+    u32* coll = kRevPass ? A.rc : A.fc;
+    u32* moves = kRevPass ? A.rm : A.fm;
+    const bool draws = P.p_bypass != 0.0;
+    const u32 nwords = (M + 31) / 32 + 2;
+    u32* vbuf = A.scratch;                 // M words: v[m] + bias, 0 = "no live value"
+    u32* bits_fr = A.bits;                 // first-in-run flags of the potential candidates
+    u32* bits_fail = A.bits + nwords;      // failed-trial flags per draw
+    u32* bits_reached = A.bits + 2 * nwords;
+    u32* word_prefix = A.bits + 3 * nwords;  // reached candidates before each word
+    // stored value = v + bias, 0 = none: rev values are positions (>= 0), fwd values are negated
+    // positions (> -(2^32 - 1))
+    const i64 bias = kRevPass ? i64(1) : i64(0xFFFFFFFFll);
+
+    // scan 1: v[m]
+    PerThread<MinPlus> f(cta.nt());
+    MB_REGION(cta, tid) {
+      u32 lo, hi;
+      chunk(tid, M, &lo, &hi);
+      MinPlus acc = minplus_identity();
+      for (u32 m = lo; m < hi; ++m) {
+        const u32 idx = sec_idx<kRevPass>(first, m);
+        if (coll_occurred(coll[idx])) {
+          acc = minplus_then(acc, minplus_const(sec_q<kRevPass>(idx)));
+        } else {
+          acc = minplus_then(acc, MinPlus{sec_pos<kRevPass>(idx), 1});
+        }
+      }
+      f[tid] = acc;
+    }
+    cta.exscan_minplus(f);
+    const i64 none = -(i64(1) << 50);
+    MB_REGION(cta, tid) {
+      u32 lo, hi;
+      chunk(tid, M, &lo, &hi);
+      i64 x = minplus_apply(f[tid], none);
+      for (u32 m = lo; m < hi; ++m) {
+        const u32 idx = sec_idx<kRevPass>(first, m);
+        if (coll_occurred(coll[idx])) {
+          x = sec_q<kRevPass>(idx);
+        } else {
+          const i64 p = sec_pos<kRevPass>(idx);
+          x = p < x + 1 ? p : x + 1;
+        }
+        const i64 sv = x + bias;
+        vbuf[m] = sv >= 1 ? static_cast<u32>(sv) : 0u;
+      }
+      for (u32 w = tid; w < 4 * nwords; w += cta.nt()) A.bits[w] = 0;
+    }
+    cta.sync();
+    // scan 2: is the chain still alive at m-1?  key = last "event" at or before m:
+    // head (stalled unit) -> 2m+1, broken chain (free unit failing the geometric test) -> 2m
+    PerThread<u64> last(cta.nt());
+    auto geom_ok = [&](u32 m) -> bool {  // free unit m would reach / pass the unit at m-1
+      if (m == 0) return false;
+      const u32 vp = vbuf[m - 1];
+      if (vp == 0) return false;
+      const u32 idx = sec_idx<kRevPass>(first, m);
+      return sec_q<kRevPass>(idx) + bias <= i64(vp);
+    };
+    MB_REGION(cta, tid) {
+      u32 lo, hi;
+      chunk(tid, M, &lo, &hi);
+      u64 key = 0;
+      for (u32 m = lo; m < hi; ++m) {
+        const u32 idx = sec_idx<kRevPass>(first, m);
+        if (coll_occurred(coll[idx])) {
+          key = 2 * u64(m) + 1 + 2;
+        } else if (!geom_ok(m)) {
+          key = 2 * u64(m) + 2;
+        }
+      }
+      last[tid] = key;
+    }
+    // exclusive max-scan over threads through the min-plus algebra (b = 0, negated keys)
+    PerThread<MinPlus> g(cta.nt());
+    MB_REGION(cta, tid) { g[tid] = MinPlus{last[tid] ? -i64(last[tid]) : kMinPlusInf, 0}; }
+    cta.exscan_minplus(g);
+    // count the potential candidates per thread
+    PerThread<u64> cnt(cta.nt());
+    MB_REGION(cta, tid) {
+      u32 lo, hi;
+      chunk(tid, M, &lo, &hi);
+      u64 key = g[tid].a >= kMinPlusInf ? 0 : static_cast<u64>(-g[tid].a);
+      u64 c = 0;
+      for (u32 m = lo; m < hi; ++m) {
+        const u32 idx = sec_idx<kRevPass>(first, m);
+        if (coll_occurred(coll[idx])) {
+          key = 2 * u64(m) + 1 + 2;
+        } else if (!geom_ok(m)) {
+          key = 2 * u64(m) + 2;
+        } else if (key & 1) {
+          ++c;  // free unit, geometric test passed, chain alive since the last head
+        }
+      }
+      cnt[tid] = c;
+    }
+    const u64 npot = cta.exscan_sum(cnt);
+    if (npot == 0) return;
+    if (draws) {
+      rng_ensure(S.rng_pos + npot);
+      // first-in-run flags + failed-trial bitmap
+      MB_REGION(cta, tid) {
+        u32 lo, hi;
+        chunk(tid, M, &lo, &hi);
+        u64 key = g[tid].a >= kMinPlusInf ? 0 : static_cast<u64>(-g[tid].a);
+        u32 c = static_cast<u32>(cnt[tid]);
+        for (u32 m = lo; m < hi; ++m) {
+          const u32 idx = sec_idx<kRevPass>(first, m);
+          if (coll_occurred(coll[idx])) {
+            key = 2 * u64(m) + 1 + 2;
+          } else if (!geom_ok(m)) {
+            key = 2 * u64(m) + 2;
+          } else if (key & 1) {
+            // first of its run when the unit right before it is the head
+            if (key == 2 * u64(m - 1) + 1 + 2) MB_ATOMIC_OR_U32(&bits_fr[c >> 5], 1u << (c & 31));
+            ++c;
+          }
+        }
+        for (u32 d = tid; d < npot; d += cta.nt()) {
+          if (!bernoulli_raw(raw(S.rng_pos + d), 1.0 - P.p_bypass))
+            MB_ATOMIC_OR_U32(&bits_fail[d >> 5], 1u << (d & 31));
+        }
+      }
+      cta.sync();
+      // leader: walk the candidates. A candidate is reached when it is the first of its run or
+      // the previous one was reached and its trial succeeded; only reached candidates draw.
+      MB_REGION(cta, tid) {
+        if (cta.leader(tid)) {
+          u32 d = 0;       // draws consumed
+          u32 c = 0;       // candidate cursor
+          bool alive = false;
+          const u32 np = static_cast<u32>(npot);
+          while (c < np) {
+            const bool is_first = (bits_fr[c >> 5] >> (c & 31)) & 1u;
+            if (is_first || alive) {
+              bits_reached[c >> 5] |= 1u << (c & 31);
+              alive = !((bits_fail[d >> 5] >> (d & 31)) & 1u);
+              ++d;
+              ++c;
+            } else {
+              // dead chain: skip to the next first-in-run candidate
+              ++c;
+              while (c < np) {
+                const u32 w = bits_fr[c >> 5] >> (c & 31);
+                if (w) {
+                  c += static_cast<u32>(
+#if MB_DEVICE_BUILD
+                      __ffs(static_cast<int>(w)) - 1
+#else
+                      __builtin_ctz(w)
+#endif
+                  );
+                  break;
+                }
+                c = (c | 31u) + 1;
+              }
+            }
+          }
+          u32 acc = 0;
+          for (u32 w = 0; w < nwords; ++w) {
+            word_prefix[w] = acc;
+#if MB_DEVICE_BUILD
+            acc += static_cast<u32>(__popc(bits_reached[w]));
+#else
+            acc += static_cast<u32>(__builtin_popcount(bits_reached[w]));
+#endif
+          }
+          S.tmp_u32[4] = d;
+        }
+      }
+      cta.sync();
+    }
+    // apply
+    MB_REGION(cta, tid) {
+      u32 lo, hi;
+      chunk(tid, M, &lo, &hi);
+      u64 key = g[tid].a >= kMinPlusInf ? 0 : static_cast<u64>(-g[tid].a);
+      u32 c = static_cast<u32>(cnt[tid]);
+      for (u32 m = lo; m < hi; ++m) {
+        const u32 idx = sec_idx<kRevPass>(first, m);
+        if (coll_occurred(coll[idx])) {
+          key = 2 * u64(m) + 1 + 2;
+        } else if (!geom_ok(m)) {
+          key = 2 * u64(m) + 2;
+        } else if (key & 1) {
+          bool reached = true, ok = true;
+          if (draws) {
+            const u32 w = bits_reached[c >> 5];
+            reached = (w >> (c & 31)) & 1u;
+            if (reached) {
+#if MB_DEVICE_BUILD
+              const u32 before = word_prefix[c >> 5] + __popc(w & ((1u << (c & 31)) - 1));
+#else
+              const u32 before =
+                  word_prefix[c >> 5] + __builtin_popcount(w & ((1u << (c & 31)) - 1));
+#endif
+              ok = !((bits_fail[before >> 5] >> (before & 31)) & 1u);
+            }
+          }
+          if (reached) {
+            const u32 blocker = sec_idx<kRevPass>(first, m - 1);
+            if (ok) {
+              const i64 vprev = i64(vbuf[m - 1]) - bias;
+              const i64 mv = sec_pos<kRevPass>(idx) - vprev;  // distance to the blocker's site
+              moves[idx] = static_cast<u32>(mv > 0 ? mv - 1 : 0);
+              coll[idx] = coll_make(blocker, kEvCollision | kEvSecondary);
+            } else {
+              coll[idx] = coll_make(blocker, kEvSecondary);
+            }
+          }
+          ++c;
+        }
+      }
+    }
+    cta.sync();
+    if (draws) {
+      MB_REGION(cta, tid) {
+        if (cta.leader(tid)) S.rng_pos += S.tmp_u32[4];
+      }
+      cta.sync();
+    }
+  }
+
+  MB_FN void process_secondary_lef_lef_collisions() {
+    const u32 n = S.num_active;
+    const u32 k0 = S.n5 > 1 ? S.n5 : 1;
+    if (k0 < n) secondary_pass<true>(k0 - 1, n - (k0 - 1));
+    const u32 sat3 = S.n3 ? S.n3 - 1 : 0;
+    const u32 kf = n - sat3 - 1;  // rank the fwd pass starts from
+    secondary_pass<false>(kf, kf + 1);
+  }
+
+  // fix_secondary_lef_lef_collisions (simulation_detect_collisions.cpp:517-644). Avoided markers
+  // are never adjacent, so every marker touches its own pair of rank slots and LEFs.
+  MB_FN void fix_secondary_lef_lef_collisions() {
+    const u32 n = S.num_active;
+    const u32 k0 = S.n5 > 1 ? S.n5 : 1;
+    MB_REGION(cta, tid) {
+      for (u32 i = k0 + tid; i < n; i += cta.nt()) {
+        const u32 idx2 = A.rr[i];
+        if (!coll_avoided(A.rc[idx2], kEvSecondary)) continue;
+        const u32 idx1 = A.rr[i - 1];
+        const u32 pos1 = A.rev[idx1] - A.rm[idx1];
+        u32 mv2 = 0;
+        if (A.rev[idx2] > pos1 + 1) mv2 = A.rev[idx2] - (pos1 + 1);
+        const u32 c2 = coll_make(idx1, kEvCollision | kEvSecondary);
+        const u32 p1 = A.rev[idx1], p2 = A.rev[idx2];
+        A.rev[idx1] = A.fwd[idx1] < p2 ? A.fwd[idx1] : p2;
+        A.rev[idx2] = A.fwd[idx2] < p1 ? A.fwd[idx2] : p1;
+        // swap collisions, moves and rank slots
+        const u32 c1 = A.rc[idx1], m1 = A.rm[idx1];
+        A.rc[idx1] = c2;
+        A.rc[idx2] = c1;
+        A.rm[idx1] = mv2;
+        A.rm[idx2] = m1;
+        A.rr[i - 1] = static_cast<u16>(idx2);
+        A.rr[i] = static_cast<u16>(idx1);
+        const u32 cap1 = A.rev[idx1] - P.start, cap2 = A.rev[idx2] - P.start;
+        if (A.rm[idx1] > cap1) A.rm[idx1] = cap1;
+        if (A.rm[idx2] > cap2) A.rm[idx2] = cap2;
+      }
+    }
+    cta.sync();
+    const u32 sat3 = S.n3 ? S.n3 - 1 : 0;
+    const u32 naf = n - sat3;
+    MB_REGION(cta, tid) {
+      for (u32 i = tid; i + 1 < naf; i += cta.nt()) {
+        const u32 idx1 = A.fr[i];
+        if (!coll_avoided(A.fc[idx1], kEvSecondary)) continue;
+        const u32 idx2 = A.fr[i + 1];
+        const u32 pos2 = A.fwd[idx2] + A.fm[idx2];
+        u32 mv1 = 0;
+        if (pos2 > A.fwd[idx1] + 1) mv1 = pos2 - (A.fwd[idx1] + 1);
+        const u32 c1 = coll_make(idx2, kEvCollision | kEvSecondary);
+        const u32 p1 = A.fwd[idx1], p2 = A.fwd[idx2];
+        A.fwd[idx1] = A.rev[idx1] > p2 ? A.rev[idx1] : p2;
+        A.fwd[idx2] = A.rev[idx2] > p1 ? A.rev[idx2] : p1;
+        const u32 c2 = A.fc[idx2], m2 = A.fm[idx2];
+        A.fc[idx1] = c2;
+        A.fc[idx2] = c1;
+        A.fm[idx1] = m2;
+        A.fm[idx2] = mv1;
+        A.fr[i] = static_cast<u16>(idx2);
+        A.fr[i + 1] = static_cast<u16>(idx1);
+        const u32 cap1 = P.end - 1 - A.fwd[idx1], cap2 = P.end - 1 - A.fwd[idx2];
+        if (A.fm[idx1] > cap1) A.fm[idx1] = cap1;
+        if (A.fm[idx2] > cap2) A.fm[idx2] = cap2;
+      }
+    }
+    cta.sync();
+  }
+
+  // Simulation::process_collisions (simulation.cpp:763-793)
+  MB_FN void process_collisions(bool with_fix) {
+    const u32 n = S.num_active;
+    MB_REGION(cta, tid) {
+      for (u32 i = tid; i < n; i += cta.nt()) {
+        A.rc[i] = 0;
+        A.fc[i] = 0;
+      }
+    }
+    cta.sync();
+    MB_REGION(cta, tid) {
+      if (cta.leader(tid)) detect_boundaries_leader();
+    }
+    cta.sync();
+    detect_lef_bar_collisions();
+    detect_primary_lef_lef_collisions();
+    correct_moves();
+    process_secondary_lef_lef_collisions();
+    if (with_fix) fix_secondary_lef_lef_collisions();
+  }
+
+  // extrude (simulation.cpp:498-521) and release_lefs (:553-601)
+  MB_FN void extrude_and_release() {
+    const u32 n = S.num_active;
+    const double base_p = S.burnin_completed ? P.p_release : P.p_release_burnin;
+    const bool draws = base_p != 0.0;
+    if (draws) rng_ensure(S.rng_pos + n);
+    const u64 base = S.rng_pos;
+    MB_REGION(cta, tid) {
+      for (u32 i = tid; i < n; i += cta.nt()) {
+        u32 rev = A.rev[i] - A.rm[i];
+        u32 fwd = A.fwd[i] + A.fm[i];
+        u32 ep = A.ep[i];
+        if (draws) {
+          int hard = 0;
+          const u32 rcol = A.rc[i], fcol = A.fc[i];
+          if (coll_is(rcol, kEvLefBar) && bar_blocks_rev(coll_index(rcol))) ++hard;
+          if (coll_is(fcol, kEvLefBar) && !bar_blocks_rev(coll_index(fcol))) ++hard;
+          const double affinity =
+              hard == 0 ? 1.0 : (hard == 1 ? 1.0 / P.soft_mult : 1.0 / P.hard_mult);
+          if (bernoulli_raw(raw(base + i), affinity * base_p)) {
+            rev = kUnbound;
+            fwd = kUnbound;
+            ep = kUnbound;
+          }
+        }
+        A.rev[i] = rev;
+        A.fwd[i] = fwd;
+        A.ep[i] = ep;
+      }
+      if (cta.leader(tid) && draws) S.rng_pos = base + n;
+    }
+    cta.sync();
+  }
+
+  // ------------------------------------------------------------------------------ main loop
+  // Simulation::simulate_one_cell (simulation.cpp:896-986)
+  MB_FN void run() {
+    init_cell();
+    for (;;) {
+      bool stop;
+      if (!P.stop_on_epochs) {
+        stop = S.num_contacts >= task.target_contacts;
+      } else {
+        stop = S.epoch - S.num_burnin_epochs >= task.target_epochs;
+      }
+      if (stop || S.epoch >= P.debug_max_epochs || S.fault != 0) break;
+      cta.sync();
+      if (!S.burnin_completed) burnin_step();
+      if (S.fault != 0) break;
+      bind_lefs();
+      rank_lefs();
+      if (S.burnin_completed) {
+        sample_and_register_contacts();
+        if (task.target_contacts != 0 && S.num_contacts >= task.target_contacts) break;
+      }
+      generate_moves();
+      next_barrier_states();
+      process_collisions(true);
+      extrude_and_release();
+      MB_REGION(cta, tid) {
+        if (cta.leader(tid)) {
+          S.lef_updates += S.num_active;
+          ++S.epoch;
+        }
+      }
+      cta.sync();
+    }
+    cta.sync();
+  }
+};
+
+}  // namespace modle_b200

@@ -1,0 +1,178 @@
+"""ctypes bindings of the host-only half of the C ABI (no GPU needed)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libmodle_b200.so")
+_LIB = None
+
+
+class ModleB200Error(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"modle_b200 error {code}: {message}")
+        self.code = code
+
+
+def lib():
+    """Loads libmodle_b200.so; raises loudly when the CUDA extension has not been built."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(_LIB_PATH):
+            raise ImportError(
+                f"{_LIB_PATH} is missing: build it with `python -m modle_b200.build` "
+                "(modle_b200 has no CPU fallback)")
+        L = C.CDLL(_LIB_PATH)
+        u64p = C.POINTER(C.c_uint64)
+        P = C.POINTER(abi.SimParams)
+        L.modle_b200_abi_version.restype = C.c_int
+        L.modle_b200_last_error.restype = C.c_char_p
+        L.modle_b200_default_params.argtypes = [P]
+        L.modle_b200_default_params.restype = None
+        L.modle_b200_transform_params.argtypes = [P, C.c_int, C.c_int, C.c_int]
+        L.modle_b200_compute_num_lefs.argtypes = [P, C.c_uint64]
+        L.modle_b200_compute_num_lefs.restype = C.c_uint64
+        L.modle_b200_compute_contacts_per_epoch.argtypes = [P, C.c_uint64]
+        L.modle_b200_compute_contacts_per_epoch.restype = C.c_uint64
+        L.modle_b200_band_shape.argtypes = [P, C.c_uint64, u64p, u64p]
+        L.modle_b200_band_shape.restype = None
+        L.modle_b200_interval_hash.argtypes = [C.c_char_p, C.c_size_t, C.c_uint64, C.c_uint64,
+                                               C.c_uint64, C.c_uint64, u64p]
+        L.modle_b200_rng_seed.argtypes = [C.c_uint64, u64p]
+        L.modle_b200_rng_seed.restype = None
+        L.modle_b200_rng_next.argtypes = [u64p]
+        L.modle_b200_rng_next.restype = C.c_uint64
+        L.modle_b200_rng_jump.argtypes = [u64p]
+        L.modle_b200_rng_jump.restype = None
+        L.modle_b200_stp_active_from_occupancy.argtypes = [C.c_double, C.c_double]
+        L.modle_b200_stp_active_from_occupancy.restype = C.c_double
+        L.modle_b200_occupancy_from_stp.argtypes = [C.c_double, C.c_double]
+        L.modle_b200_occupancy_from_stp.restype = C.c_double
+        L.modle_b200_make_cell_tasks.argtypes = [P, C.c_char_p, C.c_size_t,
+                                                 C.POINTER(abi.Interval), C.c_void_p]
+        L.modle_b200_init.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+        L.modle_b200_destroy.argtypes = [C.c_void_p]
+        L.modle_b200_destroy.restype = None
+        L.modle_b200_synchronize.argtypes = [C.c_void_p]
+        L.modle_b200_kernel_launches.argtypes = [C.c_void_p]
+        L.modle_b200_kernel_launches.restype = C.c_uint64
+        L.modle_b200_simulate_interval.argtypes = [
+            C.c_void_p, P, C.POINTER(abi.Interval), C.c_void_p, C.c_size_t, C.c_void_p,
+            C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, u64p]
+        L.modle_b200_simulate_interval_device.argtypes = [
+            C.c_void_p, P, C.POINTER(abi.Interval), C.c_void_p, C.c_size_t, C.c_void_p,
+            C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.modle_b200_snapshot_cell.argtypes = [
+            C.c_void_p, P, C.POINTER(abi.Interval), C.c_void_p, C.c_size_t, C.c_void_p,
+            C.POINTER(abi.CellSnapshot), C.POINTER(abi.CellStats)]
+        L.modle_b200_register_contacts_device.argtypes = [
+            C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_void_p,
+            C.c_void_p, C.c_void_p]
+        _LIB = L
+    return _LIB
+
+
+EXPORTED_SYMBOLS = [
+    "modle_b200_abi_version", "modle_b200_last_error", "modle_b200_default_params",
+    "modle_b200_transform_params", "modle_b200_compute_num_lefs",
+    "modle_b200_compute_contacts_per_epoch", "modle_b200_band_shape", "modle_b200_interval_hash",
+    "modle_b200_rng_seed", "modle_b200_rng_next", "modle_b200_rng_jump",
+    "modle_b200_stp_active_from_occupancy", "modle_b200_occupancy_from_stp",
+    "modle_b200_make_cell_tasks", "modle_b200_init", "modle_b200_destroy",
+    "modle_b200_simulate_interval", "modle_b200_simulate_interval_device",
+    "modle_b200_synchronize", "modle_b200_snapshot_cell", "modle_b200_register_contacts_device",
+    "modle_b200_kernel_launches",
+]
+
+
+def check(rc):
+    if rc != 0:
+        raise ModleB200Error(rc, lib().modle_b200_last_error().decode(errors="replace"))
+
+
+def default_params():
+    p = abi.SimParams()
+    lib().modle_b200_default_params(C.byref(p))
+    return p
+
+
+def transform_params(p, rev_speed_given=False, fwd_speed_given=False,
+                     barrier_occupancy_given=False):
+    check(lib().modle_b200_transform_params(C.byref(p), int(rev_speed_given), int(fwd_speed_given),
+                                            int(barrier_occupancy_given)))
+    return p
+
+
+def compute_num_lefs(p, size_bp):
+    return int(lib().modle_b200_compute_num_lefs(C.byref(p), size_bp))
+
+
+def compute_contacts_per_epoch(p, num_lefs):
+    return int(lib().modle_b200_compute_contacts_per_epoch(C.byref(p), num_lefs))
+
+
+def band_shape(p, size_bp):
+    nrows, ncols = C.c_uint64(), C.c_uint64()
+    lib().modle_b200_band_shape(C.byref(p), size_bp, C.byref(nrows), C.byref(ncols))
+    return int(nrows.value), int(ncols.value)
+
+
+def interval_hash(name, chrom_size, start, end, seed):
+    out = C.c_uint64()
+    b = name.encode()
+    check(lib().modle_b200_interval_hash(b, len(b), chrom_size, start, end, seed, C.byref(out)))
+    return int(out.value)
+
+
+def rng_seed(seed):
+    st = (C.c_uint64 * 4)()
+    lib().modle_b200_rng_seed(seed, st)
+    return [int(x) for x in st]
+
+
+def rng_next(state):
+    st = (C.c_uint64 * 4)(*state)
+    v = lib().modle_b200_rng_next(st)
+    return int(v), [int(x) for x in st]
+
+
+def rng_jump(state):
+    st = (C.c_uint64 * 4)(*state)
+    lib().modle_b200_rng_jump(st)
+    return [int(x) for x in st]
+
+
+def make_cell_tasks(p, name, interval):
+    """Per-interval fan-out of Simulation::run_simulate (scheduler_simulate.cpp:104-160)."""
+    _, task_dt, _ = abi.np_dtypes()
+    tasks = np.zeros(int(p.num_cells), dtype=task_dt)
+    b = name.encode()
+    check(lib().modle_b200_make_cell_tasks(C.byref(p), b, len(b), C.byref(interval),
+                                           tasks.ctypes.data))
+    return tasks
+
+
+def barriers_from_records(records, p):
+    """BED-like records (pos, strand '+'/'-', score) -> barrier array, sorted by position.
+
+    Follows generate_barriers_from_bed_records / compute_barrier_stp
+    (src/libmodle/internal/genome.cpp:255-271,423-469) and, when
+    override_extrusion_barrier_occupancy is set, simulation.cpp:51-60.
+    """
+    barrier_dt, _, _ = abi.np_dtypes()
+    recs = sorted(records, key=lambda r: r[0])
+    out = np.zeros(len(recs), dtype=barrier_dt)
+    L = lib()
+    for i, (pos, strand, score) in enumerate(recs):
+        if p.override_extrusion_barrier_occupancy:
+            stp_a, stp_i = p.barrier_occupied_stp, p.barrier_not_occupied_stp
+        elif score != 0.0:
+            stp_i = p.barrier_not_occupied_stp
+            stp_a = L.modle_b200_stp_active_from_occupancy(stp_i, score)
+        else:
+            stp_a, stp_i = p.barrier_occupied_stp, p.barrier_not_occupied_stp
+        out[i] = (pos, stp_a, stp_i, abi.DIR_REV if strand == "+" else abi.DIR_FWD, 0)
+    return out

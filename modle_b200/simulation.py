@@ -1,0 +1,232 @@
+"""Host-side mirror of the slice of modle::Simulation that drives the hot path.
+
+Reference (paths relative to the reference checkout):
+  Simulation(Config) / run_simulate()          src/libmodle/cpu/simulation.cpp:93-115,
+                                               src/libmodle/cpu/scheduler_simulate.cpp:43-170
+  Task fan-out (seed, targets, jump per cell)  scheduler_simulate.cpp:104-160
+  worker -> simulate_one_cell                  scheduler_simulate.cpp:190-271
+
+Only the boundary is reproduced: the per-cell work itself runs in the CUDA library through the
+C ABI (include/modle_b200.h). Names follow the reference (Config fields, GenomicInterval,
+run_simulate); there is no CPU fallback.
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import abi, host
+
+
+class Config:
+    """modle::Config restricted to the fields the path reads (simulation_config.hpp:53-113).
+
+    Attribute access is forwarded to the underlying C struct, so names are the reference's.
+    `transform()` applies Cli::transform_args (src/modle/cli.cpp:993-1016).
+    """
+
+    def __init__(self, **overrides):
+        object.__setattr__(self, "_p", host.default_params())
+        object.__setattr__(self, "_given", set())
+        for k, v in overrides.items():
+            setattr(self, k, v)
+
+    def __getattr__(self, name):
+        return getattr(object.__getattribute__(self, "_p"), name)
+
+    def __setattr__(self, name, value):
+        p = object.__getattribute__(self, "_p")
+        if not hasattr(p, name):
+            raise AttributeError(f"modle::Config has no field '{name}' on the simulated path")
+        setattr(p, name, value)
+        object.__getattribute__(self, "_given").add(name)
+
+    def transform(self):
+        g = object.__getattribute__(self, "_given")
+        host.transform_params(self._p, "rev_extrusion_speed" in g, "fwd_extrusion_speed" in g,
+                              "extrusion_barrier_occupancy" in g)
+        return self
+
+    @property
+    def params(self):
+        return object.__getattribute__(self, "_p")
+
+
+@dataclass
+class GenomicInterval:
+    """modle::GenomicInterval (src/libmodle/internal/include/modle/genome.hpp:125-195)."""
+    chrom_name: str
+    chrom_size: int
+    start: int
+    end: int
+    barriers: np.ndarray = None  # abi barrier dtype, sorted by pos
+    num_lefs: int = 0
+    nrows: int = 0
+    ncols: int = 0
+    contacts: np.ndarray = None          # band, reference layout (nrows*ncols+1 uint32)
+    lef_1d_occupancy: np.ndarray = None  # ncols uint64
+    missed_updates: int = 0
+    stats: np.ndarray = None
+
+    def size(self):
+        return self.end - self.start
+
+    def npixels(self):
+        return self.nrows * self.ncols
+
+    def abi_interval(self):
+        return abi.Interval(self.chrom_size, self.start, self.end, self.num_lefs)
+
+
+class Context:
+    """RAII wrapper of modle_b200_context (one per GPU)."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        host.check(host.lib().modle_b200_init(C.byref(self._h), int(device)))
+        self.device = int(device)
+
+    def close(self):
+        if self._h:
+            host.lib().modle_b200_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def synchronize(self):
+        host.check(host.lib().modle_b200_synchronize(self._h))
+
+    def kernel_launches(self):
+        return int(host.lib().modle_b200_kernel_launches(self._h))
+
+    # -- HOST buffers in, HOST buffers out (the reference-facing call) -----------------------
+    def simulate_interval(self, params, interval, barriers, tasks, band=None, occ1d=None):
+        _, _, stats_dt = abi.np_dtypes()
+        nrows, ncols = host.band_shape(params, int(interval.end - interval.start))
+        if band is None:
+            band = np.zeros(nrows * ncols + 1, dtype=np.uint32)
+        if occ1d is None:
+            occ1d = np.zeros(ncols, dtype=np.uint64)
+        stats = np.zeros(len(tasks), dtype=stats_dt)
+        missed = C.c_uint64(0)
+        barriers = np.ascontiguousarray(barriers)
+        tasks = np.ascontiguousarray(tasks)
+        rc = host.lib().modle_b200_simulate_interval(
+            self._h, C.byref(params), C.byref(interval),
+            barriers.ctypes.data if len(barriers) else None, len(barriers), tasks.ctypes.data,
+            len(tasks), band.ctypes.data, occ1d.ctypes.data, stats.ctypes.data, C.byref(missed))
+        host.check(rc)
+        return band, occ1d, stats, int(missed.value)
+
+    # -- device-resident buffers (raw device pointers, e.g. torch tensors' data_ptr()) --------
+    def simulate_interval_device(self, params, interval, barriers_host, d_tasks, num_cells, d_band,
+                                 d_occ1d, d_stats, d_missed, stream=None):
+        barriers_host = np.ascontiguousarray(barriers_host)
+        rc = host.lib().modle_b200_simulate_interval_device(
+            self._h, C.byref(params), C.byref(interval),
+            barriers_host.ctypes.data if len(barriers_host) else None, len(barriers_host),
+            C.c_void_p(d_tasks), num_cells, C.c_void_p(d_band),
+            C.c_void_p(d_occ1d) if d_occ1d else None, C.c_void_p(d_stats) if d_stats else None,
+            C.c_void_p(d_missed), C.c_void_p(stream) if stream else None)
+        host.check(rc)
+
+    def register_contacts_device(self, d_bin1, d_bin2, n, nrows, ncols, d_band, d_missed,
+                                 stream=None):
+        rc = host.lib().modle_b200_register_contacts_device(
+            self._h, C.c_void_p(d_bin1), C.c_void_p(d_bin2), n, nrows, ncols, C.c_void_p(d_band),
+            C.c_void_p(d_missed), C.c_void_p(stream) if stream else None)
+        host.check(rc)
+
+    def snapshot_cell(self, params, interval, barriers, task):
+        n = int(interval.num_lefs)
+        nb = len(barriers)
+        arrs = {k: np.zeros(n, dtype=np.uint64)
+                for k in ("rev_pos", "fwd_pos", "binding_epoch", "rev_ranks", "fwd_ranks")}
+        arrs["barrier_active"] = np.zeros(max(nb, 1), dtype=np.uint8)
+        snap = abi.CellSnapshot()
+        for k, v in arrs.items():
+            ptr_t = C.POINTER(C.c_uint8 if k == "barrier_active" else C.c_uint64)
+            setattr(snap, k, v.ctypes.data_as(ptr_t))
+        st = abi.CellStats()
+        barriers = np.ascontiguousarray(barriers)
+        task = np.ascontiguousarray(task)
+        rc = host.lib().modle_b200_snapshot_cell(
+            self._h, C.byref(params), C.byref(interval),
+            barriers.ctypes.data if nb else None, nb, task.ctypes.data, C.byref(snap),
+            C.byref(st))
+        host.check(rc)
+        arrs["barrier_active"] = arrs["barrier_active"][:nb]
+        arrs["num_active_lefs"] = int(snap.num_active_lefs)
+        arrs["burnin_completed"] = int(snap.burnin_completed)
+        arrs["stats"] = {f: int(getattr(st, f)) for f, _ in abi.CellStats._fields_}
+        return arrs
+
+
+@dataclass
+class Simulation:
+    """modle::Simulation: owns the Config and the genome, `run_simulate()` runs every interval.
+
+    `genome` is a list of (chrom_name, chrom_size, start, end, barrier_records) where
+    barrier_records are (pos, strand, score) tuples (what Genome's ctor derives from the
+    chrom.sizes file, the optional genomic-intervals BED and the barrier BED,
+    src/libmodle/internal/genome.cpp:299-330).
+
+    Work is sharded over `world_size` processes (one per GPU) by whole intervals, heaviest
+    first; `rank` processes only its own intervals.
+    """
+    config: Config
+    genome: list
+    device: int = 0
+    rank: int = 0
+    world_size: int = 1
+    intervals: list = field(default_factory=list)
+
+    def __post_init__(self):
+        p = self.config.params
+        for name, size, start, end, records in self.genome:
+            iv = GenomicInterval(name, size, start, end)
+            iv.barriers = host.barriers_from_records(
+                [r for r in records if start <= r[0] < end], p)
+            iv.num_lefs = host.compute_num_lefs(p, end - start)
+            iv.nrows, iv.ncols = host.band_shape(p, end - start)
+            self.intervals.append(iv)
+
+    def partition(self):
+        """Cost-weighted assignment of whole intervals to ranks (longest-processing-time first)."""
+        order = sorted(range(len(self.intervals)), key=lambda i: -self.intervals[i].num_lefs)
+        load = [0] * self.world_size
+        owner = {}
+        for i in order:
+            r = min(range(self.world_size), key=lambda k: load[k])
+            owner[i] = r
+            load[r] += self.intervals[i].num_lefs
+        return owner
+
+    def run_simulate(self, ctx=None):
+        p = self.config.params
+        own_ctx = ctx is None
+        if own_ctx:
+            ctx = Context(self.device)
+        owner = self.partition()
+        try:
+            for idx, iv in enumerate(self.intervals):
+                if owner[idx] != self.rank:
+                    continue
+                # intervals without barriers are skipped (scheduler_simulate.cpp:111-124)
+                if len(iv.barriers) == 0:
+                    continue
+                tasks = host.make_cell_tasks(p, iv.chrom_name, iv.abi_interval())
+                iv.contacts, iv.lef_1d_occupancy, iv.stats, iv.missed_updates = \
+                    ctx.simulate_interval(p, iv.abi_interval(), iv.barriers, tasks)
+        finally:
+            if own_ctx:
+                ctx.close()
+        return self.intervals
