@@ -1494,6 +1494,9 @@ struct CellSim {
     if (n5 == n || n3 == n) return;
     const u32 i2 = n - (n3 ? n3 - 1 : 0);
     const u32 M = n - n5;
+    // run_lef_lef_collision_trial (simulation_impl.hpp:93-96): no draw when bypass == 0 (always
+    // collide) and none when 1 - bypass == 0 (Bernoulli(0) never draws and never succeeds)
+    if (P.p_bypass != 0.0 && 1.0 - P.p_bypass == 0.0) return;
     const bool draws = P.p_bypass != 0.0;
     PerThread<u64> cnt(cta.nt());
     u64 total = 0;
@@ -1589,7 +1592,8 @@ struct CellSim {
     if (M < 2) return;
     u32* coll = kRevPass ? A.rc : A.fc;
     u32* moves = kRevPass ? A.rm : A.fm;
-    const bool draws = P.p_bypass != 0.0;
+    const bool never = P.p_bypass != 0.0 && 1.0 - P.p_bypass == 0.0;  // trials fail, no draws
+    const bool draws = P.p_bypass != 0.0 && !never;
     const u32 nwords = (M + 31) / 32 + 2;
     u32* vbuf = A.scratch;                 // M words: v[m] + bias, 0 = "no live value"
     u32* bits_fr = A.bits;                 // first-in-run flags of the potential candidates
@@ -1773,7 +1777,10 @@ struct CellSim {
           key = 2 * u64(m) + 2;
         } else if (key & 1) {
           bool reached = true, ok = true;
-          if (draws) {
+          if (never) {
+            reached = key == 2 * u64(m - 1) + 1 + 2;  // only the first unit behind a head
+            ok = false;
+          } else if (draws) {
             const u32 w = bits_reached[c >> 5];
             reached = (w >> (c & 31)) & 1u;
             if (reached) {

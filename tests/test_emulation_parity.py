@@ -1,0 +1,149 @@
+"""The data-parallel restatement used by the CUDA kernel (modle_b200/csrc/sim_core.hpp), run on
+the CPU through tests/emu, must agree bit for bit with the sequential oracle: LEF trajectories,
+ranks, barrier states, RNG draw counts, epochs, band matrix, 1D occupancy."""
+import numpy as np
+import pytest
+
+import emu_lib
+from common import make_case, results_equal
+from oracle import pyoracle
+
+CASES = {
+    "defaults_small": dict(size=3_000_000, ncells=4, target_contact_density=0.01),
+    "large_staging": dict(size=3_000_000, ncells=3, target_contact_density=0.01, _staging=2,
+                          _vt=96),
+    "more_barriers": dict(size=8_000_000, ncells=3, nbar=150, target_contact_density=0.02,
+                          _vt=128),
+    "no_bypass": dict(size=5_000_000, ncells=3, nbar=90, target_contact_density=0.02,
+                      probability_of_extrusion_unit_bypass=0.0),
+    "fractional_pblock": dict(size=5_000_000, ncells=3, nbar=90, target_contact_density=0.02,
+                              lef_bar_major_collision_pblock=0.8,
+                              lef_bar_minor_collision_pblock=0.1),
+    "lef_density_x4": dict(size=5_000_000, ncells=2, nbar=300, target_contact_density=0.02,
+                           number_of_lefs_per_mbp=80, probability_of_extrusion_unit_bypass=0.01),
+    "epochs_criterion": dict(size=5_000_000, ncells=3, nbar=90, stopping_criterion=1,
+                             target_simulation_epochs=50),
+    "skip_burnin": dict(size=5_000_000, ncells=3, nbar=90, skip_burnin=1,
+                        target_contact_density=0.02),
+    "loop_only_no_noise": dict(size=4_000_000, ncells=2, nbar=60, target_contact_density=0.01,
+                               contact_sampling_strategy=4),
+    "tad_only": dict(size=4_000_000, ncells=2, nbar=60, target_contact_density=0.01,
+                     contact_sampling_strategy=3),
+    "no_1d_track": dict(size=4_000_000, ncells=2, nbar=60, target_contact_density=0.01,
+                        track_1d_lef_position=0),
+    "sub_interval": dict(size=9_000_000, start=2_000_000, end=6_500_000, ncells=2, nbar=70,
+                         target_contact_density=0.02),
+    "narrow_band_missed_updates": dict(size=4_000_000, ncells=2, nbar=20, diagonal_width=20_000,
+                                       target_contact_density=0.5),
+    "constant_speed": dict(size=4_000_000, ncells=2, nbar=60, target_contact_density=0.01,
+                           rev_extrusion_speed_std=0.0, fwd_extrusion_speed_std=0.0),
+    "max_burnin_forced": dict(size=4_000_000, ncells=2, nbar=60, target_contact_density=0.01,
+                              max_burnin_epochs=150),
+    "tiny_interval": dict(size=120_000, ncells=3, nbar=3, target_contact_density=0.05),
+    "no_barriers": dict(size=2_000_000, ncells=2, nbar=0, target_contact_density=0.01),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_emulation_matches_oracle(name):
+    kw = dict(CASES[name])
+    vt = kw.pop("_vt", 64)
+    staging = kw.pop("_staging", 0)
+    p, iv, bars, tasks = make_case(**kw)
+    a = pyoracle.simulate_interval(p, iv, bars, tasks, nthreads=4)
+    b = emu_lib.simulate_interval(p, iv, bars, tasks, virtual_threads=vt, staging=staging)
+    assert b[2]["device_fault"].max() == 0
+    assert results_equal(a, b) == []
+    assert int(a[0].sum()) + a[3] == int(a[2]["num_contacts"].sum())
+
+
+def test_1kb_bins_long_sampling_phase():
+    p, iv, bars, tasks = make_case(size=3_000_000, ncells=1, nbar=60, bin_size=1000,
+                                   target_contact_density=0.005)
+    a = pyoracle.simulate_interval(p, iv, bars, tasks)
+    b = emu_lib.simulate_interval(p, iv, bars, tasks, virtual_threads=77)
+    assert results_equal(a, b) == []
+
+
+@pytest.mark.parametrize("epochs", [1, 2, 7, 40, 250])
+def test_per_epoch_state_matches_oracle(epochs):
+    p, iv, bars, tasks = make_case(size=6_000_000, ncells=1, nbar=110)
+    p.debug_max_epochs = epochs
+    a = pyoracle.snapshot_cell(p, iv, bars, tasks[0:1])
+    b = emu_lib.snapshot_cell(p, iv, bars, tasks[0:1], virtual_threads=33)
+    for k in a:
+        if isinstance(a[k], np.ndarray):
+            assert np.array_equal(a[k], b[k]), k
+        else:
+            assert a[k] == b[k], k
+
+
+def test_virtual_cta_width_does_not_matter():
+    p, iv, bars, tasks = make_case(size=3_000_000, ncells=2, nbar=50, target_contact_density=0.01)
+    ref = emu_lib.simulate_interval(p, iv, bars, tasks, virtual_threads=1)
+    for vt in (2, 31, 64, 257):
+        assert results_equal(ref, emu_lib.simulate_interval(p, iv, bars, tasks,
+                                                           virtual_threads=vt)) == []
+
+
+def _random_state(rng, n, nb, size, speed):
+    rev = rng.integers(0, size, n)
+    span = rng.integers(0, max(2, size // max(n, 1)) * 2, n)
+    fwd = np.minimum(rev + span, size - 1)
+    for i in range(n):
+        if rng.random() < 0.1 and i > 0:
+            j = rng.integers(0, i)
+            if rng.random() < 0.5:
+                rev[i] = rev[j]
+                fwd[i] = max(fwd[i], rev[i])
+            else:
+                fwd[i] = fwd[j]
+                rev[i] = min(rev[i], fwd[i])
+        if rng.random() < 0.03:
+            rev[i] = 0
+        if rng.random() < 0.03:
+            fwd[i] = size - 1
+    ep = rng.integers(0, 5, n)
+    rr, fr = pyoracle.rank_lefs(rev, fwd, ep, np.arange(n), np.arange(n), init_buffers=True)
+    rm = np.maximum(0, np.round(rng.normal(speed, speed * 0.3, n))).astype(np.int64)
+    fm = np.maximum(0, np.round(rng.normal(speed, speed * 0.3, n))).astype(np.int64)
+    bp = np.sort(rng.choice(size, nb, replace=False)) if nb else np.zeros(0, dtype=np.int64)
+    return rev, fwd, ep, rr, fr, rm, fm, bp, rng.integers(1, 3, nb), \
+        (rng.random(nb) < 0.8).astype(np.uint8)
+
+
+ALL_STEPS = ["adjust", "clamp", "boundaries", "lef_bar", "primary", "correct_lef_bar",
+             "correct_primary", "secondary", "fix_secondary"]
+
+
+@pytest.mark.parametrize("bypass,pmaj,pmin", [(0.0, 1.0, 0.0), (0.1, 1.0, 0.0), (0.3, 0.7, 0.2),
+                                              (1.0, 1.0, 1.0)])
+def test_collision_pipeline_fuzz(bypass, pmaj, pmin):
+    """Random dense layouts (ties, units at both interval ends, inactive barriers): the kernel's
+    scans must reproduce the sequential pipeline including the number of RNG draws."""
+    for seed in range(400):
+        rng = np.random.default_rng(seed)
+        n = int(rng.integers(1, 60))
+        nb = int(rng.integers(0, 30))
+        size = int(rng.choice([300, 2000, 20000]))
+        st = _random_state(rng, n, nb, size, size / 40)
+        kw = dict(prob_bypass=bypass, pblock_major=pmaj, pblock_minor=pmin, rng_seed=seed)
+        a = pyoracle.collision_steps(ALL_STEPS, 0, size, *st, **kw)
+        b = emu_lib.collision_steps(ALL_STEPS, 0, size, *st, virtual_threads=1 + seed % 9, **kw)
+        assert b["fault"] == 0
+        for k in ("rev", "fwd", "rr", "fr", "rm", "fm", "rc", "fc", "n5", "n3", "ndraws"):
+            assert np.array_equal(a[k], b[k]), (seed, k)
+
+
+def test_rank_lefs_fuzz_with_ties():
+    for seed in range(300):
+        rng = np.random.default_rng(1000 + seed)
+        n = int(rng.integers(2, 80))
+        rev = rng.integers(0, 40, n)
+        fwd = rev + rng.integers(0, 10, n)
+        ep = rng.integers(0, 3, n)
+        rr0 = rng.permutation(n)
+        fr0 = rng.permutation(n)
+        a = pyoracle.rank_lefs(rev, fwd, ep, rr0, fr0)
+        b = emu_lib.rank_lefs(rev, fwd, ep, rr0, fr0)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), seed

@@ -1,0 +1,155 @@
+"""`-m gpu`: the CUDA path, called through the C ABI, against the CPU oracle on the same seeded
+inputs (bit-exact: every quantity is integer), plus size-independent properties at the full
+BASELINE C1 size."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from common import make_case, results_equal
+from oracle import pyoracle
+
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    "defaults_small": dict(size=3_000_000, ncells=8, target_contact_density=0.01),
+    "many_small_cells": dict(size=1_500_000, ncells=700, nbar=25, target_contact_density=0.05),
+    "more_barriers": dict(size=8_000_000, ncells=6, nbar=150, target_contact_density=0.02),
+    "no_bypass": dict(size=5_000_000, ncells=5, nbar=90, target_contact_density=0.02,
+                      probability_of_extrusion_unit_bypass=0.0),
+    "always_bypass": dict(size=5_000_000, ncells=3, nbar=90, target_contact_density=0.02,
+                          probability_of_extrusion_unit_bypass=1.0),
+    "fractional_pblock": dict(size=5_000_000, ncells=5, nbar=90, target_contact_density=0.02,
+                              lef_bar_major_collision_pblock=0.8,
+                              lef_bar_minor_collision_pblock=0.1),
+    "c4_high_collision": dict(size=12_000_000, ncells=4, nbar=800, target_contact_density=0.01,
+                              number_of_lefs_per_mbp=80,
+                              probability_of_extrusion_unit_bypass=0.01),
+    "epochs_criterion": dict(size=5_000_000, ncells=5, nbar=90, stopping_criterion=1,
+                             target_simulation_epochs=50),
+    "skip_burnin": dict(size=5_000_000, ncells=5, nbar=90, skip_burnin=1,
+                        target_contact_density=0.02),
+    "loop_only_no_noise": dict(size=4_000_000, ncells=4, nbar=60, target_contact_density=0.01,
+                               contact_sampling_strategy=4),
+    "tad_only": dict(size=4_000_000, ncells=4, nbar=60, target_contact_density=0.01,
+                     contact_sampling_strategy=3),
+    "no_1d_track": dict(size=4_000_000, ncells=4, nbar=60, target_contact_density=0.01,
+                        track_1d_lef_position=0),
+    "sub_interval": dict(size=9_000_000, start=2_000_000, end=6_500_000, ncells=4, nbar=70,
+                         target_contact_density=0.02),
+    "narrow_band_missed_updates": dict(size=4_000_000, ncells=4, nbar=20, diagonal_width=20_000,
+                                       target_contact_density=0.5),
+    "constant_speed": dict(size=4_000_000, ncells=4, nbar=60, target_contact_density=0.01,
+                           rev_extrusion_speed_std=0.0, fwd_extrusion_speed_std=0.0),
+    "max_burnin_forced": dict(size=4_000_000, ncells=4, nbar=60, target_contact_density=0.01,
+                              max_burnin_epochs=150),
+    "tiny_interval": dict(size=120_000, ncells=5, nbar=3, target_contact_density=0.05),
+    "no_barriers": dict(size=2_000_000, ncells=3, nbar=0, target_contact_density=0.01),
+    "c5_1kb_bins": dict(size=3_000_000, ncells=2, nbar=60, bin_size=1000,
+                        target_contact_density=0.005),
+    "c1_chr20_shape": dict(size=64_444_167, ncells=6, nbar=1132, target_contact_density=0.002,
+                           name="chr20"),
+    "c3_chr1_shape": dict(size=248_956_422, ncells=3, nbar=3518, target_contact_density=0.0004,
+                          name="chr1"),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_cuda_matches_oracle(gpu_ctx, name):
+    p, iv, bars, tasks = make_case(**CASES[name])
+    a = pyoracle.simulate_interval(p, iv, bars, tasks, nthreads=8)
+    b = gpu_ctx.simulate_interval(p, iv, bars, tasks)
+    assert b[2]["device_fault"].max() == 0
+    assert results_equal(a, b) == []
+
+
+@pytest.mark.parametrize("epochs", [1, 3, 60, 400])
+def test_cuda_per_epoch_state_matches_oracle(gpu_ctx, epochs):
+    """LEF positions, binding epochs, both rank permutations, barrier states and the number of
+    raw RNG draws after a fixed number of epochs."""
+    p, iv, bars, tasks = make_case(size=20_000_000, ncells=1, nbar=350)
+    p.debug_max_epochs = epochs
+    a = pyoracle.snapshot_cell(p, iv, bars, tasks[0:1])
+    b = gpu_ctx.snapshot_cell(p, iv, bars, tasks[0:1])
+    for k in a:
+        if isinstance(a[k], np.ndarray):
+            assert np.array_equal(a[k], b[k]), k
+        else:
+            assert a[k] == b[k], k
+
+
+def test_c1_full_size_properties(gpu_ctx):
+    """BASELINE config C1 (chr20 shape, 512 cells, density 1): properties that do not need the
+    oracle at full size, plus an oracle check of a sample of cells."""
+    p, iv, bars, tasks = make_case(size=64_444_167, ncells=512, nbar=1132, name="chr20")
+    band, occ, stats, missed = gpu_ctx.simulate_interval(p, iv, bars, tasks)
+    assert stats["device_fault"].max() == 0
+    # every cell hits its contact target exactly; the band holds all of them
+    assert np.array_equal(stats["num_contacts"], tasks["num_target_contacts"])
+    assert int(band.astype(np.uint64).sum()) + missed == int(stats["num_contacts"].sum())
+    assert int(stats["num_contacts"].sum()) == 600 * 12889
+    assert band[-1] == 0  # the reference's +1 slack element is never written
+    # 1D occupancy: two increments per successful event, never more than 2 per sampling event
+    assert int(occ.sum()) % 2 == 0 and int(occ.sum()) <= 2 * int(stats["num_contacts"].sum()) + 2 * 206 * 512
+    assert (stats["num_epochs"] > stats["num_burnin_epochs"] - 5).all()
+    # determinism: a second run is identical
+    band2, occ2, stats2, missed2 = gpu_ctx.simulate_interval(p, iv, bars, tasks)
+    assert results_equal((band, occ, stats, missed), (band2, occ2, stats2, missed2)) == []
+    # independence of the cell batch: cells 100..103 alone give the same per-cell stats
+    sub = gpu_ctx.simulate_interval(p, iv, bars, tasks[100:104])
+    for f in ("num_contacts", "num_epochs", "num_burnin_epochs", "num_rng_draws"):
+        assert np.array_equal(sub[2][f], stats[f][100:104])
+    ora = pyoracle.simulate_interval(p, iv, bars, tasks[100:104], nthreads=4)
+    assert results_equal(ora, sub) == []
+
+
+def test_results_accumulate_into_caller_buffers(gpu_ctx):
+    p, iv, bars, tasks = make_case(size=3_000_000, ncells=4, target_contact_density=0.01)
+    band, occ, stats, missed = gpu_ctx.simulate_interval(p, iv, bars, tasks)
+    band2 = band.copy()
+    occ2 = occ.copy()
+    gpu_ctx.simulate_interval(p, iv, bars, tasks, band=band2, occ1d=occ2)
+    assert np.array_equal(band2, 2 * band) and np.array_equal(occ2, 2 * occ)
+
+
+def test_register_contacts_kernel(gpu_ctx):
+    import torch
+
+    rng = np.random.default_rng(3)
+    nrows, ncols = 50, 4000
+    n = 1_000_003
+    b1 = rng.integers(0, ncols, n, dtype=np.uint32)
+    b2 = np.clip(b1.astype(np.int64) + rng.integers(-70, 70, n), 0, ncols - 1).astype(np.uint32)
+    i = np.abs(b1.astype(np.int64) - b2.astype(np.int64))
+    j = np.maximum(b1, b2).astype(np.int64)
+    ok = i < nrows
+    expect = np.bincount(j[ok] * nrows + i[ok], minlength=nrows * ncols + 1).astype(np.uint32)
+    d1 = torch.from_numpy(b1.view(np.int32)).cuda()
+    d2 = torch.from_numpy(b2.view(np.int32)).cuda()
+    band = torch.zeros(nrows * ncols + 1, dtype=torch.int32, device="cuda")
+    missed = torch.zeros(1, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    gpu_ctx.register_contacts_device(d1.data_ptr(), d2.data_ptr(), n, nrows, ncols,
+                                     band.data_ptr(), missed.data_ptr())
+    gpu_ctx.synchronize()
+    assert np.array_equal(band.cpu().numpy().view(np.uint32), expect)
+    assert int(missed.item()) == int((~ok).sum())
+
+
+def test_unsupported_inputs_fail_loudly(gpu_ctx):
+    from modle_b200.host import ModleB200Error
+
+    p, iv, bars, tasks = make_case(size=3_000_000, ncells=2)
+    bad = bars.copy()
+    bad["pos"][0] = iv.end + 5
+    with pytest.raises(ModleB200Error):
+        gpu_ctx.simulate_interval(p, iv, bad, tasks)
+    unsorted = bars[::-1].copy()
+    with pytest.raises(ModleB200Error):
+        gpu_ctx.simulate_interval(p, iv, unsorted, tasks)
+    # an interval whose per-cell state cannot live in shared memory is refused, not degraded
+    p2, iv2, bars2, tasks2 = make_case(size=248_956_422, ncells=1, nbar=100,
+                                       number_of_lefs_per_mbp=100)
+    with pytest.raises(ModleB200Error) as e:
+        gpu_ctx.simulate_interval(p2, iv2, bars2, tasks2)
+    assert e.value.code in (-4,)

@@ -1,0 +1,144 @@
+"""Host half of the C ABI: symbol table, parameter derivation (Cli::transform_args), geometry,
+seeding and task fan-out, checked against the values SURVEY.md derives from the reference and
+against the oracle's independent restatement. No GPU needed."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from modle_b200 import abi, host
+from oracle import pyoracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(product_lib):
+    header = open(os.path.join(ROOT, "include", "modle_b200.h")).read()
+    declared = set(re.findall(r"\b(modle_b200_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(host.EXPORTED_SYMBOLS)
+    for name in declared:
+        assert hasattr(product_lib, name), name
+    assert product_lib.modle_b200_abi_version() == 1
+
+
+def test_struct_layouts_match_header(product_lib):
+    # sizes implied by the header (all members 8-byte aligned except the trailing u32 block)
+    assert C.sizeof(abi.Interval) == 32
+    assert C.sizeof(abi.Barrier) == 32
+    assert C.sizeof(abi.CellTask) == 56
+    assert C.sizeof(abi.CellStats) == 48
+    p = host.default_params()
+    assert p.bin_size == 5000 and p.num_cells == 512 and p.debug_max_epochs == abi.U64_MAX
+    assert p.contact_sampling_strategy == 7 and p.track_1d_lef_position == 1
+
+
+def test_no_gpu_means_loud_failure(product_lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    h = C.c_void_p()
+    rc = product_lib.modle_b200_init(C.byref(h), 0)
+    assert rc == abi.ERR_NO_DEVICE
+    assert b"no CPU fallback" in product_lib.modle_b200_last_error()
+
+
+def test_transform_defaults_5kb(product_lib):
+    p = host.transform_params(host.default_params())
+    assert p.rev_extrusion_speed == 4000 and p.fwd_extrusion_speed == 4000
+    assert p.rev_extrusion_speed_std == 200.0 and p.fwd_extrusion_speed_std == 200.0
+    assert p.prob_of_lef_release == 8000 / 300000
+    assert p.burnin_target_epochs_for_lef_activation == 187
+    assert p.probability_of_extrusion_unit_bypass == 0.1
+    assert p.lef_bar_major_collision_pblock == 1.0 and p.lef_bar_minor_collision_pblock == 0.0
+    assert p.barrier_not_occupied_stp == 0.70
+    assert abs(p.extrusion_barrier_occupancy - 0.3 / 1.3) < 1e-15  # from stp 0.0 / 0.7
+    assert p.tad_to_loop_contact_ratio == 5.0
+
+
+def test_transform_1kb_normalises_probabilities(product_lib):
+    p = host.default_params()
+    p.bin_size = 1000
+    host.transform_params(p)
+    assert p.rev_extrusion_speed == 800 and p.rev_extrusion_speed_std == 40.0
+    assert abs(p.prob_of_lef_release - 1600 / 300000) < 1e-18
+    assert p.burnin_target_epochs_for_lef_activation == 937
+    # ratio 1600/8000 = 0.2
+    assert abs(p.barrier_not_occupied_stp - 0.7 ** 0.2) < 1e-12
+    assert abs(p.probability_of_extrusion_unit_bypass - 0.02) < 1e-15
+    assert p.lef_bar_major_collision_pblock == 1.0 and p.lef_bar_minor_collision_pblock == 0.0
+
+
+def test_transform_strategy_and_stopping(product_lib):
+    p = host.default_params()
+    p.contact_sampling_strategy = abi.SAMPLE_LOOP | abi.SAMPLE_NOISIFY
+    p.stopping_criterion = abi.STOP_SIMULATION_EPOCHS
+    host.transform_params(p)
+    assert p.tad_to_loop_contact_ratio == 0.0 and p.target_contact_density == -1
+    p = host.default_params()
+    p.contact_sampling_strategy = abi.SAMPLE_TAD
+    host.transform_params(p)
+    assert np.isinf(p.tad_to_loop_contact_ratio)
+    p = host.default_params()
+    p.extrusion_barrier_occupancy = 0.9
+    host.transform_params(p, barrier_occupancy_given=True)
+    assert p.override_extrusion_barrier_occupancy == 1
+    assert abs(host.lib().modle_b200_occupancy_from_stp(p.barrier_occupied_stp, 0.7) - 0.9) < 1e-12
+
+
+@pytest.mark.parametrize("name,size,nlefs,ncols,cpe", [
+    ("chr20", 64444167, 1289, 12889, 206), ("chr1", 248956422, 4979, 49792, 797)])
+def test_interval_derived_sizes(product_lib, name, size, nlefs, ncols, cpe):
+    p = host.transform_params(host.default_params())
+    assert host.compute_num_lefs(p, size) == nlefs == pyoracle.compute_num_lefs(20.0, size)
+    assert host.band_shape(p, size) == (600, ncols)
+    assert host.compute_contacts_per_epoch(p, nlefs) == cpe
+
+
+def test_seeding_matches_oracle_and_python_xxhash(product_lib):
+    xxhash = pytest.importorskip("xxhash")
+    for name, size, start, end, seed in [("chr20", 64444167, 0, 64444167, 0),
+                                         ("chrX_some_long_name" * 4, 10**8, 5, 10**7, 99)]:
+        key = name.encode() + b"".join(int(v).to_bytes(8, "little") for v in (size, start, end))
+        h = host.interval_hash(name, size, start, end, seed)
+        assert h == xxhash.xxh3_64_intdigest(key, seed=seed)
+        assert h == pyoracle.interval_hash(name, size, start, end, seed)
+    st = host.rng_seed(12345)
+    assert st == pyoracle.rng_seed(12345)
+    assert host.rng_jump(st) == pyoracle.rng_jump(st)
+    assert host.rng_next(st) == pyoracle.rng_next(st)
+
+
+def test_task_fanout_matches_oracle(product_lib):
+    p = host.transform_params(host.default_params())
+    p.num_cells = 37
+    p.seed = 7
+    iv = abi.Interval(64444167, 0, 64444167, 1289)
+    t1 = host.make_cell_tasks(p, "chr20", iv)
+    t2 = pyoracle.make_cell_tasks(p, "chr20", iv)
+    assert np.array_equal(t1, t2)
+    tot = round(600 * 12889 * 1.0)
+    assert t1["num_target_contacts"].sum() == tot
+    assert t1["num_target_contacts"][0] == -(-tot // 37)
+    # cell k's engine is the interval engine after k jumps (scheduler_simulate.cpp:143-158)
+    st = host.rng_seed(host.interval_hash("chr20", 64444167, 0, 64444167, 7))
+    for k in range(3):
+        assert list(t1["rng_state"][k]) == st
+        st = host.rng_jump(st)
+    # low density over many cells: trailing cells get 0 contacts and are skipped
+    p.num_cells = 512
+    p.target_contact_density = 0.00001
+    t = host.make_cell_tasks(p, "chr20", iv)
+    assert t["num_target_contacts"].sum() == round(600 * 12889 * 0.00001)
+    assert (t["num_target_contacts"] == 0).sum() > 0
+
+
+def test_barrier_records_to_stp(product_lib):
+    p = host.transform_params(host.default_params())
+    b = host.barriers_from_records([(500, "-", 0.9), (100, "+", 0.0), (300, "+", 0.8)], p)
+    assert list(b["pos"]) == [100, 300, 500]
+    assert list(b["blocking_direction"]) == [abi.DIR_REV, abi.DIR_REV, abi.DIR_FWD]
+    assert b["stp_active"][0] == p.barrier_occupied_stp
+    occ = host.lib().modle_b200_occupancy_from_stp(b["stp_active"][1], b["stp_inactive"][1])
+    assert abs(occ - 0.8) < 1e-12
