@@ -218,7 +218,11 @@ def run_ours(args, rank, world, local_rank):
             d_missed=torch.zeros(1, dtype=torch.int64, device=dev))
         mine.append(entry)
     mine.sort(key=lambda e: -e["iv"].num_lefs)
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream: the C ABI treats a NULL stream handle as "the context's own
+    # stream", and the timing events must sit on the stream the kernels are launched on
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
 
     def step_device(events=None):
         for e in mine:

@@ -100,6 +100,8 @@ struct Cta {
   MB_FN int step() const { return static_cast<int>(blockDim.x); }
   MB_FN bool leader(int tid) const { return tid == 0; }
   MB_FN void sync() const { __syncthreads(); }
+  // x / nt(); the launcher only uses power-of-two CTA widths
+  MB_FN u32 div_nt(u32 x) const { return x >> (31 - __clz(static_cast<int>(blockDim.x))); }
 
   // exclusive prefix sum of one u64 per thread; *total receives the CTA-wide sum
   MB_FN u64 exscan_sum(int tid, u64 v, u64* total) const {
@@ -252,6 +254,7 @@ struct Cta {
   int step() const { return 1; }
   bool leader(int tid) const { return tid == 0; }
   void sync() const {}
+  u32 div_nt(u32 x) const { return x / static_cast<u32>(nthreads); }
 
   u64 exscan_sum(PerThread<u64>& v) const {
     u64 acc = 0;

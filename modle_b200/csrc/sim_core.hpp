@@ -100,10 +100,10 @@ struct CellSim {
   CellTaskDev task;
 
   // ------------------------------------------------------------------------------ helpers
+  // [lo, hi): thread tid's contiguous share of n items (n < 2^16, tid < 2^10: no overflow)
   MB_FN void chunk(int tid, u32 n, u32* lo, u32* hi) const {
-    const u64 nt = static_cast<u64>(cta.nt());
-    *lo = static_cast<u32>(static_cast<u64>(n) * static_cast<u64>(tid) / nt);
-    *hi = static_cast<u32>(static_cast<u64>(n) * (static_cast<u64>(tid) + 1) / nt);
+    *lo = cta.div_nt(n * static_cast<u32>(tid));
+    *hi = cta.div_nt(n * (static_cast<u32>(tid) + 1));
   }
   MB_FN void fault(u32 code) const {
     if (S.fault == 0) S.fault = code;  // benign race: any code is reported
@@ -712,19 +712,10 @@ struct CellSim {
     return prev_slot[a] < prev_slot[b];
   }
 
-  MB_FN void rank_lefs() {
+  // Full sort of both rank arrays (first epoch of --skip-burnin, or whenever the incremental
+  // path below finds its assumptions violated). prev_r / prev_f: previous slot of every LEF.
+  MB_FN void rank_lefs_full(const u16* prev_r, const u16* prev_f) {
     const u32 n = S.num_active;
-    if (n < 2) return;
-    // scratch areas that are dead at this point of the epoch: moves and collision words
-    u16* prev_r = reinterpret_cast<u16*>(A.rc);  // previous slot of every LEF in the rev order
-    u16* prev_f = reinterpret_cast<u16*>(A.fc);
-    MB_REGION(cta, tid) {
-      for (u32 k = tid; k < n; k += cta.nt()) {
-        prev_r[A.rr[k]] = static_cast<u16>(k);
-        prev_f[A.fr[k]] = static_cast<u16>(k);
-      }
-    }
-    cta.sync();
 #if MB_DEVICE_BUILD
     u32 npad = 1;
     while (npad < n) npad <<= 1;
@@ -774,6 +765,212 @@ struct CellSim {
     std::sort(A.rr, A.rr + n, [&](u16 a, u16 b) { return rank_less<true>(a, b, prev_r); });
     std::sort(A.fr, A.fr + n, [&](u16 a, u16 b) { return rank_less<false>(a, b, prev_f); });
 #endif
+  }
+
+  // number of elements of the sorted list `lst` (length m) that order before LEF `x`
+  template <bool kRev>
+  MB_FN u32 count_less(const u16* lst, u32 m, u32 x, const u16* prev_slot) const {
+    u32 a = 0, b = m;
+    while (a < b) {
+      const u32 mid = (a + b) >> 1;
+      if (rank_less<kRev>(lst[mid], x, prev_slot)) {
+        a = mid + 1;
+      } else {
+        b = mid;
+      }
+    }
+    return a;
+  }
+
+  // rank_lefs (simulation.cpp:410-496). extrude() keeps the relative order of the LEFs that were
+  // not (re)bound this epoch, so the new permutation is the old one minus the changed LEFs,
+  // merged with the few changed ones: compact the unchanged LEFs, rank the changed ones among
+  // themselves by counting and among the unchanged ones by binary search, then place everything.
+  // The result is verified (adjacent pairs under the total order); ties that extrude() created
+  // between unchanged LEFs are repaired by odd-even transposition passes, and anything else
+  // (more changed LEFs than the scratch holds, a still unsorted list) takes the full sort.
+  MB_FN void rank_lefs() {
+    const u32 n = S.num_active;
+    if (n < 2) return;
+    // scratch areas that are dead at this point of the epoch: moves, collision words, scratch
+    u16* prev_r = reinterpret_cast<u16*>(A.rc);  // previous slot of every LEF in the rev order
+    u16* prev_f = reinterpret_cast<u16*>(A.fc);
+    const u32 cur = static_cast<u32>(S.epoch);
+    u32 max_changed = static_cast<u32>(cell_scratch_words(P.n_lefs, P.n_bar) / 4);
+    if (max_changed > 512) max_changed = 512;
+    PerThread<u64> cnt(cta.nt());
+    MB_REGION(cta, tid) {
+      u32 lo, hi;
+      chunk(tid, n, &lo, &hi);
+      u64 c = 0;
+      for (u32 k = lo; k < hi; ++k) {
+        const u32 r = A.rr[k], f = A.fr[k];
+        prev_r[r] = static_cast<u16>(k);
+        prev_f[f] = static_cast<u16>(k);
+        c += A.ep[r] == cur;
+        c += u64(A.ep[f] == cur) << 32;
+      }
+      cnt[tid] = c;
+      if (cta.leader(tid)) S.tmp_u32[5] = 0;
+    }
+    const u64 tot = cta.exscan_sum(cnt);
+    const u32 nc = static_cast<u32>(tot & 0xFFFFFFFFu);
+    if (nc > max_changed) {
+      rank_lefs_full(prev_r, prev_f);
+      return;
+    }
+    if (nc != 0) rank_lefs_merge(cnt, nc, prev_r, prev_f);
+    // Verify / repair: units can legitimately cross during extrude() (a unit is not tested
+    // against the unit behind an avoided secondary collision) and new ties need their epoch
+    // order, so run odd-even transposition passes until one finds nothing to swap.
+    constexpr u32 kRepairPasses = 8;
+    for (u32 pass = 0; pass < kRepairPasses; ++pass) {
+      for (u32 parity = 0; parity < 2; ++parity) {
+        MB_REGION(cta, tid) {
+          bool swapped = false;
+          for (u32 k = parity + 2 * static_cast<u32>(tid); k + 1 < n; k += 2 * cta.nt()) {
+            const u16 a = A.rr[k], b = A.rr[k + 1];
+            if (rank_less<true>(b, a, prev_r)) {
+              A.rr[k] = b;
+              A.rr[k + 1] = a;
+              swapped = true;
+            }
+            const u16 c = A.fr[k], d = A.fr[k + 1];
+            if (rank_less<false>(d, c, prev_f)) {
+              A.fr[k] = d;
+              A.fr[k + 1] = c;
+              swapped = true;
+            }
+          }
+          if (swapped) S.tmp_u32[5 + (pass & 1)] = 1;
+          // the other flag was last read before this pass's first barrier: safe to reset now
+          if (parity == 1 && cta.leader(tid)) S.tmp_u32[5 + ((pass + 1) & 1)] = 0;
+        }
+        cta.sync();
+      }
+      if (S.tmp_u32[5 + (pass & 1)] == 0) return;
+    }
+    cta.sync();
+    rank_lefs_full(prev_r, prev_f);
+  }
+
+  // The merge step of rank_lefs: cnt = per-thread exclusive counts of changed LEFs (rev order in
+  // the low word, fwd order in the high word), nc = number of changed LEFs.
+  MB_FN void rank_lefs_merge(const PerThread<u64>& cnt, u32 nc, const u16* prev_r,
+                             const u16* prev_f) {
+    const u32 n = S.num_active;
+    const u32 cur = static_cast<u32>(S.epoch);
+    u16* un_r = reinterpret_cast<u16*>(A.rm);  // [0, nu): unchanged LEFs in their old order
+    u16* un_f = reinterpret_cast<u16*>(A.fm);
+    u16* ch_r = un_r + n;  // [0, nc): changed LEFs in their old order
+    u16* ch_f = un_f + n;
+    const u32 nu = n - nc;
+    u32* rank_r = A.scratch;            // [nc] rank of each changed LEF among the changed ones
+    u32* rank_f = A.scratch + nc;
+    u16* pos_r = reinterpret_cast<u16*>(A.scratch + 2 * nc);  // [nc] unchanged LEFs before it
+    u16* pos_f = pos_r + nc;
+    u16* ts_r = pos_f + nc;  // [nc] pos_* ordered by rank_*
+    u16* ts_f = ts_r + nc;
+    MB_REGION(cta, tid) {
+      u32 lo, hi;
+      chunk(tid, n, &lo, &hi);
+      u32 cr = static_cast<u32>(cnt[tid] & 0xFFFFFFFFu), cf = static_cast<u32>(cnt[tid] >> 32);
+      for (u32 k = lo; k < hi; ++k) {
+        const u16 r = A.rr[k], f = A.fr[k];
+        if (A.ep[r] == cur) {
+          ch_r[cr++] = r;
+        } else {
+          un_r[k - cr] = r;
+        }
+        if (A.ep[f] == cur) {
+          ch_f[cf++] = f;
+        } else {
+          un_f[k - cf] = f;
+        }
+      }
+      for (u32 j = tid; j < 2 * nc; j += cta.nt()) A.scratch[j] = 0;
+    }
+    cta.sync();
+    // work items: (changed LEF j, segment s of the changed list) -> partial rank; then one
+    // binary search over the unchanged list per changed LEF; rev order first, then fwd
+    u32 nseg = static_cast<u32>(cta.nt()) / (2 * nc);
+    if (nseg < 1) nseg = 1;
+    if (nseg > nc) nseg = nc;
+    const u32 per_dir = nc * nseg + nc;
+    MB_REGION(cta, tid) {
+      for (u32 w = tid; w < 2 * per_dir; w += cta.nt()) {
+        const bool is_rev = w < per_dir;
+        const u32 v = is_rev ? w : w - per_dir;
+        const u16* ch = is_rev ? ch_r : ch_f;
+        if (v < nc * nseg) {
+          const u32 j = v / nseg, s = v % nseg;
+          const u32 a = s * nc / nseg, b = (s + 1) * nc / nseg;
+          const u32 x = ch[j];
+          u32 c = 0;
+          if (is_rev) {
+            for (u32 q = a; q < b; ++q) c += rank_less<true>(ch[q], x, prev_r);
+          } else {
+            for (u32 q = a; q < b; ++q) c += rank_less<false>(ch[q], x, prev_f);
+          }
+          if (c) MB_ATOMIC_ADD_U32(is_rev ? &rank_r[j] : &rank_f[j], c);
+        } else {
+          const u32 j = v - nc * nseg;
+          if (is_rev) {
+            pos_r[j] = static_cast<u16>(count_less<true>(un_r, nu, ch[j], prev_r));
+          } else {
+            pos_f[j] = static_cast<u16>(count_less<false>(un_f, nu, ch[j], prev_f));
+          }
+        }
+      }
+    }
+    cta.sync();
+    MB_REGION(cta, tid) {
+      for (u32 j = tid; j < nc; j += cta.nt()) {
+        ts_r[rank_r[j]] = pos_r[j];
+        ts_f[rank_f[j]] = pos_f[j];
+        A.rr[rank_r[j] + pos_r[j]] = ch_r[j];
+        A.fr[rank_f[j] + pos_f[j]] = ch_f[j];
+      }
+    }
+    cta.sync();
+    // unchanged LEF number u lands at slot u + #{changed LEFs with pos <= u}
+    MB_REGION(cta, tid) {
+      u32 lo, hi;
+      chunk(tid, nu, &lo, &hi);
+      if (lo < hi) {
+        u32 jr = 0, jf = 0;
+        {
+          u32 a = 0, b = nc;
+          while (a < b) {
+            const u32 m = (a + b) >> 1;
+            if (ts_r[m] <= lo) {
+              a = m + 1;
+            } else {
+              b = m;
+            }
+          }
+          jr = a;
+          a = 0;
+          b = nc;
+          while (a < b) {
+            const u32 m = (a + b) >> 1;
+            if (ts_f[m] <= lo) {
+              a = m + 1;
+            } else {
+              b = m;
+            }
+          }
+          jf = a;
+        }
+        for (u32 u = lo; u < hi; ++u) {
+          while (jr < nc && ts_r[jr] <= u) ++jr;
+          while (jf < nc && ts_f[jf] <= u) ++jf;
+          A.rr[u + jr] = un_r[u];
+          A.fr[u + jf] = un_f[u];
+        }
+      }
+    }
+    cta.sync();
   }
 
   // ------------------------------------------------------------------------------ contacts
