@@ -107,6 +107,9 @@ def build_workload(name, cells):
     elif name == "c3":
         cfg, genome = workloads.config_c3(cells or 8192)
         desc = "C3 chr1 shape, %d cells, 5 kb bins, default parameters"
+    elif name == "c4":
+        cfg, genome = workloads.config_c4(cells or 512)
+        desc = "C4 high-collision: chr20 size, 80 LEFs/Mbp, barriers 1/15 kb, bypass 0.01, %d cells"
     else:
         cfg, genome = workloads.config_c2(cells or 512)
         desc = "C2 GRCh38 genome-wide shape (24 chromosomes, 38,815 synthetic barriers), " \
@@ -115,11 +118,21 @@ def build_workload(name, cells):
 
 
 # ------------------------------------------------------------------------------- CPU (oracle)
-def oracle_sample_run(cfg, genome, cells_per_interval, nthreads_total):
-    """Simulates the first `cells_per_interval` cells of every interval with the CPU oracle,
-    intervals in parallel. Returns (lef_updates, seconds, cores_used)."""
-    from concurrent.futures import ThreadPoolExecutor
+def cpu_sample_cells(cfg, genome, cores, target_seconds=10.0, lu_per_core_s=4.5e6):
+    """Cells per interval for the bounded CPU sample: a multiple of the core count sized for
+    about `target_seconds` of wall time (the oracle does ~4-5 M LEF-updates/s per core)."""
+    from modle_b200 import host
 
+    p = cfg.params
+    lu_per_cell = sum(host.compute_num_lefs(p, e - s) for _, _, s, e, _ in genome) * 545.0
+    k = max(1, int(round(target_seconds * lu_per_core_s / lu_per_cell)))
+    return max(1, min(int(cfg.num_cells), cores * k))
+
+
+def oracle_sample_run(cfg, genome, cells_per_interval, nthreads_total):
+    """Simulates the first `cells_per_interval` cells of every interval with the CPU oracle, one
+    interval after the other, cells spread over `nthreads_total` threads (the reference's
+    one-cell-per-worker-thread layout). Returns (lef_updates, seconds, cores_used)."""
     from modle_b200 import abi, host
     from oracle import pyoracle
 
@@ -130,17 +143,14 @@ def oracle_sample_run(cfg, genome, cells_per_interval, nthreads_total):
         bars = host.barriers_from_records(recs, p)
         tasks = host.make_cell_tasks(p, name, iv)[:cells_per_interval]
         jobs.append((iv, bars, tasks))
-    per_job = max(1, min(cells_per_interval, nthreads_total // max(1, len(jobs))
-                         if len(jobs) < nthreads_total else 1))
-    workers = max(1, min(len(jobs), nthreads_total // per_job))
     pyoracle.lib()
+    used = max(1, min(nthreads_total, cells_per_interval))
     t0 = time.perf_counter()
-    with ThreadPoolExecutor(max_workers=workers) as ex:
-        res = list(ex.map(lambda j: pyoracle.simulate_interval(p, j[0], j[1], j[2],
-                                                               nthreads=per_job), jobs))
+    res = [pyoracle.simulate_interval(p, iv, bars, tasks, nthreads=used)
+           for iv, bars, tasks in jobs]
     dt = time.perf_counter() - t0
     lu = sum(int(r[2]["num_lef_updates"].sum()) for r in res)
-    return lu, dt, min(nthreads_total, workers * per_job)
+    return lu, dt, used
 
 
 def run_reference(args, rank, world):
@@ -149,7 +159,7 @@ def run_reference(args, rank, world):
     cfg, genome, desc = build_workload(args.workload, args.cells)
     cores = os.cpu_count() or 1
     # bounded sample: every interval, a few cells each (work scales with the core count)
-    cpi = max(1, min(int(cfg.num_cells), -(-2 * cores // max(1, len(genome)))))
+    cpi = cpu_sample_cells(cfg, genome, cores)
     sample = f"first {cpi} cell(s) of each of the {len(genome)} intervals of the workload per step"
     for _ in range(args.warmup):
         oracle_sample_run(cfg, genome, cpi, cores)
@@ -177,8 +187,8 @@ def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
 
-    from modle_b200 import abi, build, host
-    from modle_b200.simulation import Context, Simulation
+    from modle_b200 import abi, build, distributed, host
+    from modle_b200.simulation import Simulation
 
     build.build()
     if not torch.cuda.is_available():
@@ -190,60 +200,58 @@ def run_ours(args, rank, world, local_rank):
     cfg, genome, desc = build_workload(args.workload, args.cells)
     p = cfg.params
     sim = Simulation(cfg, genome, device=local_rank, rank=rank, world_size=world)
-    split_cells = len(sim.intervals) < world  # e.g. c3: one chromosome, cells split over ranks
-    owner = sim.partition()
-    ctx = Context(local_rank)
+    engine = distributed.DeviceEngine(local_rank, num_streams=args.streams)
+    ctx = engine.ctx
     barrier_dt, task_dt, stats_dt = abi.np_dtypes()
+    shards = distributed.plan_shards(
+        [iv.num_lefs if len(iv.barriers) else 0 for iv in sim.intervals], int(p.num_cells), world)
+    roots = distributed.interval_roots(shards)
+    split = sorted(i for i, (_, ranks) in roots.items() if len(ranks) > 1)
 
     # ---- stage my share of the work on the device ------------------------------------------
+    bufs = {}   # interval -> (band, occ, missed)
     mine = []
-    for idx, iv in enumerate(sim.intervals):
-        if len(iv.barriers) == 0:
-            continue
-        tasks = host.make_cell_tasks(p, iv.chrom_name, iv.abi_interval())
-        if split_cells:
-            tasks = tasks[rank::world]
-        elif owner[idx] != rank:
-            continue
-        if len(tasks) == 0:
-            continue
-        npx = iv.nrows * iv.ncols + 1
+    for s in sorted((s for s in shards if s.rank == rank), key=lambda s: (-s.weight, s.interval)):
+        iv = sim.intervals[s.interval]
+        if s.interval not in bufs:
+            bufs[s.interval] = engine.alloc_outputs(iv.nrows, iv.ncols)
+        tasks = host.make_cell_tasks(p, iv.chrom_name, iv.abi_interval())[s.cell_lo:s.cell_hi]
         h_tasks = torch.from_numpy(tasks.view(np.uint8).reshape(-1).copy()).pin_memory()
-        entry = dict(
-            iv=iv, abi_iv=iv.abi_interval(), ntasks=len(tasks), h_tasks_np=tasks,
-            h_tasks=h_tasks, d_tasks=h_tasks.to(dev),
-            d_band=torch.zeros(npx, dtype=torch.int32, device=dev),
-            d_occ=torch.zeros(iv.ncols, dtype=torch.int64, device=dev),
-            d_stats=torch.zeros(len(tasks) * stats_dt.itemsize, dtype=torch.uint8, device=dev),
-            d_missed=torch.zeros(1, dtype=torch.int64, device=dev))
-        mine.append(entry)
-    mine.sort(key=lambda e: -e["iv"].num_lefs)
-    # a real (non-default) stream: the C ABI treats a NULL stream handle as "the context's own
-    # stream", and the timing events must sit on the stream the kernels are launched on
-    stream = torch.cuda.Stream(device=dev)
-    torch.cuda.set_stream(stream)
-    assert stream.cuda_stream != 0
+        mine.append(dict(iv=iv, idx=s.interval, abi_iv=iv.abi_interval(), ntasks=len(tasks),
+                         d_tasks=h_tasks.to(dev),
+                         d_stats=torch.zeros(len(tasks) * stats_dt.itemsize, dtype=torch.uint8,
+                                             device=dev)))
+    for idx in split:  # a rank without a piece of a split interval contributes zeros to its reduce
+        if idx not in bufs:
+            bufs[idx] = engine.alloc_outputs(sim.intervals[idx].nrows, sim.intervals[idx].ncols)
+    main_stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(main_stream)
 
     def step_device(events=None):
-        for e in mine:
-            e["d_band"].zero_()
-            e["d_occ"].zero_()
-            e["d_missed"].zero_()
+        for band, occ, missed in bufs.values():
+            band.zero_()
+            occ.zero_()
+            missed.zero_()
+        for k, e in enumerate(mine):
+            stream = engine.streams[k % len(engine.streams)]
+            stream.wait_stream(main_stream)
+            band, occ, missed = bufs[e["idx"]]
             if events is not None:
                 ev0 = torch.cuda.Event(enable_timing=True)
                 ev1 = torch.cuda.Event(enable_timing=True)
                 ev0.record(stream)
             ctx.simulate_interval_device(p, e["abi_iv"], e["iv"].barriers, e["d_tasks"].data_ptr(),
-                                         e["ntasks"], e["d_band"].data_ptr(),
-                                         e["d_occ"].data_ptr(), e["d_stats"].data_ptr(),
-                                         e["d_missed"].data_ptr(), stream.cuda_stream)
+                                         e["ntasks"], band.data_ptr(), occ.data_ptr(),
+                                         e["d_stats"].data_ptr(), missed.data_ptr(),
+                                         stream.cuda_stream)
             if events is not None:
                 ev1.record(stream)
                 events.append((e, ev0, ev1))
-        if split_cells and world > 1:
-            for e in mine:
-                dist.reduce(e["d_band"], dst=0, op=dist.ReduceOp.SUM)  # u32 sum == i32 sum mod 2^32
-                dist.reduce(e["d_occ"], dst=0, op=dist.ReduceOp.SUM)
+        for stream in engine.streams:
+            main_stream.wait_stream(stream)
+        for idx in split:  # the one exchange step: sum a split interval onto its root
+            for b in bufs[idx]:
+                dist.reduce(b, dst=roots[idx][0], op=dist.ReduceOp.SUM)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -251,18 +259,11 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
             torch.cuda.synchronize()
 
-    def max_over_ranks(x):
+    def all_reduce(x, op):
         if world == 1:
             return x
         t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def sum_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        dist.all_reduce(t, op=op)
         return float(t.item())
 
     # ---- device-resident timing -------------------------------------------------------------
@@ -270,105 +271,117 @@ def run_ours(args, rank, world, local_rank):
         step_device()
     sync_all()
     launches0 = ctx.kernel_launches()
+    ctx.phase_cycles(reset=True)
     events = []
     t_start = torch.cuda.Event(enable_timing=True)
     t_end = torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
         sync_all()
-        t_start.record(stream)
+        t_start.record(main_stream)
         for _ in range(args.steps):
             step_device(events)
-        t_end.record(stream)
+        t_end.record(main_stream)
         sync_all()
-    elapsed_ms = max_over_ranks(t_start.elapsed_time(t_end))
+    elapsed_ms = all_reduce(t_start.elapsed_time(t_end), dist.ReduceOp.MAX if world > 1 else None)
     launches = ctx.kernel_launches() - launches0
+    phases = ctx.phase_cycles(reset=True)
 
     # work done per step (identical every step: the simulation is deterministic)
-    lef_updates = 0
-    alg_bytes = 0
-    contacts = 0
-    faults = 0
+    lef_updates = contacts = faults = alg_bytes = epochs = 0
     for e in mine:
         st = e["d_stats"].cpu().numpy().view(stats_dt)
         lef_updates += int(st["num_lef_updates"].sum())
         contacts += int(st["num_contacts"].sum())
+        epochs += int(st["num_epochs"].sum())
         faults += int((st["device_fault"] != 0).sum())
-        e["alg_bytes"] = 32 * int(st["num_lef_updates"].sum()) + \
+        alg_bytes += 32 * int(st["num_lef_updates"].sum()) + \
             2 * len(e["iv"].barriers) * int(st["num_epochs"].sum())
-        alg_bytes += e["alg_bytes"]
     if faults:
         raise SystemExit(f"bench.py: {faults} cells reported a device fault")
-    total_lu = sum_over_ranks(float(lef_updates))
+    total_lu = all_reduce(float(lef_updates), dist.ReduceOp.SUM if world > 1 else None)
+    total_contacts = all_reduce(float(contacts), dist.ReduceOp.SUM if world > 1 else None)
     value = total_lu * args.steps / (elapsed_ms * 1e-3)
-    kernel_ms = sum(ev0.elapsed_time(ev1) for _, ev0, ev1 in events)
+    launch_ms = [ev0.elapsed_time(ev1) for _, ev0, ev1 in events]
     peak, peak_src = measured_peaks()
-    achieved = (alg_bytes * args.steps / 1e9) / (kernel_ms * 1e-3) if kernel_ms > 0 else 0.0
+    # launches overlap (several streams), so the kernel's rate is taken over the timed region
+    my_ms = t_start.elapsed_time(t_end)
+    achieved = (alg_bytes * args.steps / 1e9) / (my_ms * 1e-3) if my_ms > 0 else 0.0
 
-    # ---- end to end through the host-buffer C ABI call ---------------------------------------
+    # ---- end to end through the public API (host buffers; copies inside the timed region) ------
     h2d = sum(e["ntasks"] * task_dt.itemsize + len(e["iv"].barriers) * barrier_dt.itemsize
               for e in mine)
-    d2h = sum((e["iv"].nrows * e["iv"].ncols + 1) * 4 + e["iv"].ncols * 8 +
-              e["ntasks"] * stats_dt.itemsize + 8 for e in mine)
-    host_bands = [np.zeros(e["iv"].nrows * e["iv"].ncols + 1, dtype=np.uint32) for e in mine]
-    host_occ = [np.zeros(e["iv"].ncols, dtype=np.uint64) for e in mine]
+    d2h = sum((sim.intervals[i].nrows * sim.intervals[i].ncols + 1) * 4 + sim.intervals[i].ncols * 8
+              + 8 for i in bufs if roots[i][0] == rank) + \
+        sum(e["ntasks"] * stats_dt.itemsize for e in mine)
 
     def step_e2e():
-        for e, hb, ho in zip(mine, host_bands, host_occ):
-            hb.fill(0)
-            ho.fill(0)
-            ctx.simulate_interval(p, e["abi_iv"], e["iv"].barriers, e["h_tasks_np"], band=hb,
-                                  occ1d=ho)
+        for iv in sim.intervals:
+            iv.contacts = None
+            iv.lef_1d_occupancy = None
+        sim.run_simulate(num_workers=args.streams)
 
     e2e_steps = max(1, min(args.steps, 2))
-    step_e2e()  # warm-up (buffers, page faults)
+    step_e2e()  # warm-up (contexts, staging buffers, page faults)
     sync_all()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         step_e2e()
     sync_all()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_s = all_reduce(time.perf_counter() - t0, dist.ReduceOp.MAX if world > 1 else None)
     e2e_value = total_lu * e2e_steps / e2e_s
+    launches_e2e = sum(c.kernel_launches() for c in sim._ctxs)
 
     # ---- CPU baseline (rank 0, single-GPU runs only) ------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        cpi = max(1, min(int(cfg.num_cells), -(-2 * cores // max(1, len(genome)))))
+        cpi = cpu_sample_cells(cfg, genome, cores)
         lu, dt, used = oracle_sample_run(cfg, genome, cpi, cores)
         cpu = {"value": lu / dt, "unit": UNIT, "cores": used, "kind": "port",
                "sample": f"first {cpi} cell(s) of each of the {len(genome)} intervals "
                          f"({lu} LEF-updates, {dt:.1f} s)"}
 
     if rank == 0:
+        tot_cyc = max(1, phases.get("total", 1))
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u32/u64 integer state, f64 samplers", "data": "synthetic",
             "config": {"workload": desc, "lef_updates_per_step": total_lu,
-                       "contacts_per_step": sum_over_ranks(float(contacts)) if world == 1 else None,
-                       "l2_policy": "band matrices (1.48 GB) + RNG staging exceed the 126 MB L2; "
-                                    "band is re-zeroed every step",
-                       "parallelism": f"{world} rank(s), " +
-                       ("cells of one chromosome split over ranks + NCCL reduce" if split_cells
-                        else "whole chromosomes dealt heaviest-first")},
+                       "contacts_per_step": total_contacts,
+                       "l2_policy": "band matrices + RNG staging of a step exceed the 126 MB L2 "
+                                    "for the genome-wide workload; bands are re-zeroed every step",
+                       "streams": args.streams,
+                       "parallelism": f"{world} rank(s), {len(shards)} (interval, cell-range) "
+                                      f"shards dealt heaviest-first, {len(split)} interval(s) "
+                                      "split over ranks and summed with one NCCL reduce each"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
-                    "ms_per_step": 1e3 * e2e_s / e2e_steps},
+                    "ms_per_step": 1e3 * e2e_s / e2e_steps,
+                    "api": "Simulation.run_simulate -> modle_b200_simulate_interval (host buffers)"
+                    if world == 1 else
+                    "Simulation.run_simulate -> device shards + NCCL reduce + D2H on roots"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_simulate_cells", "achieved": achieved,
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": None,
-                         "kernel_ms_per_step": kernel_ms / args.steps,
+                         "avg_launch_ms": sum(launch_ms) / max(1, len(launch_ms)),
                          "algorithmic_bytes_per_step": int(alg_bytes),
-                         "note": "state is shared-memory resident by design; algorithmic bytes = "
-                                 "32 B per LEF-update + 2 B per barrier-epoch (SURVEY 8d)"},
+                         "note": "cell state is shared-memory resident by design, so this kernel "
+                                 "is issue/latency bound, not HBM bound; algorithmic bytes = 32 B "
+                                 "per LEF-update + 2 B per barrier-epoch (SURVEY 8d); launches "
+                                 "overlap on several streams, so the rate is taken over the "
+                                 "whole timed region of rank 0"},
+            "phase_share": {k: round(v / tot_cyc, 4) for k, v in phases.items() if k != "total"},
+            "cycles_per_cell_epoch": tot_cyc / max(1, epochs * args.steps),
             "clocks": clocks.summary(),
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
-    ctx.close()
+    sim.close()
+    engine.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -379,9 +392,11 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3"])
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4"])
     ap.add_argument("--cells", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=3,
+                    help="concurrent launches per GPU (streams / host worker threads)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

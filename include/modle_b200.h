@@ -237,6 +237,15 @@ int modle_b200_register_contacts_device(modle_b200_context* ctx, const uint32_t*
                                         uint64_t ncols, uint32_t* d_band,
                                         uint64_t* d_missed_updates, void* cuda_stream);
 
+/* Profiling aid (the reference has none; --skip-output + perf is its recipe, cli.cpp:182-186):
+ * SM-clock cycles the simulate kernel spent in each phase of the per-cell loop, summed over all
+ * cells simulated on this context since the last reset. Slots, in order: init, burn-in, bind,
+ * rank, contacts, move generation, move adjust/clamp, barrier states, LEF-BAR detect, primary
+ * LEF-LEF detect, move correction, secondary LEF-LEF, rank fix-up, extrude+release, RNG refill
+ * (nested inside the others), whole cell. Waits for the context's own stream first. */
+#define MODLE_B200_NUM_PHASES 16
+int modle_b200_phase_cycles(modle_b200_context* ctx, uint64_t* out, size_t n, int reset);
+
 /* Number of kernels this library has launched on the context so far (bench bookkeeping). */
 uint64_t modle_b200_kernel_launches(const modle_b200_context* ctx);
 

@@ -27,18 +27,22 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, variant=None, defines=()):
+    """Builds the product library, or with `variant` an experimental copy
+    libmodle_b200_<variant>.so compiled with extra -D `defines` (profiling sessions load it
+    through the MODLE_B200_LIB environment variable)."""
+    out = LIB if variant is None else os.path.join(HERE, f"libmodle_b200_{variant}.so")
+    if variant is None and not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-        [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
+        ["-D" + d for d in defines] + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", out]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed building libmodle_b200.so")
-    return LIB
+        raise RuntimeError("nvcc failed building " + out)
+    return out
 
 
 if __name__ == "__main__":

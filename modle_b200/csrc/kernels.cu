@@ -35,11 +35,19 @@ struct LaunchArgs {
   u64* ring_pool;   // grid * 2W
   u64* state_pool;  // grid * 4G
   // optional snapshot of cell 0 (debug)
+  u64* phase_cycles;  // kNumPhases accumulators (SM clock cycles per phase, all cells)
   u64* snap_u64;  // 5 * n_lefs + 2
   u8* snap_bar;   // n_bar
 };
 
-__global__ void __launch_bounds__(512, 1) k_simulate_cells(const __grid_constant__ LaunchArgs a) {
+// Two instantiations: <256, kSmallMinBlocks> for intervals whose state leaves room for several
+// CTAs per SM, <512, 1> for the large ones (one CTA owns the SM's shared memory).
+#ifndef MODLE_B200_SMALL_MIN_BLOCKS
+#define MODLE_B200_SMALL_MIN_BLOCKS 3
+#endif
+template <int kThreads, int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks)
+    k_simulate_cells(const __grid_constant__ LaunchArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   CellShared& S = *reinterpret_cast<CellShared*>(smem);
   CellArrays A = carve_cell_arrays(smem + ((sizeof(CellShared) + 15) / 16) * 16, a.kp.n_lefs,
@@ -66,6 +74,9 @@ __global__ void __launch_bounds__(512, 1) k_simulate_cells(const __grid_constant
       sim.run();
     }
     __syncthreads();
+    if (has_work && threadIdx.x < kNumPhases && a.phase_cycles)
+      atomicAdd(reinterpret_cast<unsigned long long*>(a.phase_cycles + threadIdx.x),
+                static_cast<unsigned long long>(S.phase_cycles[threadIdx.x]));
     if (threadIdx.x == 0 && a.stats) {
       modle_b200_cell_stats st;
       st.num_contacts = has_work ? S.num_contacts : 0;
@@ -132,6 +143,23 @@ namespace {
                               std::string(#expr) + ": " + cudaGetErrorString(e_));       \
   } while (0)
 
+struct PinnedBuf {  // page-locked host staging (device->host copies at full PCIe rate)
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    const cudaError_t e = cudaMallocHost(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  ~PinnedBuf() {
+    if (p) cudaFreeHost(p);
+  }
+};
+
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
@@ -151,6 +179,17 @@ struct DevBuf {
 
 }  // namespace
 
+// Buffers one in-flight launch owns. A context keeps a few of them so that launches issued on
+// different streams can overlap (the tail of one interval's cells then runs next to the head of
+// the next interval's); a slot is reused once the launch that used it last has finished.
+struct LaunchSlot {
+  DevBuf d_queue, d_rings, d_states;                     // launch scratch
+  DevBuf d_bar_pos, d_bar_dir, d_stp_a, d_stp_i, d_occ;  // per-interval arrays
+  cudaEvent_t done = nullptr;
+  bool in_flight = false;
+};
+constexpr int kLaunchSlots = 4;
+
 struct modle_b200_context {
   int device = 0;
   int num_sms = 0;
@@ -158,10 +197,12 @@ struct modle_b200_context {
   cudaStream_t stream = nullptr;
   bool jump_uploaded[kJumpSlots] = {false, false};
   ZigguratTables zig;
-  DevBuf d_zig;                                    // nx, ny, ex, ey
-  DevBuf d_args, d_queue, d_rings, d_states;       // launch scratch
-  DevBuf d_bar_pos, d_bar_dir, d_stp_a, d_stp_i, d_occ;  // per-interval arrays
-  DevBuf d_barriers, d_tasks, d_band, d_occ1d, d_stats, d_missed, d_snap_u64, d_snap_bar;
+  DevBuf d_zig;    // nx, ny, ex, ey
+  DevBuf d_phase;  // kNumPhases cycle accumulators
+  LaunchSlot slots[kLaunchSlots];
+  int next_slot = 0;
+  DevBuf d_tasks, d_band, d_occ1d, d_stats, d_missed, d_snap_u64, d_snap_bar;
+  PinnedBuf h_stage;  // band | occ1d | stats | missed of the host-buffer entry point
   uint64_t launches = 0;
 };
 
@@ -192,6 +233,16 @@ int modle_b200_init(modle_b200_context** out, int device) {
   CUDA_TRY(cudaMemcpy(z + 129, ctx->zig.ny, sizeof(double) * 129, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(z + 258, ctx->zig.ex, sizeof(double) * 257, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(z + 515, ctx->zig.ey, sizeof(double) * 257, cudaMemcpyHostToDevice));
+  CUDA_TRY(ctx->d_phase.reserve(sizeof(u64) * kNumPhases));
+  CUDA_TRY(cudaMemset(ctx->d_phase.p, 0, sizeof(u64) * kNumPhases));
+  for (auto& sl : ctx->slots) CUDA_TRY(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+  // opt in to the full shared memory once (the attribute is per function and device, and several
+  // contexts may launch concurrently with different sizes)
+  const int optin = static_cast<int>(ctx->max_smem_optin);
+  CUDA_TRY(cudaFuncSetAttribute(k_simulate_cells<256, MODLE_B200_SMALL_MIN_BLOCKS>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  CUDA_TRY(cudaFuncSetAttribute(k_simulate_cells<512, 1>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
   *out = ctx;
   return MODLE_B200_OK;
 }
@@ -199,6 +250,9 @@ int modle_b200_init(modle_b200_context** out, int device) {
 void modle_b200_destroy(modle_b200_context* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  for (auto& sl : ctx->slots)
+    if (sl.done) cudaEventDestroy(sl.done);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -207,10 +261,26 @@ uint64_t modle_b200_kernel_launches(const modle_b200_context* ctx) {
   return ctx ? ctx->launches : 0;
 }
 
+int modle_b200_phase_cycles(modle_b200_context* ctx, uint64_t* out, size_t n, int reset) {
+  if (!ctx || !out) return fail(MODLE_B200_ERR_INVALID_ARGUMENT, "NULL argument");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  u64 h[kNumPhases];
+  CUDA_TRY(cudaMemcpy(h, ctx->d_phase.p, sizeof(h), cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < n; ++i) out[i] = i < size_t(kNumPhases) ? h[i] : 0;
+  if (reset) CUDA_TRY(cudaMemset(ctx->d_phase.p, 0, sizeof(h)));
+  return MODLE_B200_OK;
+}
+
 int modle_b200_synchronize(modle_b200_context* ctx) {
   if (!ctx) return fail(MODLE_B200_ERR_INVALID_ARGUMENT, "ctx is NULL");
   CUDA_TRY(cudaSetDevice(ctx->device));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  for (auto& sl : ctx->slots) {
+    if (!sl.in_flight) continue;
+    CUDA_TRY(cudaEventSynchronize(sl.done));
+    sl.in_flight = false;
+  }
   return MODLE_B200_OK;
 }
 
@@ -247,51 +317,66 @@ int launch_simulate(modle_b200_context* ctx, const modle_b200_sim_params* params
                                 sizeof(u64) * 1024 * sc.jump_slot, cudaMemcpyHostToDevice));
     ctx->jump_uploaded[sc.jump_slot] = true;
   }
+  // pick a launch slot: the first idle one, else wait for the oldest
+  LaunchSlot* sl = nullptr;
+  for (int k = 0; k < kLaunchSlots && !sl; ++k) {
+    LaunchSlot& c = ctx->slots[(ctx->next_slot + k) % kLaunchSlots];
+    if (c.in_flight && cudaEventQuery(c.done) == cudaSuccess) c.in_flight = false;
+    if (!c.in_flight) {
+      sl = &c;
+      ctx->next_slot = (ctx->next_slot + k + 1) % kLaunchSlots;
+    }
+  }
+  if (!sl) {
+    sl = &ctx->slots[ctx->next_slot];
+    ctx->next_slot = (ctx->next_slot + 1) % kLaunchSlots;
+    CUDA_TRY(cudaEventSynchronize(sl->done));
+    sl->in_flight = false;
+  }
+  cudaGetLastError();  // cudaEventQuery's cudaErrorNotReady is not an error
   // per-interval arrays (pageable host -> device; small)
   const size_t nb = num_barriers;
-  CUDA_TRY(ctx->d_bar_pos.reserve(sizeof(u32) * (nb + 1)));
-  CUDA_TRY(ctx->d_bar_dir.reserve(sizeof(u32) * hd.bar_dir_rev.size()));
-  CUDA_TRY(ctx->d_stp_a.reserve(sizeof(double) * (nb + 1)));
-  CUDA_TRY(ctx->d_stp_i.reserve(sizeof(double) * (nb + 1)));
-  CUDA_TRY(ctx->d_occ.reserve(sizeof(double) * (nb + 1)));
-  // the previous launch on this context may still read these buffers
-  CUDA_TRY(cudaStreamSynchronize(stream));
-  if (stream != ctx->stream) CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(sl->d_bar_pos.reserve(sizeof(u32) * (nb + 1)));
+  CUDA_TRY(sl->d_bar_dir.reserve(sizeof(u32) * hd.bar_dir_rev.size()));
+  CUDA_TRY(sl->d_stp_a.reserve(sizeof(double) * (nb + 1)));
+  CUDA_TRY(sl->d_stp_i.reserve(sizeof(double) * (nb + 1)));
+  CUDA_TRY(sl->d_occ.reserve(sizeof(double) * (nb + 1)));
   if (nb) {
-    CUDA_TRY(cudaMemcpyAsync(ctx->d_bar_pos.p, hd.bar_pos.data(), sizeof(u32) * nb,
+    CUDA_TRY(cudaMemcpyAsync(sl->d_bar_pos.p, hd.bar_pos.data(), sizeof(u32) * nb,
                              cudaMemcpyHostToDevice, stream));
-    CUDA_TRY(cudaMemcpyAsync(ctx->d_stp_a.p, hd.stp_active.data(), sizeof(double) * nb,
+    CUDA_TRY(cudaMemcpyAsync(sl->d_stp_a.p, hd.stp_active.data(), sizeof(double) * nb,
                              cudaMemcpyHostToDevice, stream));
-    CUDA_TRY(cudaMemcpyAsync(ctx->d_stp_i.p, hd.stp_inactive.data(), sizeof(double) * nb,
+    CUDA_TRY(cudaMemcpyAsync(sl->d_stp_i.p, hd.stp_inactive.data(), sizeof(double) * nb,
                              cudaMemcpyHostToDevice, stream));
-    CUDA_TRY(cudaMemcpyAsync(ctx->d_occ.p, hd.occupancy.data(), sizeof(double) * nb,
+    CUDA_TRY(cudaMemcpyAsync(sl->d_occ.p, hd.occupancy.data(), sizeof(double) * nb,
                              cudaMemcpyHostToDevice, stream));
   }
-  CUDA_TRY(cudaMemcpyAsync(ctx->d_bar_dir.p, hd.bar_dir_rev.data(),
+  CUDA_TRY(cudaMemcpyAsync(sl->d_bar_dir.p, hd.bar_dir_rev.data(),
                            sizeof(u32) * hd.bar_dir_rev.size(), cudaMemcpyHostToDevice, stream));
 
   // grid: persistent CTAs, as many as fit
-  CUDA_TRY(cudaFuncSetAttribute(k_simulate_cells, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                static_cast<int>(smem)));
+  const bool small = sc.cta_threads == 256;
+  void (*kernel)(const LaunchArgs) =
+      small ? k_simulate_cells<256, MODLE_B200_SMALL_MIN_BLOCKS> : k_simulate_cells<512, 1>;
   int per_sm = 0;
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_simulate_cells,
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel,
                                                          static_cast<int>(sc.cta_threads), smem));
   if (per_sm < 1) return fail(MODLE_B200_ERR_UNSUPPORTED, "kernel does not fit on an SM");
   const u32 grid = static_cast<u32>(
       std::min<size_t>(num_cells, size_t(per_sm) * static_cast<size_t>(ctx->num_sms)));
-  CUDA_TRY(ctx->d_rings.reserve(sizeof(u64) * 2 * size_t(sc.window) * grid));
-  CUDA_TRY(ctx->d_states.reserve(sizeof(u64) * 4 * size_t(sc.gen_threads) * grid));
-  CUDA_TRY(ctx->d_queue.reserve(sizeof(u32) * 4));
-  CUDA_TRY(cudaMemsetAsync(ctx->d_queue.p, 0, sizeof(u32) * 4, stream));
+  CUDA_TRY(sl->d_rings.reserve(sizeof(u64) * 2 * size_t(sc.window) * grid));
+  CUDA_TRY(sl->d_states.reserve(sizeof(u64) * 4 * size_t(sc.gen_threads) * grid));
+  CUDA_TRY(sl->d_queue.reserve(sizeof(u32) * 4));
+  CUDA_TRY(cudaMemsetAsync(sl->d_queue.p, 0, sizeof(u32) * 4, stream));
 
   LaunchArgs a;
   a.kp = kp;
   const double* z = static_cast<const double*>(ctx->d_zig.p);
-  a.D.bar_pos = static_cast<const u32*>(ctx->d_bar_pos.p);
-  a.D.bar_dir_rev = static_cast<const u32*>(ctx->d_bar_dir.p);
-  a.D.bar_stp_active = static_cast<const double*>(ctx->d_stp_a.p);
-  a.D.bar_stp_inactive = static_cast<const double*>(ctx->d_stp_i.p);
-  a.D.bar_occupancy = static_cast<const double*>(ctx->d_occ.p);
+  a.D.bar_pos = static_cast<const u32*>(sl->d_bar_pos.p);
+  a.D.bar_dir_rev = static_cast<const u32*>(sl->d_bar_dir.p);
+  a.D.bar_stp_active = static_cast<const double*>(sl->d_stp_a.p);
+  a.D.bar_stp_inactive = static_cast<const double*>(sl->d_stp_i.p);
+  a.D.bar_occupancy = static_cast<const double*>(sl->d_occ.p);
   a.D.zig_nx = z;
   a.D.zig_ny = z + 129;
   a.D.zig_ex = z + 258;
@@ -302,13 +387,16 @@ int launch_simulate(modle_b200_context* ctx, const modle_b200_sim_params* params
   a.tasks = d_tasks;
   a.stats = d_stats;
   a.num_cells = static_cast<u32>(num_cells);
-  a.queue = static_cast<u32*>(ctx->d_queue.p);
-  a.ring_pool = static_cast<u64*>(ctx->d_rings.p);
-  a.state_pool = static_cast<u64*>(ctx->d_states.p);
+  a.queue = static_cast<u32*>(sl->d_queue.p);
+  a.ring_pool = static_cast<u64*>(sl->d_rings.p);
+  a.state_pool = static_cast<u64*>(sl->d_states.p);
+  a.phase_cycles = static_cast<u64*>(ctx->d_phase.p);
   a.snap_u64 = d_snap_u64;
   a.snap_bar = d_snap_bar;
-  k_simulate_cells<<<grid, sc.cta_threads, smem, stream>>>(a);
+  kernel<<<grid, sc.cta_threads, smem, stream>>>(a);
   CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaEventRecord(sl->done, stream));
+  sl->in_flight = true;
   ++ctx->launches;
   return MODLE_B200_OK;
 }
@@ -380,22 +468,27 @@ int modle_b200_simulate_interval(modle_b200_context* ctx, const modle_b200_sim_p
       nullptr, nullptr);
   if (rc != MODLE_B200_OK) return rc;
   // results are ADDED to the caller's buffers (the reference accumulates into a shared matrix)
-  std::vector<u32> h_band(npx);
-  std::vector<u64> h_occ(ncols);
-  std::vector<modle_b200_cell_stats> h_stats(num_cells);
-  u64 h_missed = 0;
-  CUDA_TRY(cudaMemcpyAsync(h_band.data(), ctx->d_band.p, sizeof(u32) * npx, cudaMemcpyDeviceToHost, s));
+  const size_t off_occ = ((sizeof(u32) * npx + 63) / 64) * 64;
+  const size_t off_stats = off_occ + ((sizeof(u64) * ncols + 63) / 64) * 64;
+  const size_t off_missed = off_stats + ((sizeof(modle_b200_cell_stats) * num_cells + 63) / 64) * 64;
+  CUDA_TRY(ctx->h_stage.reserve(off_missed + 64));
+  unsigned char* hs = static_cast<unsigned char*>(ctx->h_stage.p);
+  const u32* h_band = reinterpret_cast<const u32*>(hs);
+  const u64* h_occ = reinterpret_cast<const u64*>(hs + off_occ);
+  const modle_b200_cell_stats* h_stats = reinterpret_cast<const modle_b200_cell_stats*>(hs + off_stats);
+  const u64* h_missed = reinterpret_cast<const u64*>(hs + off_missed);
+  CUDA_TRY(cudaMemcpyAsync(hs, ctx->d_band.p, sizeof(u32) * npx, cudaMemcpyDeviceToHost, s));
   if (occ1d_out)
-    CUDA_TRY(cudaMemcpyAsync(h_occ.data(), ctx->d_occ1d.p, sizeof(u64) * ncols,
+    CUDA_TRY(cudaMemcpyAsync(hs + off_occ, ctx->d_occ1d.p, sizeof(u64) * ncols,
                              cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaMemcpyAsync(h_stats.data(), ctx->d_stats.p,
+  CUDA_TRY(cudaMemcpyAsync(hs + off_stats, ctx->d_stats.p,
                            sizeof(modle_b200_cell_stats) * num_cells, cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaMemcpyAsync(&h_missed, ctx->d_missed.p, sizeof(u64), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(hs + off_missed, ctx->d_missed.p, sizeof(u64), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
   for (size_t i = 0; i < npx; ++i) band_out[i] += h_band[i];
   if (occ1d_out)
     for (size_t i = 0; i < ncols; ++i) occ1d_out[i] += h_occ[i];
-  if (missed_updates_out) *missed_updates_out += h_missed;
+  if (missed_updates_out) *missed_updates_out += *h_missed;
   u64 first_fault = 0;
   for (size_t i = 0; i < num_cells; ++i) {
     if (stats_out) stats_out[i] = h_stats[i];

@@ -15,12 +15,19 @@ constexpr int kJumpSlots = 2;
 #if MB_DEVICE_BUILD
 __constant__ u64 c_jump[kJumpSlots][1024];
 #define MB_JUMP(slot, idx) c_jump[slot][idx]
-#define MB_LDCG_U64(p) __ldcg(p)
+// The RNG ring lives in global memory and is written and read by the same CTA with a CTA
+// barrier in between, so plain (L1-cached) loads are coherent; MODLE_B200_RING_LDCG forces the
+// L2-only path for comparison.
+#ifdef MODLE_B200_RING_LDCG
+#define MB_LD_RING_U64(p) __ldcg(p)
+#else
+#define MB_LD_RING_U64(p) (*(p))
+#endif
 #define MB_ATOMIC_MIN_U32(ptr, val) atomicMin((ptr), (val))
 #else
 extern u64 g_emu_jump[kJumpSlots][1024];
 #define MB_JUMP(slot, idx) g_emu_jump[slot][idx]
-#define MB_LDCG_U64(p) (*(p))
+#define MB_LD_RING_U64(p) (*(p))
 #define MB_ATOMIC_MIN_U32(ptr, val) (*(ptr) = std::min<u32>(*(ptr), (val)))
 #endif
 
@@ -108,7 +115,22 @@ struct CellSim {
   MB_FN void fault(u32 code) const {
     if (S.fault == 0) S.fault = code;  // benign race: any code is reported
   }
-  MB_FN u64 raw(u64 off) const { return MB_LDCG_U64(A.rng_ring + (off & (2 * u64(P.rng_window) - 1))); }
+  MB_FN u64 raw(u64 off) const { return MB_LD_RING_U64(A.rng_ring + (off & (2 * u64(P.rng_window) - 1))); }
+
+  // Phase timing: thread 0 charges the SM-clock cycles since the previous lap to phase `ph`.
+  // (No-op in the CPU emulation.)
+  u64 t_last = 0;
+  MB_FN void lap(int ph) {
+#if MB_DEVICE_BUILD
+    if (threadIdx.x == 0) {
+      const u64 now = static_cast<u64>(clock64());
+      S.phase_cycles[ph] += now - t_last;
+      t_last = now;
+    }
+#else
+    (void)ph;
+#endif
+  }
 
   // A serial reader of the raw stream used by the few inherently sequential samplers.
   struct Cursor {
@@ -143,6 +165,11 @@ struct CellSim {
       cta.sync();
       return;
     }
+#if MB_DEVICE_BUILD
+    const bool refill = S.rng_generated < need_end;
+    u64 t_refill = 0;
+    if (refill && threadIdx.x == 0) t_refill = static_cast<u64>(clock64());
+#endif
     while (S.rng_generated < need_end) {
       const u64 wbase = S.rng_generated;
       cta.sync();
@@ -174,6 +201,10 @@ struct CellSim {
       }
       cta.sync();
     }
+#if MB_DEVICE_BUILD
+    if (refill && threadIdx.x == 0)
+      S.phase_cycles[kPhRngGenerate] += static_cast<u64>(clock64()) - t_refill;
+#endif
   }
 
   // Positions the G generator sub-streams at offsets g*l of the cell's stream (leader walks the
@@ -467,6 +498,7 @@ struct CellSim {
         S.hist_len = 0;
         S.hist_head = 0;
         S.done = 0;
+        for (int k = 0; k < kNumPhases; ++k) S.phase_cycles[k] = 0;
         if (P.burnin_history > kMaxBurninHistory || P.burnin_window + 1 >= P.burnin_history)
           fault(kFaultBurninHistory);
       }
@@ -1431,7 +1463,9 @@ struct CellSim {
     const bool done = S.burnin_completed != 0;
     generate_moves_dir(A.rm, done ? P.rev_speed : P.rev_speed_burnin, P.rev_std);
     generate_moves_dir(A.fm, done ? P.fwd_speed : P.fwd_speed_burnin, P.fwd_std);
+    lap(kPhMovesGen);
     adjust_and_clamp_moves();
+    lap(kPhMovesAdjust);
   }
 
   // ExtrusionBarriers::next_state (extrusion_barriers.cpp:145-161): one canonical per barrier
@@ -1914,47 +1948,35 @@ struct CellSim {
       cta.sync();
       // leader: walk the candidates. A candidate is reached when it is the first of its run or
       // the previous one was reached and its trial succeeded; only reached candidates draw.
+      // The walk works on one 32-candidate word at a time, held in registers together with the
+      // window of failed-trial bits that starts at the current draw.
       MB_REGION(cta, tid) {
         if (cta.leader(tid)) {
-          u32 d = 0;       // draws consumed
-          u32 c = 0;       // candidate cursor
-          bool alive = false;
+          u32 d = 0;  // draws consumed
+          u32 alive = 0;
+          u32 acc = 0;  // reached candidates so far (== d)
           const u32 np = static_cast<u32>(npot);
-          while (c < np) {
-            const bool is_first = (bits_fr[c >> 5] >> (c & 31)) & 1u;
-            if (is_first || alive) {
-              bits_reached[c >> 5] |= 1u << (c & 31);
-              alive = !((bits_fail[d >> 5] >> (d & 31)) & 1u);
-              ++d;
-              ++c;
-            } else {
-              // dead chain: skip to the next first-in-run candidate
-              ++c;
-              while (c < np) {
-                const u32 w = bits_fr[c >> 5] >> (c & 31);
-                if (w) {
-                  c += static_cast<u32>(
-#if MB_DEVICE_BUILD
-                      __ffs(static_cast<int>(w)) - 1
-#else
-                      __builtin_ctz(w)
-#endif
-                  );
-                  break;
-                }
-                c = (c | 31u) + 1;
-              }
+          const u32 ncw = (np + 31) / 32;
+          for (u32 w = 0; w < ncw; ++w) {
+            const u32 F = bits_fr[w];
+            const u32 lim = np - 32 * w < 32 ? np - 32 * w : 32;
+            // fail bits of draws d, d+1, ... (at most 32 are used by this word)
+            const u32 lo = bits_fail[d >> 5], hi = bits_fail[(d >> 5) + 1];
+            const u32 sh = d & 31;
+            const u32 fb = sh ? ((lo >> sh) | (hi << (32 - sh))) : lo;
+            u32 R = 0, k = 0;
+            for (u32 i = 0; i < lim; ++i) {
+              const u32 reach = ((F >> i) & 1u) | alive;
+              R |= reach << i;
+              alive = reach & ~(fb >> k) & 1u;
+              k += reach;
             }
-          }
-          u32 acc = 0;
-          for (u32 w = 0; w < nwords; ++w) {
+            bits_reached[w] = R;
             word_prefix[w] = acc;
-#if MB_DEVICE_BUILD
-            acc += static_cast<u32>(__popc(bits_reached[w]));
-#else
-            acc += static_cast<u32>(__builtin_popcount(bits_reached[w]));
-#endif
+            acc += k;
+            d += k;
           }
+          for (u32 w = ncw; w < nwords; ++w) word_prefix[w] = acc;
           S.tmp_u32[4] = d;
         }
       }
@@ -2098,10 +2120,15 @@ struct CellSim {
     }
     cta.sync();
     detect_lef_bar_collisions();
+    lap(kPhLefBar);
     detect_primary_lef_lef_collisions();
+    lap(kPhPrimary);
     correct_moves();
+    lap(kPhCorrect);
     process_secondary_lef_lef_collisions();
+    lap(kPhSecondary);
     if (with_fix) fix_secondary_lef_lef_collisions();
+    lap(kPhFix);
   }
 
   // extrude (simulation.cpp:498-521) and release_lefs (:553-601)
@@ -2141,7 +2168,12 @@ struct CellSim {
   // ------------------------------------------------------------------------------ main loop
   // Simulation::simulate_one_cell (simulation.cpp:896-986)
   MB_FN void run() {
+#if MB_DEVICE_BUILD
+    const u64 t_begin = static_cast<u64>(clock64());
+    t_last = t_begin;
+#endif
     init_cell();
+    lap(kPhInit);
     for (;;) {
       bool stop;
       if (!P.stop_on_epochs) {
@@ -2152,17 +2184,23 @@ struct CellSim {
       if (stop || S.epoch >= P.debug_max_epochs || S.fault != 0) break;
       cta.sync();
       if (!S.burnin_completed) burnin_step();
+      lap(kPhBurnin);
       if (S.fault != 0) break;
       bind_lefs();
+      lap(kPhBind);
       rank_lefs();
+      lap(kPhRank);
       if (S.burnin_completed) {
         sample_and_register_contacts();
+        lap(kPhContacts);
         if (task.target_contacts != 0 && S.num_contacts >= task.target_contacts) break;
       }
       generate_moves();
       next_barrier_states();
+      lap(kPhBarriers);
       process_collisions(true);
       extrude_and_release();
+      lap(kPhExtrudeRelease);
       MB_REGION(cta, tid) {
         if (cta.leader(tid)) {
           S.lef_updates += S.num_active;
@@ -2171,6 +2209,10 @@ struct CellSim {
       }
       cta.sync();
     }
+    cta.sync();
+#if MB_DEVICE_BUILD
+    if (threadIdx.x == 0) S.phase_cycles[kPhTotal] = static_cast<u64>(clock64()) - t_begin;
+#endif
     cta.sync();
   }
 };

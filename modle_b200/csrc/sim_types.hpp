@@ -38,6 +38,28 @@ enum : u32 {
 
 constexpr int kMaxBurninHistory = 256;
 
+// Phases of the per-cell loop whose SM-clock cycles the kernel accumulates (cheap: two clock
+// reads by one thread per phase). Read back with modle_b200_phase_cycles().
+enum : int {
+  kPhInit = 0,
+  kPhBurnin,
+  kPhBind,
+  kPhRank,
+  kPhContacts,
+  kPhMovesGen,
+  kPhMovesAdjust,
+  kPhBarriers,
+  kPhLefBar,
+  kPhPrimary,
+  kPhCorrect,
+  kPhSecondary,
+  kPhFix,
+  kPhExtrudeRelease,
+  kPhRngGenerate,  // nested inside the phases above (time spent refilling the RNG ring)
+  kPhTotal,
+  kNumPhases
+};
+
 // Everything the kernel needs to know about the run; one per launch, in global memory.
 struct KernelParams {
   u32 start, end;  // interval [start, end)
@@ -110,6 +132,7 @@ struct CellShared {
   u32 done;
   u32 tmp_u32[8];
   u64 tmp_u64[4];
+  u64 phase_cycles[kNumPhases];  // SM clock cycles spent per phase of the epoch loop (thread 0)
   double avg_hist[kMaxBurninHistory];
   double cv_hist[kMaxBurninHistory];
   CtaScratch scratch;

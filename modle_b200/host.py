@@ -7,7 +7,8 @@ import numpy as np
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libmodle_b200.so")
+# MODLE_B200_LIB: load an experimental build of the same library instead (profiling sessions)
+_LIB_PATH = os.environ.get("MODLE_B200_LIB") or os.path.join(_HERE, "libmodle_b200.so")
 _LIB = None
 
 
@@ -57,6 +58,7 @@ def lib():
         L.modle_b200_destroy.argtypes = [C.c_void_p]
         L.modle_b200_destroy.restype = None
         L.modle_b200_synchronize.argtypes = [C.c_void_p]
+        L.modle_b200_phase_cycles.argtypes = [C.c_void_p, u64p, C.c_size_t, C.c_int]
         L.modle_b200_kernel_launches.argtypes = [C.c_void_p]
         L.modle_b200_kernel_launches.restype = C.c_uint64
         L.modle_b200_simulate_interval.argtypes = [
@@ -84,8 +86,12 @@ EXPORTED_SYMBOLS = [
     "modle_b200_make_cell_tasks", "modle_b200_init", "modle_b200_destroy",
     "modle_b200_simulate_interval", "modle_b200_simulate_interval_device",
     "modle_b200_synchronize", "modle_b200_snapshot_cell", "modle_b200_register_contacts_device",
-    "modle_b200_kernel_launches",
+    "modle_b200_kernel_launches", "modle_b200_phase_cycles",
 ]
+
+PHASE_NAMES = ["init", "burnin", "bind", "rank", "contacts", "moves_generate", "moves_adjust",
+               "barrier_states", "lef_bar", "primary", "correct_moves", "secondary", "fix_ranks",
+               "extrude_release", "rng_refill(nested)", "total"]
 
 
 def check(rc):

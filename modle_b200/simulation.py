@@ -104,6 +104,13 @@ class Context:
     def synchronize(self):
         host.check(host.lib().modle_b200_synchronize(self._h))
 
+    def phase_cycles(self, reset=True):
+        """{phase name: SM-clock cycles} summed over the cells simulated since the last reset."""
+        out = (C.c_uint64 * len(host.PHASE_NAMES))()
+        host.check(host.lib().modle_b200_phase_cycles(self._h, out, len(host.PHASE_NAMES),
+                                                      1 if reset else 0))
+        return dict(zip(host.PHASE_NAMES, [int(x) for x in out]))
+
     def kernel_launches(self):
         return int(host.lib().modle_b200_kernel_launches(self._h))
 
@@ -188,6 +195,8 @@ class Simulation:
     rank: int = 0
     world_size: int = 1
     intervals: list = field(default_factory=list)
+    _ctxs: list = field(default_factory=list, repr=False)
+    _engine: object = field(default=None, repr=False)
 
     def __post_init__(self):
         p = self.config.params
@@ -200,7 +209,8 @@ class Simulation:
             self.intervals.append(iv)
 
     def partition(self):
-        """Cost-weighted assignment of whole intervals to ranks (longest-processing-time first)."""
+        """Whole-interval owner per interval index (see distributed.plan_shards for the general
+        plan, which also splits an interval's cells when whole intervals do not balance)."""
         order = sorted(range(len(self.intervals)), key=lambda i: -self.intervals[i].num_lefs)
         load = [0] * self.world_size
         owner = {}
@@ -210,23 +220,95 @@ class Simulation:
             load[r] += self.intervals[i].num_lefs
         return owner
 
-    def run_simulate(self, ctx=None):
+    def run_simulate(self, ctx=None, num_workers=3):
+        """Simulation::run_simulate (scheduler_simulate.cpp:43-170) for this process' share.
+
+        world_size == 1: every interval goes through the host-buffer C-ABI call
+        (modle_b200_simulate_interval). `num_workers` host threads, each with its own context
+        (stream + device buffers), pull intervals heaviest-first from a queue -- the analogue of
+        the reference's worker threads -- so the tail of one interval's cells and its
+        device->host copy overlap the next interval's kernel.
+        world_size > 1: shards come from distributed.plan_shards; bands stay on the device, split
+        intervals are reduced onto their root rank (NCCL), and each root copies its intervals out.
+        """
         p = self.config.params
-        own_ctx = ctx is None
-        if own_ctx:
-            ctx = Context(self.device)
-        owner = self.partition()
-        try:
-            for idx, iv in enumerate(self.intervals):
-                if owner[idx] != self.rank:
-                    continue
-                # intervals without barriers are skipped (scheduler_simulate.cpp:111-124)
-                if len(iv.barriers) == 0:
-                    continue
-                tasks = host.make_cell_tasks(p, iv.chrom_name, iv.abi_interval())
-                iv.contacts, iv.lef_1d_occupancy, iv.stats, iv.missed_updates = \
-                    ctx.simulate_interval(p, iv.abi_interval(), iv.barriers, tasks)
-        finally:
-            if own_ctx:
-                ctx.close()
+        if self.world_size > 1:
+            return self._run_simulate_sharded()
+        # intervals without barriers are skipped (scheduler_simulate.cpp:111-124)
+        todo = sorted((i for i, iv in enumerate(self.intervals) if len(iv.barriers)),
+                      key=lambda i: -self.intervals[i].num_lefs)
+
+        def one(c, idx):
+            iv = self.intervals[idx]
+            tasks = host.make_cell_tasks(p, iv.chrom_name, iv.abi_interval())
+            iv.contacts, iv.lef_1d_occupancy, iv.stats, iv.missed_updates = \
+                c.simulate_interval(p, iv.abi_interval(), iv.barriers, tasks,
+                                    band=iv.contacts, occ1d=iv.lef_1d_occupancy)
+
+        if ctx is not None:
+            for idx in todo:
+                one(ctx, idx)
+            return self.intervals
+        nw = max(1, min(num_workers, len(todo)))
+        while len(self._ctxs) < nw:  # contexts (streams, device buffers) persist across calls
+            self._ctxs.append(Context(self.device))
+        if nw == 1:
+            for idx in todo:
+                one(self._ctxs[0], idx)
+            return self.intervals
+
+        import queue
+        import threading
+
+        q = queue.SimpleQueue()
+        for idx in todo:
+            q.put(idx)
+        errors = []
+
+        def worker(c):
+            try:
+                while not errors:
+                    try:
+                        idx = q.get_nowait()
+                    except queue.Empty:
+                        break
+                    one(c, idx)
+            except Exception as e:  # re-raised on the caller's thread, like ContextManager does
+                errors.append(e)
+
+        threads = [threading.Thread(target=worker, args=(self._ctxs[k],)) for k in range(nw)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
         return self.intervals
+
+    def _run_simulate_sharded(self):
+        import torch.distributed as dist
+
+        from . import distributed
+
+        p = self.config.params
+        if self._engine is None:
+            self._engine = distributed.DeviceEngine(self.device)
+        out = distributed.run_sharded(self._engine, p, self.intervals, self.rank, self.world_size,
+                                      dist)
+        for idx, o in out.items():
+            iv = self.intervals[idx]
+            iv.stats = np.concatenate(o["stats"]) if o["stats"] else None
+            if o["root"] != self.rank:
+                continue
+            iv.contacts = o["band"].cpu().numpy().view(np.uint32)
+            iv.lef_1d_occupancy = o["occ1d"].cpu().numpy().view(np.uint64)[:iv.ncols]
+            iv.missed_updates = int(o["missed"].item())
+        return self.intervals
+
+    def close(self):
+        for c in self._ctxs:
+            c.close()
+        self._ctxs.clear()
+        if self._engine is not None:
+            self._engine.close()
+            self._engine = None

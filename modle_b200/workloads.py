@@ -53,6 +53,16 @@ def config_c3(ncells=8192):
     return Config(num_cells=ncells).transform(), genome({"chr1"})
 
 
+def config_c4(ncells=512):
+    """BASELINE C4: high-collision regime -- chr20 size, LEF density x4, dense synthetic barriers
+    (1 per 15 kb), bypass probability 0.01."""
+    size = 64_444_167
+    cfg = Config(num_cells=ncells, number_of_lefs_per_mbp=80.0,
+                 probability_of_extrusion_unit_bypass=0.01).transform()
+    recs = synthetic_barrier_records(size, size // 15_000, seed=20260117 + 100)
+    return cfg, [("chr20", size, 0, size, recs)]
+
+
 def estimate_lef_updates(params, genome_list, mean_epochs=630):
     """Rough work estimate used only to size bounded CPU samples."""
     return sum(host.compute_num_lefs(params, e - s) for _, _, s, e, _ in genome_list) * \

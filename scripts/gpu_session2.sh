@@ -1,0 +1,23 @@
+#!/bin/bash
+# GPU session 2: parity, phase breakdown after the leader-walk fix, stream overlap.
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+tail -3 gpurun_out/pytest_gpu.log
+{
+timeout 300 python scripts/gpu_phases.py c1 512 2
+timeout 300 python scripts/gpu_phases.py c3 296 2
+timeout 300 python scripts/gpu_phases.py c4 296 1
+} > gpurun_out/phases2.log 2>&1
+cat gpurun_out/phases2.log
+for st in 1 3; do
+  timeout 600 python bench.py --workload c1 --steps 2 --warmup 3 --streams $st --no-cpu-baseline > gpurun_out/bench_c1_s$st.json 2> gpurun_out/bench_c1_s$st.err
+  timeout 900 python bench.py --steps 1 --warmup 1 --streams $st --no-cpu-baseline > gpurun_out/bench_c2_s$st.json 2> gpurun_out/bench_c2_s$st.err
+done
+python - <<'PY'
+import json,glob
+for f in sorted(glob.glob('gpurun_out/bench_c*_s*.json')):
+    try:
+        d=json.load(open(f)); print(f, 'value %.1f M/s'%(d['value']/1e6), 'ms %.1f'%d['ms_per_step'], 'e2e %.1f M/s'%(d['e2e']['value']/1e6), 'e2e ms %.1f'%d['e2e']['ms_per_step'])
+    except Exception as e: print(f, 'FAILED', e)
+PY
+tail -5 gpurun_out/bench_c2_s3.err
