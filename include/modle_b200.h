@@ -242,8 +242,9 @@ int modle_b200_register_contacts_device(modle_b200_context* ctx, const uint32_t*
  * cells simulated on this context since the last reset. Slots, in order: init, burn-in, bind,
  * rank, contacts, move generation, move adjust/clamp, barrier states, LEF-BAR detect, primary
  * LEF-LEF detect, move correction, secondary LEF-LEF, rank fix-up, extrude+release, RNG refill
- * (nested inside the others), whole cell. Waits for the context's own stream first. */
-#define MODLE_B200_NUM_PHASES 16
+ * (nested inside the others), whole cell; then a finer split of move generation (4 slots) and
+ * of the secondary pass (6 slots). Waits for the context's own stream first. */
+#define MODLE_B200_NUM_PHASES 26
 int modle_b200_phase_cycles(modle_b200_context* ctx, uint64_t* out, size_t n, int reset);
 
 /* Number of kernels this library has launched on the context so far (bench bookkeeping). */

@@ -41,6 +41,7 @@ constexpr int kMaxWarps = kMaxThreads / 32;
 struct CtaScratch {
   u64 warp_u64[kMaxWarps];
   u64 warp_u64b[kMaxWarps];
+  u64 warp_u64c[kMaxWarps];
   double warp_f64[kMaxWarps];
   u64 bcast_u64;
   double bcast_f64;
@@ -70,6 +71,36 @@ MB_FN i64 minplus_apply(const MinPlus& f, i64 x) {
   if (f.b >= kMinPlusInf) return f.a;
   const i64 y = x + f.b;
   return f.a < y ? f.a : y;
+}
+
+// Element of the secondary-collision scan (sim_core.hpp secondary_pass): a map on the state
+// (alive, v) of the unit just walked. kind COND: alive' = alive && v >= T, v' = min(a, v + b);
+// CONST (b == kSecConst): alive' = 1, v' = a; DEAD (b == kSecDead): alive' = 0.
+struct SecOp {
+  i64 T, a, b;
+};
+constexpr i64 kSecConst = kMinPlusInf;
+constexpr i64 kSecDead = kMinPlusInf + 1;
+MB_FN SecOp secop_identity() { return SecOp{-kMinPlusInf, kMinPlusInf, 0}; }
+MB_FN SecOp secop_const(i64 v) { return SecOp{0, v, kSecConst}; }
+MB_FN SecOp secop_dead() { return SecOp{0, 0, kSecDead}; }
+// apply `f`, then `g`
+MB_FN SecOp secop_then(const SecOp& f, const SecOp& g) {
+  if (g.b >= kMinPlusInf) return g;
+  if (f.b == kSecDead) return f;
+  if (f.b == kSecConst) {
+    if (f.a < g.T) return secop_dead();
+    const i64 y = f.a + g.b;
+    return secop_const(g.a < y ? g.a : y);
+  }
+  if (f.a < g.T) return secop_dead();
+  SecOp r;
+  const i64 t2 = g.T - f.b;
+  r.T = f.T > t2 ? f.T : t2;
+  const i64 y = f.a >= kMinPlusInf ? kMinPlusInf : f.a + g.b;
+  r.a = g.a < y ? g.a : y;
+  r.b = f.b + g.b;
+  return r;
 }
 
 // One value per thread that survives across regions: a register on the device, an array indexed
@@ -233,6 +264,48 @@ struct Cta {
     return reduce_sum_f64(first(), v.val);
   }
   MB_FN void exscan_minplus(PerThread<MinPlus>& v) const { v.val = exscan_minplus(first(), v.val); }
+
+  // Exclusive scan of SecOp elements in thread order (composition of all lower threads).
+  MB_FN void exscan_secop(PerThread<SecOp>& pv) const {
+    const int tid = first();
+    const int lane = tid & 31, warp = tid >> 5, nw = (nt() + 31) >> 5;
+    SecOp inc = pv.val;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      SecOp o;
+      o.T = __shfl_up_sync(0xffffffffu, inc.T, d);
+      o.a = __shfl_up_sync(0xffffffffu, inc.a, d);
+      o.b = __shfl_up_sync(0xffffffffu, inc.b, d);
+      if (lane >= d) inc = secop_then(o, inc);
+    }
+    if (lane == 31) {
+      scr->warp_u64[warp] = static_cast<u64>(inc.T);
+      scr->warp_u64b[warp] = static_cast<u64>(inc.a);
+      scr->warp_u64c[warp] = static_cast<u64>(inc.b);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      SecOp acc = secop_identity();
+      for (int w = 0; w < nw; ++w) {
+        const SecOp cur{static_cast<i64>(scr->warp_u64[w]), static_cast<i64>(scr->warp_u64b[w]),
+                        static_cast<i64>(scr->warp_u64c[w])};
+        scr->warp_u64[w] = static_cast<u64>(acc.T);
+        scr->warp_u64b[w] = static_cast<u64>(acc.a);
+        scr->warp_u64c[w] = static_cast<u64>(acc.b);
+        acc = secop_then(acc, cur);
+      }
+    }
+    __syncthreads();
+    const SecOp wprefix{static_cast<i64>(scr->warp_u64[warp]), static_cast<i64>(scr->warp_u64b[warp]),
+                        static_cast<i64>(scr->warp_u64c[warp])};
+    SecOp ex;
+    ex.T = __shfl_up_sync(0xffffffffu, inc.T, 1);
+    ex.a = __shfl_up_sync(0xffffffffu, inc.a, 1);
+    ex.b = __shfl_up_sync(0xffffffffu, inc.b, 1);
+    if (lane == 0) ex = secop_identity();
+    pv.val = secop_then(wprefix, ex);
+    __syncthreads();
+  }
 };
 
 #define MB_ATOMIC_MAX_U32(ptr, val) atomicMax((ptr), (val))
@@ -241,6 +314,8 @@ struct Cta {
 #define MB_ATOMIC_ADD_U64(ptr, val) \
   atomicAdd(reinterpret_cast<unsigned long long*>(ptr), static_cast<unsigned long long>(val))
 #define MB_U64_TO_F64(x) __ull2double_rn(x)
+#define MB_POPC(x) __popc(x)
+#define MB_FFS(x) __ffs(static_cast<int>(x))
 
 #else  // ---------------------------------------------------------------- emulation
 
@@ -304,6 +379,14 @@ struct Cta {
       acc = minplus_then(acc, x);
     }
   }
+  void exscan_secop(PerThread<SecOp>& v) const {
+    SecOp acc = secop_identity();
+    for (int t = 0; t < nthreads; ++t) {
+      const SecOp x = v[t];
+      v[t] = acc;
+      acc = secop_then(acc, x);
+    }
+  }
 };
 
 #define MB_ATOMIC_MAX_U32(ptr, val) (*(ptr) = std::max<u32>(*(ptr), (val)))
@@ -311,6 +394,8 @@ struct Cta {
 #define MB_ATOMIC_ADD_U32(ptr, val) (*(ptr) += (val))
 #define MB_ATOMIC_ADD_U64(ptr, val) (*(ptr) += (val))
 #define MB_U64_TO_F64(x) static_cast<double>(x)
+#define MB_POPC(x) __builtin_popcount(x)
+#define MB_FFS(x) __builtin_ffs(static_cast<int>(x))
 
 #endif
 

@@ -105,24 +105,40 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks)
   }
 }
 
-// Contact register: one (bin1, bin2) pair per thread, grid-stride. Out-of-band pairs are counted
-// once per warp (warp-aggregated) into *missed.
+// Contact register: scatters (bin1, bin2) pairs into the band with RED.ADD.U32. Each thread
+// takes four pairs per iteration through two 16-byte loads (streaming, evict-first) so that four
+// independent reductions are in flight per thread; out-of-band pairs are counted once per warp.
+__device__ __forceinline__ u32 register_one(u32 b1, u32 b2, u32 nrows, u32* __restrict__ band) {
+  const u32 i = b1 > b2 ? b1 - b2 : b2 - b1;
+  const u32 j = b1 > b2 ? b1 : b2;
+  if (i >= nrows) return 1;
+  atomicAdd(band + (size_t(j) * nrows + i), 1u);  // result unused -> RED.E.ADD
+  return 0;
+}
+
 __global__ void __launch_bounds__(256) k_register_contacts(const u32* __restrict__ bin1,
                                                            const u32* __restrict__ bin2, size_t n,
                                                            u32 nrows, u32* __restrict__ band,
-                                                           u64* __restrict__ missed) {
+                                                           u64* __restrict__ missed, int vec_ok) {
   const size_t stride = size_t(gridDim.x) * blockDim.x;
+  const size_t tid = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   u32 my_missed = 0;
-  for (size_t e = size_t(blockIdx.x) * blockDim.x + threadIdx.x; e < n; e += stride) {
-    const u32 b1 = __ldcs(bin1 + e), b2 = __ldcs(bin2 + e);
-    const u32 i = b1 > b2 ? b1 - b2 : b2 - b1;
-    const u32 j = b1 > b2 ? b1 : b2;
-    if (i >= nrows) {
-      ++my_missed;
-    } else {
-      atomicAdd(band + (size_t(j) * nrows + i), 1u);  // result unused -> RED.E.ADD
+  size_t done = 0;
+  if (vec_ok) {
+    const size_t n4 = n / 4;
+    const uint4* v1 = reinterpret_cast<const uint4*>(bin1);
+    const uint4* v2 = reinterpret_cast<const uint4*>(bin2);
+    for (size_t e = tid; e < n4; e += stride) {
+      const uint4 a = __ldcs(v1 + e), b = __ldcs(v2 + e);
+      my_missed += register_one(a.x, b.x, nrows, band);
+      my_missed += register_one(a.y, b.y, nrows, band);
+      my_missed += register_one(a.z, b.z, nrows, band);
+      my_missed += register_one(a.w, b.w, nrows, band);
     }
+    done = n4 * 4;
   }
+  for (size_t e = done + tid; e < n; e += stride)
+    my_missed += register_one(__ldcs(bin1 + e), __ldcs(bin2 + e), nrows, band);
   const u32 warp_missed = __reduce_add_sync(0xffffffffu, my_missed);
   if ((threadIdx.x & 31) == 0 && warp_missed)
     atomicAdd(reinterpret_cast<unsigned long long*>(missed),
@@ -195,7 +211,7 @@ struct modle_b200_context {
   int num_sms = 0;
   size_t max_smem_optin = 0;
   cudaStream_t stream = nullptr;
-  bool jump_uploaded[kJumpSlots] = {false, false};
+  DevBuf d_jump[kJumpSlots];  // byte-indexed jump tables, built on first use
   ZigguratTables zig;
   DevBuf d_zig;    // nx, ny, ex, ey
   DevBuf d_phase;  // kNumPhases cycle accumulators
@@ -238,11 +254,18 @@ int modle_b200_init(modle_b200_context** out, int device) {
   for (auto& sl : ctx->slots) CUDA_TRY(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
   // opt in to the full shared memory once (the attribute is per function and device, and several
   // contexts may launch concurrently with different sizes)
-  const int optin = static_cast<int>(ctx->max_smem_optin);
-  CUDA_TRY(cudaFuncSetAttribute(k_simulate_cells<256, MODLE_B200_SMALL_MIN_BLOCKS>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-  CUDA_TRY(cudaFuncSetAttribute(k_simulate_cells<512, 1>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  {
+    cudaFuncAttributes fa;
+    CUDA_TRY(cudaFuncGetAttributes(&fa, k_simulate_cells<256, MODLE_B200_SMALL_MIN_BLOCKS>));
+    CUDA_TRY(cudaFuncSetAttribute(k_simulate_cells<256, MODLE_B200_SMALL_MIN_BLOCKS>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(ctx->max_smem_optin - fa.sharedSizeBytes)));
+    CUDA_TRY(cudaFuncGetAttributes(&fa, k_simulate_cells<512, 1>));
+    CUDA_TRY(cudaFuncSetAttribute(k_simulate_cells<512, 1>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(ctx->max_smem_optin - fa.sharedSizeBytes)));
+    ctx->max_smem_optin -= fa.sharedSizeBytes;
+  }
   *out = ctx;
   return MODLE_B200_OK;
 }
@@ -310,12 +333,12 @@ int launch_simulate(modle_b200_context* ctx, const modle_b200_sim_params* params
   if (num_cells == 0) return MODLE_B200_OK;
   if (num_cells > 0x7FFFFFFFull) return fail(MODLE_B200_ERR_INVALID_ARGUMENT, "too many cells");
 
-  if (!ctx->jump_uploaded[sc.jump_slot]) {
-    std::vector<u64> table(1024);
+  if (!ctx->d_jump[sc.jump_slot].p) {
+    std::vector<u64> table(kJumpTableWords);
     build_jump_table(sc.window, table.data());
-    CUDA_TRY(cudaMemcpyToSymbol(c_jump, table.data(), sizeof(u64) * 1024,
-                                sizeof(u64) * 1024 * sc.jump_slot, cudaMemcpyHostToDevice));
-    ctx->jump_uploaded[sc.jump_slot] = true;
+    CUDA_TRY(ctx->d_jump[sc.jump_slot].reserve(sizeof(u64) * kJumpTableWords));
+    CUDA_TRY(cudaMemcpy(ctx->d_jump[sc.jump_slot].p, table.data(), sizeof(u64) * kJumpTableWords,
+                        cudaMemcpyHostToDevice));
   }
   // pick a launch slot: the first idle one, else wait for the oldest
   LaunchSlot* sl = nullptr;
@@ -381,6 +404,7 @@ int launch_simulate(modle_b200_context* ctx, const modle_b200_sim_params* params
   a.D.zig_ny = z + 129;
   a.D.zig_ex = z + 258;
   a.D.zig_ey = z + 515;
+  a.D.jump_tbl = static_cast<const u64*>(ctx->d_jump[sc.jump_slot].p);
   a.K.band = d_band;
   a.K.occ1d = kp.track_1d ? d_occ1d : nullptr;
   a.K.missed = d_missed;
@@ -572,10 +596,13 @@ int modle_b200_register_contacts_device(modle_b200_context* ctx, const uint32_t*
   cudaStream_t stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
   if (n == 0) return MODLE_B200_OK;
   const int threads = 256;
-  const size_t want = (n + threads - 1) / threads;
+  const int vec_ok = (reinterpret_cast<uintptr_t>(d_bin1) % 16 == 0) &&
+                     (reinterpret_cast<uintptr_t>(d_bin2) % 16 == 0);
+  const size_t items = vec_ok ? (n + 3) / 4 : n;
+  const size_t want = (items + threads - 1) / threads;
   const u32 grid = static_cast<u32>(std::min<size_t>(want, size_t(ctx->num_sms) * 8));
   k_register_contacts<<<grid, threads, 0, stream>>>(d_bin1, d_bin2, n, static_cast<u32>(nrows),
-                                                    d_band, d_missed_updates);
+                                                    d_band, d_missed_updates, vec_ok);
   CUDA_TRY(cudaGetLastError());
   ++ctx->launches;
   return MODLE_B200_OK;

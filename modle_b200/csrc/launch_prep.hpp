@@ -57,15 +57,26 @@ struct ZigguratTables {
 struct StagingConfig {
   u32 cta_threads, gen_threads, per_thread, window, jump_slot;
 };
-inline StagingConfig staging_large() { return StagingConfig{512, 512, 64, 512 * 64, 0}; }
+inline StagingConfig staging_large() { return StagingConfig{512, 256, 128, 256 * 128, 0}; }
 inline StagingConfig staging_small() { return StagingConfig{256, 64, 128, 64 * 128, 1}; }
 
-// Flattens T^window into the [256 columns][4 words] layout of c_jump.
-inline void build_jump_table(u32 window, u64* out /*1024*/) {
+// Byte-indexed table of T^window (layout: see sim_core.hpp xs_jump): entry (k, v) is the XOR of
+// the matrix columns 8k+b over the set bits b of v.
+inline void build_jump_table(u32 window, u64* out /*32*256*4*/) {
   const host::StateMatrix m = host::StateMatrix::power(window);
-  for (int j = 0; j < 256; ++j)
-    for (int w = 0; w < 4; ++w) out[j * 4 + w] = m.col[j][w];
+  for (int k = 0; k < 32; ++k) {
+    for (int v = 0; v < 256; ++v) {
+      u64* e = out + (size_t(k) * 256 + v) * 4;
+      e[0] = e[1] = e[2] = e[3] = 0;
+      for (int b = 0; b < 8; ++b) {
+        if (!((v >> b) & 1)) continue;
+        for (int w = 0; w < 4; ++w) e[w] ^= m.col[8 * k + b][w];
+      }
+    }
+  }
 }
+
+inline u64 worst_phase_draws(u32 n_lefs) { return 2 * u64(n_lefs) + n_lefs / 4 + 512; }
 
 struct IntervalHostData {
   std::vector<u32> bar_pos, bar_dir_rev;
@@ -134,8 +145,9 @@ inline std::string prepare_interval(const modle_b200_sim_params& p, const modle_
   k.rng_per_thread = sc.per_thread;
   k.rng_window = sc.window;
   k.rng_jump_slot = sc.jump_slot;
-  // every phase must fit one staging window (largest consumer: 2 x the normal draws of a pass)
-  const u64 worst = u64(iv.num_lefs) + iv.num_lefs / 8 + 512;
+  // every phase must fit one staging window (largest consumer: the normal draws of both move
+  // arrays, 2n items + n/4 + 64 slack + 192), and a thread's chunk of them one 32-bit mask
+  const u64 worst = worst_phase_draws(static_cast<u32>(iv.num_lefs));
   if (worst > sc.window || nb + 64 > sc.window) return "interval too large for the RNG staging window";
 
   hd->bar_pos.resize(nb);
@@ -165,7 +177,7 @@ inline StagingConfig pick_staging(u32 n_lefs, u32 n_bar) {
   // small intervals: several CTAs per SM, few generator threads each; large: one fat CTA per SM
   const size_t bytes = cell_array_bytes(n_lefs, n_bar) + sizeof(CellShared);
   const StagingConfig s = staging_small();
-  const u64 worst = u64(n_lefs) + n_lefs / 8 + 512;
+  const u64 worst = worst_phase_draws(n_lefs);
   if (bytes <= 100 * 1024 && worst <= s.window && u64(n_bar) + 64 <= s.window) return s;
   return staging_large();
 }

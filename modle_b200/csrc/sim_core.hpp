@@ -10,11 +10,13 @@
 
 namespace modle_b200 {
 
-// ---- jump-ahead matrices T^W (256 columns x 4 words), one slot per staging configuration -------
+// ---- jump-ahead: g <- T^W g through byte-indexed tables ------------------------------------------
+// tbl[(k * 256 + v) * 4 + w] = word w of T^W applied to the state whose k-th byte is v (all other
+// bytes 0); T^W g is the XOR of the 32 entries selected by the bytes of g. One table (256 KB) per
+// staging configuration, built on the host (launch_prep.hpp) and kept in global memory.
 constexpr int kJumpSlots = 2;
+constexpr size_t kJumpTableWords = size_t(32) * 256 * 4;
 #if MB_DEVICE_BUILD
-__constant__ u64 c_jump[kJumpSlots][1024];
-#define MB_JUMP(slot, idx) c_jump[slot][idx]
 // The RNG ring lives in global memory and is written and read by the same CTA with a CTA
 // barrier in between, so plain (L1-cached) loads are coherent; MODLE_B200_RING_LDCG forces the
 // L2-only path for comparison.
@@ -25,8 +27,6 @@ __constant__ u64 c_jump[kJumpSlots][1024];
 #endif
 #define MB_ATOMIC_MIN_U32(ptr, val) atomicMin((ptr), (val))
 #else
-extern u64 g_emu_jump[kJumpSlots][1024];
-#define MB_JUMP(slot, idx) g_emu_jump[slot][idx]
 #define MB_LD_RING_U64(p) (*(p))
 #define MB_ATOMIC_MIN_U32(ptr, val) (*(ptr) = std::min<u32>(*(ptr), (val)))
 #endif
@@ -51,21 +51,28 @@ MB_FN u64 xs_next(Xs& g) {
   g.s3 = rotl64(g.s3, 45);
   return r;
 }
-// g <- T^W g : 256 masked XORs of matrix columns
-MB_FN Xs xs_jump(const Xs& g, int slot) {
+MB_FN Xs xs_jump(const Xs& g, const u64* tbl) {
   Xs r{0, 0, 0, 0};
   const u64 w[4] = {g.s0, g.s1, g.s2, g.s3};
-#pragma unroll 1
+#pragma unroll
   for (int wi = 0; wi < 4; ++wi) {
-    const u64 word = w[wi];
-#pragma unroll 4
-    for (int b = 0; b < 64; ++b) {
-      const u64 m = u64(0) - ((word >> b) & 1);
-      const int c = (wi * 64 + b) * 4;
-      r.s0 ^= MB_JUMP(slot, c + 0) & m;
-      r.s1 ^= MB_JUMP(slot, c + 1) & m;
-      r.s2 ^= MB_JUMP(slot, c + 2) & m;
-      r.s3 ^= MB_JUMP(slot, c + 3) & m;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const u32 v = static_cast<u32>(w[wi] >> (8 * b)) & 0xFFu;
+      const u64* e = tbl + (size_t(wi * 8 + b) * 256 + v) * 4;
+#if MB_DEVICE_BUILD
+      const ulonglong2 x = __ldg(reinterpret_cast<const ulonglong2*>(e));
+      const ulonglong2 y = __ldg(reinterpret_cast<const ulonglong2*>(e) + 1);
+      r.s0 ^= x.x;
+      r.s1 ^= x.y;
+      r.s2 ^= y.x;
+      r.s3 ^= y.y;
+#else
+      r.s0 ^= e[0];
+      r.s1 ^= e[1];
+      r.s2 ^= e[2];
+      r.s3 ^= e[3];
+#endif
     }
   }
   return r;
@@ -119,6 +126,23 @@ struct CellSim {
 
   // Phase timing: thread 0 charges the SM-clock cycles since the previous lap to phase `ph`.
   // (No-op in the CPU emulation.)
+  u64 t_sub = 0;
+  MB_FN void sub_begin() {
+#if MB_DEVICE_BUILD
+    if (threadIdx.x == 0) t_sub = static_cast<u64>(clock64());
+#endif
+  }
+  MB_FN void sub_lap(int ph) {
+#if MB_DEVICE_BUILD
+    if (threadIdx.x == 0) {
+      const u64 now = static_cast<u64>(clock64());
+      S.phase_cycles[ph] += now - t_sub;
+      t_sub = now;
+    }
+#else
+    (void)ph;
+#endif
+  }
   u64 t_last = 0;
   MB_FN void lap(int ph) {
 #if MB_DEVICE_BUILD
@@ -178,18 +202,24 @@ struct CellSim {
         for (u32 gi = static_cast<u32>(tid); gi < G; gi += static_cast<u32>(cta.nt())) {
           Xs g{A.rng_state[gi], A.rng_state[G + gi], A.rng_state[2 * G + gi],
                A.rng_state[3 * G + gi]};
-          const Xs nxt = xs_jump(g, static_cast<int>(P.rng_jump_slot));
+          const Xs nxt = xs_jump(g, D.jump_tbl);
           const u64 mask = 2 * u64(P.rng_window) - 1;
           const u64 o0 = wbase + u64(gi) * P.rng_per_thread;
-          for (u32 i = 0; i < P.rng_per_thread; i += 2) {
+          for (u32 i = 0; i < P.rng_per_thread; i += 4) {  // one full 32-byte sector per store
             const u64 a = xs_next(g);
             const u64 b = xs_next(g);
+            const u64 c = xs_next(g);
+            const u64 e = xs_next(g);
             u64* dst = A.rng_ring + ((o0 + i) & mask);
 #if MB_DEVICE_BUILD
-            *reinterpret_cast<ulonglong2*>(dst) = make_ulonglong2(a, b);
+            asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "l"(a), "l"(b),
+                         "l"(c), "l"(e)
+                         : "memory");
 #else
             dst[0] = a;
             dst[1] = b;
+            dst[2] = c;
+            dst[3] = e;
 #endif
           }
           A.rng_state[gi] = nxt.s0;
@@ -1185,39 +1215,63 @@ struct CellSim {
   }
 
   // ------------------------------------------------------------------------------ moves
-  // generate_moves_helper (simulation.cpp:272-297) for one direction: one Normal(speed, sd) per
-  // LEF in index order. The fast ziggurat path uses exactly one draw; the rare slow paths are
-  // evaluated speculatively and stitched into the stream by the leader.
-  MB_FN void generate_moves_dir(u32* moves, double speed, double sd) {
-    const u32 n = S.num_active;
-    if (sd == 0.0) {
-      const u32 mi = static_cast<u32>(round(speed));
-      MB_REGION(cta, tid) {
-        for (u32 i = tid; i < n; i += cta.nt()) moves[i] = mi;
-      }
-      cta.sync();
-      return;
-    }
-    const u32 slack = n / 8 + 64;
-    const u32 span = n + slack;  // offsets examined
+  // std::round(x) for x >= 0 (half away from zero == half up): x - trunc(x) is exact.
+  MB_FN static u32 round_nonneg_u32(double x) {
+    const u32 t = static_cast<u32>(x);
+    return t + ((x - static_cast<double>(t)) >= 0.5 ? 1u : 0u);
+  }
+  // generate_moves_helper (simulation.cpp:272-297): round(max(0, Normal(speed, sd)))
+  MB_FN static u32 move_from_z(double z, double speed, double sd) {
+    const double v = z * sd + speed;
+    return round_nonneg_u32(v < 0.0 ? 0.0 : v);
+  }
+  // value of an accepted fast-path draw (no acceptance test)
+  MB_FN double unit_normal_fast_value(u64 u) const {
+    int bits;
+    const double r = int_float_pair8(u, &bits);
+    const double x = r * A.zig_nx[bits >> 1];
+    return (bits & 1) ? x : -x;
+  }
+
+  // One Normal(speed, sd) per item, items in stream order: the first n_rev items are the rev
+  // moves of LEFs 0..n_rev-1, the others the fwd moves (generate_moves, simulation.cpp:299-330,
+  // draws all rev moves and then all fwd moves). The fast ziggurat path uses exactly one draw;
+  // the rare slow paths are evaluated speculatively and stitched into the stream by the leader.
+  MB_FN void draw_normal_moves(u32 items, u32 n_rev, double rev_speed, double fwd_speed) {
+    const u32 slack = items / 8 + 64;
+    const u32 span = items + slack;  // offsets examined
     const u64 base = S.rng_pos;
     const u64 limit = base + span + 192;
+    sub_begin();
     rng_ensure(limit);
+    sub_lap(kPhMvEnsure);
     // exception records live in scratch: 4 words each {offset, draws consumed, z lo, z hi}
     u32* ex = A.scratch;
     const u32 ex_cap = ((P.n_lefs > P.n_bar ? P.n_lefs : P.n_bar) + 64) / 4;
     PerThread<u64> cnt(cta.nt());
+    PerThread<u32> slow(cta.nt());  // bit k: offset lo + k of this thread's chunk is not fast
     MB_REGION(cta, tid) {
       u32 lo, hi;
       chunk(tid, span, &lo, &hi);
-      u64 c = 0;
-      for (u32 o = lo; o < hi; ++o) {
+      u32 m = 0, c = 0;
+      for (u32 o = lo; o < hi; o += 4) {  // (reads up to 3 draws past hi: inside the staged range)
+        const u64 r0 = raw(base + o), r1 = raw(base + o + 1), r2 = raw(base + o + 2),
+                  r3 = raw(base + o + 3);
         double z;
-        c += !unit_normal_fast(raw(base + o), &z);
+        const u32 k = (o - lo) & 31u;
+        u32 q = 0;
+        if (!unit_normal_fast(r0, &z)) q |= 1u;
+        if (o + 1 < hi && !unit_normal_fast(r1, &z)) q |= 2u;
+        if (o + 2 < hi && !unit_normal_fast(r2, &z)) q |= 4u;
+        if (o + 3 < hi && !unit_normal_fast(r3, &z)) q |= 8u;
+        m |= q << k;
+        c += static_cast<u32>(MB_POPC(q));
       }
+      slow[tid] = m;
       cnt[tid] = c;
     }
     const u64 n_exc = cta.exscan_sum(cnt);
+    sub_lap(kPhMvScan);
     if (n_exc > ex_cap) {
       MB_REGION(cta, tid) {
         if (cta.leader(tid)) fault(kFaultSerialDraws);
@@ -1229,9 +1283,18 @@ struct CellSim {
       u32 lo, hi;
       chunk(tid, span, &lo, &hi);
       u32 j = static_cast<u32>(cnt[tid]);
-      for (u32 o = lo; o < hi; ++o) {
-        double z;
-        if (!unit_normal_fast(raw(base + o), &z)) ex[4 * j++] = o;
+      if (hi - lo <= 32) {
+        u32 m = slow[tid];
+        while (m) {
+          const u32 k = static_cast<u32>(MB_FFS(m)) - 1;
+          m &= m - 1;
+          ex[4 * j++] = lo + k;
+        }
+      } else {  // chunk wider than the mask (never with the CTA widths the launcher uses)
+        for (u32 o = lo; o < hi; ++o) {
+          double z;
+          if (!unit_normal_fast(raw(base + o), &z)) ex[4 * j++] = o;
+        }
       }
     }
     cta.sync();
@@ -1261,7 +1324,7 @@ struct CellSim {
           const u32 off = ex[4 * j];
           if (off < covered) continue;
           const u32 item = off - shift;
-          if (item >= n) break;
+          if (item >= items) break;
           const u32 c = ex[4 * j + 1];
           covered = off + c;
           shift += c - 1;
@@ -1278,9 +1341,11 @@ struct CellSim {
     }
     cta.sync();
     const u32 kept = S.tmp_u32[2];
+    sub_lap(kPhMvExceptions);
+    const double rev_sd = P.rev_std, fwd_sd = P.fwd_std;
     MB_REGION(cta, tid) {
       u32 lo, hi;
-      chunk(tid, n, &lo, &hi);
+      chunk(tid, items, &lo, &hi);
       // first kept exception with item >= lo
       u32 a = 0, b = kept;
       while (a < b) {
@@ -1293,30 +1358,47 @@ struct CellSim {
       }
       u32 e = a;
       u32 shift = e ? ex[4 * (e - 1) + 1] : 0;
-      for (u32 i = lo; i < hi; ++i) {
-        double z;
-        if (e < kept && ex[4 * e] == i) {
+      auto store = [&](u32 item, double z) {
+        if (item < n_rev) {
+          A.rm[item] = move_from_z(z, rev_speed, rev_sd);
+        } else {
+          A.fm[item - n_rev] = move_from_z(z, fwd_speed, fwd_sd);
+        }
+      };
+      u32 i = lo;
+      while (i < hi) {
+        const u32 next_exc = e < kept ? ex[4 * e] : 0xFFFFFFFFu;
+        const u32 run_end = hi < next_exc ? hi : next_exc;  // [i, run_end): fast items
+        const u64 o = base + shift;
+        for (; i + 4 <= run_end; i += 4) {
+          const u64 r0 = raw(o + i), r1 = raw(o + i + 1), r2 = raw(o + i + 2), r3 = raw(o + i + 3);
+          store(i, unit_normal_fast_value(r0));
+          store(i + 1, unit_normal_fast_value(r1));
+          store(i + 2, unit_normal_fast_value(r2));
+          store(i + 3, unit_normal_fast_value(r3));
+        }
+        for (; i < run_end; ++i) store(i, unit_normal_fast_value(raw(o + i)));
+        if (i < hi && i == next_exc) {
           const u64 zb = u64(ex[4 * e + 2]) | (u64(ex[4 * e + 3]) << 32);
+          double z;
 #if MB_DEVICE_BUILD
           z = __longlong_as_double(static_cast<long long>(zb));
 #else
           std::memcpy(&z, &zb, 8);
 #endif
+          store(i, z);
           shift = ex[4 * e + 1];  // later items start after this item's extra draws
           ++e;
-        } else {
-          unit_normal_fast(raw(base + i + shift), &z);
+          ++i;
         }
-        const double v = z * sd + speed;
-        const double clamped = v < 0.0 ? 0.0 : v;  // std::max(0.0, v)
-        moves[i] = static_cast<u32>(round(clamped));
       }
     }
     cta.sync();
     MB_REGION(cta, tid) {
-      if (cta.leader(tid)) S.rng_pos = base + n + S.tmp_u32[3];
+      if (cta.leader(tid)) S.rng_pos = base + items + S.tmp_u32[3];
     }
     cta.sync();
+    sub_lap(kPhMvFinal);
   }
 
   // adjust_moves_of_consecutive_extr_units (simulation.cpp:350-407) + clamp_moves (:332-347).
@@ -1461,8 +1543,23 @@ struct CellSim {
   // generate_moves (simulation.cpp:299-330)
   MB_FN void generate_moves() {
     const bool done = S.burnin_completed != 0;
-    generate_moves_dir(A.rm, done ? P.rev_speed : P.rev_speed_burnin, P.rev_std);
-    generate_moves_dir(A.fm, done ? P.fwd_speed : P.fwd_speed_burnin, P.fwd_std);
+    const double rs = done ? P.rev_speed : P.rev_speed_burnin;
+    const double fs = done ? P.fwd_speed : P.fwd_speed_burnin;
+    const u32 n = S.num_active;
+    const bool draw_r = P.rev_std != 0.0, draw_f = P.fwd_std != 0.0;
+    if (!draw_r || !draw_f) {  // constant moves take no draws
+      const u32 rmi = round_nonneg_u32(rs < 0.0 ? 0.0 : rs), fmi = round_nonneg_u32(fs < 0.0 ? 0.0 : fs);
+      MB_REGION(cta, tid) {
+        for (u32 i = tid; i < n; i += cta.nt()) {
+          if (!draw_r) A.rm[i] = rmi;
+          if (!draw_f) A.fm[i] = fmi;
+        }
+      }
+      cta.sync();
+    }
+    const u32 n_rev = draw_r ? n : 0;
+    const u32 items = n_rev + (draw_f ? n : 0);
+    if (items) draw_normal_moves(items, n_rev, rs, fs);
     lap(kPhMovesGen);
     adjust_and_clamp_moves();
     lap(kPhMovesAdjust);
@@ -1818,6 +1915,10 @@ struct CellSim {
     return kRevPass ? i64(A.rev[idx]) - i64(A.rm[idx]) : -(i64(A.fwd[idx]) + i64(A.fm[idx]));
   }
 
+  // State of the walk after scan position m: `alive` = the unit at m ends the epoch stalled
+  // (collided before this pass, or stalled by this pass assuming its trial succeeds), v = its
+  // final position. A free unit at m is a candidate when alive(m-1) and q[m] <= v(m-1).
+  // One scan over SecOp elements gives every thread the state at the start of its chunk.
   template <bool kRevPass>
   MB_FN void secondary_pass(u32 first, u32 M) {
     if (M < 2) return;
@@ -1826,119 +1927,83 @@ struct CellSim {
     const bool never = P.p_bypass != 0.0 && 1.0 - P.p_bypass == 0.0;  // trials fail, no draws
     const bool draws = P.p_bypass != 0.0 && !never;
     const u32 nwords = (M + 31) / 32 + 2;
-    u32* vbuf = A.scratch;                 // M words: v[m] + bias, 0 = "no live value"
-    u32* bits_fr = A.bits;                 // first-in-run flags of the potential candidates
-    u32* bits_fail = A.bits + nwords;      // failed-trial flags per draw
-    u32* bits_reached = A.bits + 2 * nwords;
-    u32* word_prefix = A.bits + 3 * nwords;  // reached candidates before each word
-    // stored value = v + bias, 0 = none: rev values are positions (>= 0), fwd values are negated
+    u32* vbuf = A.scratch;                  // candidates only: v(m-1) + bias
+    u32* bits_cand = A.bits;                // by scan position: the unit is a candidate
+    u32* bits_first = A.bits + nwords;      // ... directly behind an already stalled unit
+    u32* bits_firstc = A.bits + 2 * nwords;  // by candidate number: first of its run
+    u32* bits_reached = A.bits + 3 * nwords;
+    u32* bits_ok = A.bits + 4 * nwords;
+    u32* bits_fail = A.bits + 5 * nwords;   // by draw
+    // stored value = v + bias: rev values are positions (>= 0), fwd values are negated
     // positions (> -(2^32 - 1))
-    const i64 bias = kRevPass ? i64(1) : i64(0xFFFFFFFFll);
+    const i64 bias = kRevPass ? i64(0) : i64(0xFFFFFFFFll);
 
-    // scan 1: v[m]
-    PerThread<MinPlus> f(cta.nt());
+    PerThread<SecOp> f(cta.nt());
+    sub_begin();
     MB_REGION(cta, tid) {
       u32 lo, hi;
       chunk(tid, M, &lo, &hi);
-      MinPlus acc = minplus_identity();
+      SecOp acc = secop_identity();
       for (u32 m = lo; m < hi; ++m) {
         const u32 idx = sec_idx<kRevPass>(first, m);
         if (coll_occurred(coll[idx])) {
-          acc = minplus_then(acc, minplus_const(sec_q<kRevPass>(idx)));
+          acc = secop_const(sec_q<kRevPass>(idx));
         } else {
-          acc = minplus_then(acc, MinPlus{sec_pos<kRevPass>(idx), 1});
+          acc = secop_then(acc, SecOp{sec_q<kRevPass>(idx), sec_pos<kRevPass>(idx), 1});
         }
       }
       f[tid] = acc;
-    }
-    cta.exscan_minplus(f);
-    const i64 none = -(i64(1) << 50);
-    MB_REGION(cta, tid) {
-      u32 lo, hi;
-      chunk(tid, M, &lo, &hi);
-      i64 x = minplus_apply(f[tid], none);
-      for (u32 m = lo; m < hi; ++m) {
-        const u32 idx = sec_idx<kRevPass>(first, m);
-        if (coll_occurred(coll[idx])) {
-          x = sec_q<kRevPass>(idx);
-        } else {
-          const i64 p = sec_pos<kRevPass>(idx);
-          x = p < x + 1 ? p : x + 1;
-        }
-        const i64 sv = x + bias;
-        vbuf[m] = sv >= 1 ? static_cast<u32>(sv) : 0u;
-      }
-      for (u32 w = tid; w < 4 * nwords; w += cta.nt()) A.bits[w] = 0;
+      for (u32 w = tid; w < 6 * nwords; w += cta.nt()) A.bits[w] = 0;
     }
     cta.sync();
-    // scan 2: is the chain still alive at m-1?  key = last "event" at or before m:
-    // head (stalled unit) -> 2m+1, broken chain (free unit failing the geometric test) -> 2m
-    PerThread<u64> last(cta.nt());
-    auto geom_ok = [&](u32 m) -> bool {  // free unit m would reach / pass the unit at m-1
-      if (m == 0) return false;
-      const u32 vp = vbuf[m - 1];
-      if (vp == 0) return false;
-      const u32 idx = sec_idx<kRevPass>(first, m);
-      return sec_q<kRevPass>(idx) + bias <= i64(vp);
-    };
-    MB_REGION(cta, tid) {
-      u32 lo, hi;
-      chunk(tid, M, &lo, &hi);
-      u64 key = 0;
-      for (u32 m = lo; m < hi; ++m) {
-        const u32 idx = sec_idx<kRevPass>(first, m);
-        if (coll_occurred(coll[idx])) {
-          key = 2 * u64(m) + 1 + 2;
-        } else if (!geom_ok(m)) {
-          key = 2 * u64(m) + 2;
-        }
-      }
-      last[tid] = key;
-    }
-    // exclusive max-scan over threads through the min-plus algebra (b = 0, negated keys)
-    PerThread<MinPlus> g(cta.nt());
-    MB_REGION(cta, tid) { g[tid] = MinPlus{last[tid] ? -i64(last[tid]) : kMinPlusInf, 0}; }
-    cta.exscan_minplus(g);
-    // count the potential candidates per thread
+    sub_lap(kPhSecCompose);
+    cta.exscan_secop(f);
+    sub_lap(kPhSecScan);
     PerThread<u64> cnt(cta.nt());
     MB_REGION(cta, tid) {
       u32 lo, hi;
       chunk(tid, M, &lo, &hi);
-      u64 key = g[tid].a >= kMinPlusInf ? 0 : static_cast<u64>(-g[tid].a);
-      u64 c = 0;
+      bool alive = f[tid].b == kSecConst;
+      i64 v = f[tid].a;
+      bool prev_head = lo > 0 && lo < hi && coll_occurred(coll[sec_idx<kRevPass>(first, lo - 1)]);
+      u32 c = 0;
       for (u32 m = lo; m < hi; ++m) {
         const u32 idx = sec_idx<kRevPass>(first, m);
         if (coll_occurred(coll[idx])) {
-          key = 2 * u64(m) + 1 + 2;
-        } else if (!geom_ok(m)) {
-          key = 2 * u64(m) + 2;
-        } else if (key & 1) {
-          ++c;  // free unit, geometric test passed, chain alive since the last head
+          alive = true;
+          v = sec_q<kRevPass>(idx);
+          prev_head = true;
+          continue;
         }
+        if (alive && sec_q<kRevPass>(idx) <= v) {
+          vbuf[m] = static_cast<u32>(v + bias);
+          MB_ATOMIC_OR_U32(&bits_cand[m >> 5], 1u << (m & 31));
+          if (prev_head) MB_ATOMIC_OR_U32(&bits_first[m >> 5], 1u << (m & 31));
+          const i64 p = sec_pos<kRevPass>(idx);
+          v = p < v + 1 ? p : v + 1;
+          ++c;
+        } else {
+          alive = false;
+        }
+        prev_head = false;
       }
       cnt[tid] = c;
     }
-    const u64 npot = cta.exscan_sum(cnt);
+    const u32 npot = static_cast<u32>(cta.exscan_sum(cnt));  // cnt[tid]: candidates before mine
+    sub_lap(kPhSecClassify);
     if (npot == 0) return;
     if (draws) {
       rng_ensure(S.rng_pos + npot);
-      // first-in-run flags + failed-trial bitmap
       MB_REGION(cta, tid) {
+        // first-in-run flags by candidate number; failed-trial flags by draw
         u32 lo, hi;
         chunk(tid, M, &lo, &hi);
-        u64 key = g[tid].a >= kMinPlusInf ? 0 : static_cast<u64>(-g[tid].a);
         u32 c = static_cast<u32>(cnt[tid]);
         for (u32 m = lo; m < hi; ++m) {
-          const u32 idx = sec_idx<kRevPass>(first, m);
-          if (coll_occurred(coll[idx])) {
-            key = 2 * u64(m) + 1 + 2;
-          } else if (!geom_ok(m)) {
-            key = 2 * u64(m) + 2;
-          } else if (key & 1) {
-            // first of its run when the unit right before it is the head
-            if (key == 2 * u64(m - 1) + 1 + 2) MB_ATOMIC_OR_U32(&bits_fr[c >> 5], 1u << (c & 31));
-            ++c;
-          }
+          if (!((bits_cand[m >> 5] >> (m & 31)) & 1u)) continue;
+          if ((bits_first[m >> 5] >> (m & 31)) & 1u)
+            MB_ATOMIC_OR_U32(&bits_firstc[c >> 5], 1u << (c & 31));
+          ++c;
         }
         for (u32 d = tid; d < npot; d += cta.nt()) {
           if (!bernoulli_raw(raw(S.rng_pos + d), 1.0 - P.p_bypass))
@@ -1946,94 +2011,104 @@ struct CellSim {
         }
       }
       cta.sync();
-      // leader: walk the candidates. A candidate is reached when it is the first of its run or
-      // the previous one was reached and its trial succeeded; only reached candidates draw.
-      // The walk works on one 32-candidate word at a time, held in registers together with the
-      // window of failed-trial bits that starts at the current draw.
-      MB_REGION(cta, tid) {
-        if (cta.leader(tid)) {
-          u32 d = 0;  // draws consumed
-          u32 alive = 0;
-          u32 acc = 0;  // reached candidates so far (== d)
-          const u32 np = static_cast<u32>(npot);
-          const u32 ncw = (np + 31) / 32;
-          for (u32 w = 0; w < ncw; ++w) {
-            const u32 F = bits_fr[w];
-            const u32 lim = np - 32 * w < 32 ? np - 32 * w : 32;
-            // fail bits of draws d, d+1, ... (at most 32 are used by this word)
-            const u32 lo = bits_fail[d >> 5], hi = bits_fail[(d >> 5) + 1];
-            const u32 sh = d & 31;
-            const u32 fb = sh ? ((lo >> sh) | (hi << (32 - sh))) : lo;
-            u32 R = 0, k = 0;
-            for (u32 i = 0; i < lim; ++i) {
-              const u32 reach = ((F >> i) & 1u) | alive;
-              R |= reach << i;
-              alive = reach & ~(fb >> k) & 1u;
-              k += reach;
-            }
-            bits_reached[w] = R;
-            word_prefix[w] = acc;
-            acc += k;
-            d += k;
+      sub_lap(kPhSecDraws);
+      // Walk the candidates in order. A candidate is reached when it is the first of its run or
+      // the previous one was reached and its trial succeeded; only reached candidates draw, so
+      // the d-th draw belongs to the d-th reached candidate.
+      const u32 ncw = (npot + 31) / 32;
+#if MB_DEVICE_BUILD
+      // Warp 0, one lane per candidate, 32 candidates at a time: start from "every candidate
+      // that can be reached is", look up each lane's draw, drop the candidates behind a failed
+      // trial, and repeat until nothing changes (a fixed point satisfies the sequential
+      // recurrence, and candidate i is final after i + 1 rounds at the latest).
+      if (threadIdx.x < 32) {
+        const u32 lane = threadIdx.x;
+        const u32 lt = (1u << lane) - 1u;
+        u32 d = 0, alive_in = 0;
+        for (u32 w = 0; w < ncw; ++w) {
+          const u32 F = bits_firstc[w];
+          const u32 nvalid = npot - 32 * w < 32 ? npot - 32 * w : 32;
+          const u32 Fle = F & (lt | (1u << lane));
+          const u32 s = Fle ? 31u - static_cast<u32>(__clz(static_cast<int>(Fle))) : 0u;
+          const u32 range = lt & ~((1u << s) - 1u);  // candidates of my run before me
+          const bool can = lane < nvalid && (Fle != 0 || alive_in != 0);
+          u32 R = __ballot_sync(0xffffffffu, can);
+          u32 bad = 0;
+          for (int it = 0; it < 34; ++it) {
+            const u32 dd = d + static_cast<u32>(__popc(R & lt));
+            const u32 fbit = (bits_fail[dd >> 5] >> (dd & 31)) & 1u;
+            bad = __ballot_sync(0xffffffffu, ((R >> lane) & 1u) && fbit);
+            const u32 Rn = __ballot_sync(0xffffffffu, can && (bad & range) == 0);
+            if (Rn == R) break;
+            R = Rn;
           }
-          for (u32 w = ncw; w < nwords; ++w) word_prefix[w] = acc;
-          S.tmp_u32[4] = d;
+          if (lane == 0) {
+            bits_reached[w] = R;
+            bits_ok[w] = R & ~bad;
+          }
+          d += static_cast<u32>(__popc(R));
+          alive_in = ((R & ~bad) >> 31) & 1u;
         }
+        if (lane == 0) S.tmp_u32[4] = d;
       }
+#else
+      {
+        u32 d = 0, alive = 0;
+        for (u32 w = 0; w < ncw; ++w) {
+          const u32 F = bits_firstc[w];
+          const u32 lim = npot - 32 * w < 32 ? npot - 32 * w : 32;
+          u32 R = 0, OK = 0;
+          for (u32 i = 0; i < lim; ++i) {
+            const u32 reach = ((F >> i) & 1u) | alive;
+            alive = reach & ~(bits_fail[d >> 5] >> (d & 31)) & 1u;
+            R |= reach << i;
+            OK |= alive << i;
+            d += reach;
+          }
+          bits_reached[w] = R;
+          bits_ok[w] = OK;
+        }
+        S.tmp_u32[4] = d;
+      }
+#endif
       cta.sync();
+      sub_lap(kPhSecLeader);
     }
-    // apply
+    // apply. Without draws: bypass == 0 -> every candidate is reached and stalls; bypass == 1 ->
+    // only the first candidate behind a stalled unit is reached, and it passes.
     MB_REGION(cta, tid) {
       u32 lo, hi;
       chunk(tid, M, &lo, &hi);
-      u64 key = g[tid].a >= kMinPlusInf ? 0 : static_cast<u64>(-g[tid].a);
       u32 c = static_cast<u32>(cnt[tid]);
       for (u32 m = lo; m < hi; ++m) {
+        if (!((bits_cand[m >> 5] >> (m & 31)) & 1u)) continue;
+        bool reached, ok;
+        if (draws) {
+          reached = (bits_reached[c >> 5] >> (c & 31)) & 1u;
+          ok = (bits_ok[c >> 5] >> (c & 31)) & 1u;
+        } else if (never) {
+          reached = (bits_first[m >> 5] >> (m & 31)) & 1u;
+          ok = false;
+        } else {
+          reached = ok = true;
+        }
+        ++c;
+        if (!reached) continue;
         const u32 idx = sec_idx<kRevPass>(first, m);
-        if (coll_occurred(coll[idx])) {
-          key = 2 * u64(m) + 1 + 2;
-        } else if (!geom_ok(m)) {
-          key = 2 * u64(m) + 2;
-        } else if (key & 1) {
-          bool reached = true, ok = true;
-          if (never) {
-            reached = key == 2 * u64(m - 1) + 1 + 2;  // only the first unit behind a head
-            ok = false;
-          } else if (draws) {
-            const u32 w = bits_reached[c >> 5];
-            reached = (w >> (c & 31)) & 1u;
-            if (reached) {
-#if MB_DEVICE_BUILD
-              const u32 before = word_prefix[c >> 5] + __popc(w & ((1u << (c & 31)) - 1));
-#else
-              const u32 before =
-                  word_prefix[c >> 5] + __builtin_popcount(w & ((1u << (c & 31)) - 1));
-#endif
-              ok = !((bits_fail[before >> 5] >> (before & 31)) & 1u);
-            }
-          }
-          if (reached) {
-            const u32 blocker = sec_idx<kRevPass>(first, m - 1);
-            if (ok) {
-              const i64 vprev = i64(vbuf[m - 1]) - bias;
-              const i64 mv = sec_pos<kRevPass>(idx) - vprev;  // distance to the blocker's site
-              moves[idx] = static_cast<u32>(mv > 0 ? mv - 1 : 0);
-              coll[idx] = coll_make(blocker, kEvCollision | kEvSecondary);
-            } else {
-              coll[idx] = coll_make(blocker, kEvSecondary);
-            }
-          }
-          ++c;
+        const u32 blocker = sec_idx<kRevPass>(first, m - 1);
+        if (ok) {
+          const i64 vprev = i64(vbuf[m]) - bias;
+          const i64 mv = sec_pos<kRevPass>(idx) - vprev;  // distance to the blocker's site
+          moves[idx] = static_cast<u32>(mv > 0 ? mv - 1 : 0);
+          coll[idx] = coll_make(blocker, kEvCollision | kEvSecondary);
+        } else {
+          coll[idx] = coll_make(blocker, kEvSecondary);
         }
       }
+      if (draws && cta.leader(tid)) S.rng_pos += S.tmp_u32[4];
     }
     cta.sync();
-    if (draws) {
-      MB_REGION(cta, tid) {
-        if (cta.leader(tid)) S.rng_pos += S.tmp_u32[4];
-      }
-      cta.sync();
-    }
+    sub_lap(kPhSecApply);
   }
 
   MB_FN void process_secondary_lef_lef_collisions() {

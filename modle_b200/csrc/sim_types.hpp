@@ -57,6 +57,17 @@ enum : int {
   kPhExtrudeRelease,
   kPhRngGenerate,  // nested inside the phases above (time spent refilling the RNG ring)
   kPhTotal,
+  // finer split of the two heaviest phases (nested; profiling builds read them the same way)
+  kPhMvEnsure,
+  kPhMvScan,
+  kPhMvExceptions,
+  kPhMvFinal,
+  kPhSecCompose,
+  kPhSecScan,
+  kPhSecClassify,
+  kPhSecDraws,
+  kPhSecLeader,
+  kPhSecApply,
   kNumPhases
 };
 
@@ -98,6 +109,7 @@ struct IntervalData {
   const double* zig_ny;         // 129
   const double* zig_ex;         // 257: unit exponential
   const double* zig_ey;         // 257
+  const u64* jump_tbl;          // byte-indexed T^W table of the staging configuration (sim_core)
 };
 
 struct CellTaskDev {
@@ -145,7 +157,7 @@ struct CellArrays {
   u32 *rm, *fm;         // moves
   u32 *rc, *fc;         // collision words
   u32* scratch;         // max(n_lefs, n_bar) + 64 words
-  u32* bits;            // 4 * (n_lefs/32 + 3) words: bitmaps of the secondary-collision pass
+  u32* bits;            // 6 * (n_lefs/32 + 3) words: bitmaps of the secondary-collision pass
   u32* bar_pos;         // n_bar (copy of IntervalData::bar_pos)
   u8* bar_active;       // n_bar bytes (0/1)
   double* zig_nx;       // 129 (copy)
@@ -158,7 +170,7 @@ struct CellArrays {
 MB_HD size_t cell_scratch_words(u32 n_lefs, u32 n_bar) {
   return size_t(n_lefs > n_bar ? n_lefs : n_bar) + 64;
 }
-MB_HD size_t cell_bits_words(u32 n_lefs) { return size_t(4) * (n_lefs / 32 + 3); }
+MB_HD size_t cell_bits_words(u32 n_lefs) { return size_t(6) * (n_lefs / 32 + 3); }
 MB_HD size_t cell_array_bytes(u32 n_lefs, u32 n_bar) {
   size_t w = 0;
   w += 260;                                // zig_nx: 129 doubles (+ pad)

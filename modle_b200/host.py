@@ -91,7 +91,9 @@ EXPORTED_SYMBOLS = [
 
 PHASE_NAMES = ["init", "burnin", "bind", "rank", "contacts", "moves_generate", "moves_adjust",
                "barrier_states", "lef_bar", "primary", "correct_moves", "secondary", "fix_ranks",
-               "extrude_release", "rng_refill(nested)", "total"]
+               "extrude_release", "rng_refill(nested)", "total",
+               "mv.ensure", "mv.scan", "mv.exceptions", "mv.final",
+               "sec.compose", "sec.scan", "sec.classify", "sec.draws", "sec.leader", "sec.apply"]
 
 
 def check(rc):

@@ -11,10 +11,10 @@
 #include "../../modle_b200/csrc/launch_prep.hpp"
 #include "../../modle_b200/csrc/sim_core.hpp"
 
-namespace modle_b200 {
-u64 g_emu_jump[kJumpSlots][1024];
-}
 using namespace modle_b200;
+namespace {
+std::vector<u64> g_emu_jump[kJumpSlots];
+}
 
 namespace {
 
@@ -37,11 +37,11 @@ struct EmuCell {
                                                      static_cast<u32>(nb));
     const std::string err = prepare_interval(p, iv, bars, nb, sc, &kp, &hd);
     if (!err.empty()) return err;
-    static bool built[kJumpSlots] = {false, false};
-    if (!built[sc.jump_slot]) {
-      build_jump_table(sc.window, g_emu_jump[sc.jump_slot]);
-      built[sc.jump_slot] = true;
+    if (g_emu_jump[sc.jump_slot].empty()) {
+      g_emu_jump[sc.jump_slot].resize(kJumpTableWords);
+      build_jump_table(sc.window, g_emu_jump[sc.jump_slot].data());
     }
+    D.jump_tbl = g_emu_jump[sc.jump_slot].data();
     D.bar_pos = hd.bar_pos.data();
     D.bar_dir_rev = hd.bar_dir_rev.data();
     D.bar_stp_active = hd.stp_active.data();
@@ -258,7 +258,7 @@ int emu_rank_lefs(const u64* rev, const u64* fwd, const u64* ep, u64* rr, u64* f
   return 0;
 }
 
-// n Normal(speed, sd) moves through the kernel's generate_moves_dir (all LEFs bound), starting at
+// n Normal(speed, sd) moves through the kernel's draw_normal_moves (all LEFs bound), starting at
 // draw 0 of PRNG state `state`; returns the number of raw draws consumed.
 long long emu_sample_moves(const u64* state, size_t n, double speed, double sd, u64* moves_out,
                            int virtual_threads, int staging) {
@@ -274,6 +274,7 @@ long long emu_sample_moves(const u64* state, size_t n, double speed, double sd, 
   Cta cta{&cell.shared->scratch, virtual_threads};
   modle_b200_cell_task t{};
   for (int i = 0; i < 4; ++i) t.rng_state[i] = state[i];
+  cell.kp.rev_std = sd;
   CellSim sim{cell.kp, cell.D, cell.A, *cell.shared, K, cta, to_task(t)};
   sim.init_cell();
   cell.shared->num_active = static_cast<u32>(n);
@@ -281,7 +282,7 @@ long long emu_sample_moves(const u64* state, size_t n, double speed, double sd, 
     cell.A.rev[i] = cell.A.fwd[i] = 500000;
     cell.A.ep[i] = 0;
   }
-  sim.generate_moves_dir(cell.A.rm, speed, sd);
+  sim.draw_normal_moves(static_cast<u32>(n), static_cast<u32>(n), speed, speed);
   for (size_t i = 0; i < n; ++i) moves_out[i] = cell.A.rm[i];
   if (cell.shared->fault) return -100 - static_cast<long long>(cell.shared->fault);
   return static_cast<long long>(cell.shared->rng_pos);

@@ -1,0 +1,85 @@
+"""Multi-GPU host logic on CPU: the shard planner, and the sharded runner over a world_size-2
+gloo group with the kernel emulation as the compute engine (results must equal the oracle's
+unsharded run bit for bit, whatever the split)."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from modle_b200 import distributed
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
+@pytest.mark.parametrize("num_lefs,cells", [([4979], 8192), ([1289, 900, 0, 3000, 40], 512),
+                                            ([100] * 24, 7), ([5000, 10], 1)])
+def test_plan_covers_every_cell_once(world, num_lefs, cells):
+    shards = distributed.plan_shards(num_lefs, cells, world)
+    assert shards == distributed.plan_shards(num_lefs, cells, world)  # deterministic
+    for i, n in enumerate(num_lefs):
+        mine = sorted((s.cell_lo, s.cell_hi) for s in shards if s.interval == i)
+        if n == 0:
+            assert mine == []
+            continue
+        assert mine[0][0] == 0 and mine[-1][1] == cells
+        assert all(a[1] == b[0] for a, b in zip(mine, mine[1:]))
+    assert all(0 <= s.rank < world for s in shards)
+
+
+def test_plan_balances_and_prefers_whole_intervals():
+    # one big chromosome, 8 ranks: equal cell ranges, one per rank
+    sh = distributed.plan_shards([4979], 8192, 8)
+    assert sorted(s.rank for s in sh) == list(range(8))
+    assert {s.cell_hi - s.cell_lo for s in sh} == {1024}
+    # many similar intervals: nothing is split
+    sh = distributed.plan_shards([1000 + 10 * i for i in range(24)], 512, 4)
+    assert all(s.cell_lo == 0 and s.cell_hi == 512 for s in sh)
+    load = [sum(s.weight for s in sh if s.rank == r) for r in range(4)]
+    assert max(load) <= 1.10 * sum(load) / 4
+    roots = distributed.interval_roots(distributed.plan_shards([4979], 8192, 8))
+    assert roots[0][0] == 0 and len(roots[0][1]) == 8
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.parametrize("force_split", [False, True])
+def test_run_sharded_world2_gloo_matches_oracle(tmp_path, force_split):
+    from dist_worker import make_genome
+    from oracle import pyoracle
+
+    port = _free_port()
+    procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "dist_worker.py"), str(r), "2",
+                               str(port), str(tmp_path), "1" if force_split else "0"])
+             for r in range(2)]
+    for pr in procs:
+        assert pr.wait(timeout=600) == 0
+    res = [np.load(tmp_path / f"rank{r}.npz") for r in range(2)]
+    p, genome = make_genome()
+    for idx, (name, iv, bars) in enumerate(genome):
+        if len(bars) == 0:  # skipped like the reference does (scheduler_simulate.cpp:111-124)
+            assert all(f"band{idx}" not in r for r in res)
+            continue
+        from modle_b200 import host
+
+        tasks = host.make_cell_tasks(p, name, iv)
+        band, occ, stats, missed = pyoracle.simulate_interval(p, iv, bars, tasks, nthreads=4)
+        holders = [r for r in res if f"band{idx}" in r]
+        assert holders
+        root = int(holders[0][f"root{idx}"][0])
+        assert all(int(r[f"root{idx}"][0]) == root for r in holders)
+        rr = res[root]
+        assert np.array_equal(rr[f"band{idx}"], band), name
+        assert np.array_equal(rr[f"occ{idx}"][:len(occ)], occ), name
+        assert int(rr[f"missed{idx}"][0]) == missed
+        assert sum(int(r[f"ncells{idx}"][0]) for r in holders) == len(tasks)
+        assert sum(int(r[f"contacts{idx}"][0]) for r in holders) == int(stats["num_contacts"].sum())
+    if force_split:
+        assert int(res[0]["calls"][0]) == 1 and int(res[1]["calls"][0]) == 2
