@@ -1315,31 +1315,111 @@ struct CellSim {
       }
     }
     cta.sync();
-    // leader: keep the exceptions that start an item (not swallowed by an earlier slow path) and
-    // turn their offsets into item indices. Record j becomes {item, cumulative extra draws, z}.
-    MB_REGION(cta, tid) {
-      if (cta.leader(tid)) {
-        u32 covered = 0, shift = 0, kept = 0;
-        for (u32 j = 0; j < n_exc; ++j) {
+    // Keep the exceptions that start an item (not swallowed by an earlier slow path) and turn
+    // their offsets into item indices: record j becomes {item, cumulative extra draws, z}.
+    if (n_exc <= static_cast<u64>(cta.nt())) {
+      // Parallel form. An exception nothing before it can reach is certainly kept and cuts the
+      // list into independent clusters; clusters (1-3 records) are resolved by their heads.
+      MB_REGION(cta, tid) {
+        const u32 j = static_cast<u32>(tid);
+        if (j < n_exc) {
           const u32 off = ex[4 * j];
-          if (off < covered) continue;
-          const u32 item = off - shift;
-          if (item >= items) break;
-          const u32 c = ex[4 * j + 1];
-          covered = off + c;
-          shift += c - 1;
-          ex[4 * kept] = item;
-          ex[4 * kept + 1] = shift;
-          ex[4 * kept + 2] = ex[4 * j + 2];
-          ex[4 * kept + 3] = ex[4 * j + 3];
-          ++kept;
+          bool head = true;
+          for (u32 i = j; i-- > 0;) {
+            const u32 oi = ex[4 * i];
+            if (off - oi >= 256u) break;  // a slow path never takes that many draws (cursor limit)
+            if (oi + (ex[4 * i + 1] & 0xFFFFu) > off) {
+              head = false;
+              break;
+            }
+          }
+          if (head) ex[4 * j + 1] |= 0x80000000u;
         }
-        S.tmp_u32[2] = kept;
-        S.tmp_u32[3] = shift;
-        if (shift > slack) fault(kFaultRngWindow);
+        if (cta.leader(tid)) {
+          S.tmp_u32[2] = 0;
+          S.tmp_u32[3] = 0;
+        }
       }
+      cta.sync();
+      MB_REGION(cta, tid) {
+        const u32 j = static_cast<u32>(tid);
+        if (j < n_exc && (ex[4 * j + 1] & 0x80000000u)) {
+          u32 covered = ex[4 * j] + (ex[4 * j + 1] & 0xFFFFu);
+          ex[4 * j + 1] |= 0x40000000u;  // kept
+          for (u32 k = j + 1; k < n_exc && !(ex[4 * k + 1] & 0x80000000u); ++k) {
+            if (ex[4 * k] >= covered) {
+              ex[4 * k + 1] |= 0x40000000u;
+              covered = ex[4 * k] + (ex[4 * k + 1] & 0xFFFFu);
+            }
+          }
+        }
+      }
+      cta.sync();
+      PerThread<u64> ks(cta.nt());  // low word: kept records, high word: extra draws
+      MB_REGION(cta, tid) {
+        const u32 j = static_cast<u32>(tid);
+        u64 v = 0;
+        if (j < n_exc && (ex[4 * j + 1] & 0x40000000u))
+          v = u64(1) | (u64((ex[4 * j + 1] & 0xFFFFu) - 1) << 32);
+        ks[tid] = v;
+      }
+      cta.exscan_sum(ks);
+      PerThread<u64> st_a(cta.nt()), st_z(cta.nt());
+      PerThread<u32> st_dest(cta.nt());
+      MB_REGION(cta, tid) {
+        const u32 j = static_cast<u32>(tid);
+        u32 dest = 0xFFFFFFFFu;
+        if (j < n_exc && (ex[4 * j + 1] & 0x40000000u)) {
+          const u32 shift_before = static_cast<u32>(ks[tid] >> 32);
+          const u32 item = ex[4 * j] - shift_before;
+          if (item < items) {
+            const u32 shift_after = shift_before + (ex[4 * j + 1] & 0xFFFFu) - 1;
+            dest = static_cast<u32>(ks[tid] & 0xFFFFFFFFu);
+            st_a[tid] = u64(item) | (u64(shift_after) << 32);
+            st_z[tid] = u64(ex[4 * j + 2]) | (u64(ex[4 * j + 3]) << 32);
+            MB_ATOMIC_MAX_U32(&S.tmp_u32[2], dest + 1);
+            MB_ATOMIC_MAX_U32(&S.tmp_u32[3], shift_after);
+          }
+        }
+        st_dest[tid] = dest;
+      }
+      cta.sync();
+      MB_REGION(cta, tid) {
+        const u32 dest = st_dest[tid];
+        if (dest != 0xFFFFFFFFu) {
+          ex[4 * dest] = static_cast<u32>(st_a[tid] & 0xFFFFFFFFu);
+          ex[4 * dest + 1] = static_cast<u32>(st_a[tid] >> 32);
+          ex[4 * dest + 2] = static_cast<u32>(st_z[tid] & 0xFFFFFFFFu);
+          ex[4 * dest + 3] = static_cast<u32>(st_z[tid] >> 32);
+        }
+        if (cta.leader(tid) && S.tmp_u32[3] > slack) fault(kFaultRngWindow);
+      }
+      cta.sync();
+    } else {
+      MB_REGION(cta, tid) {
+        if (cta.leader(tid)) {
+          u32 covered = 0, shift = 0, kept = 0;
+          for (u32 j = 0; j < n_exc; ++j) {
+            const u32 off = ex[4 * j];
+            if (off < covered) continue;
+            const u32 item = off - shift;
+            if (item >= items) break;
+            const u32 c = ex[4 * j + 1];
+            covered = off + c;
+            shift += c - 1;
+            ex[4 * kept] = item;
+            ex[4 * kept + 1] = shift;
+            ex[4 * kept + 2] = ex[4 * j + 2];
+            ex[4 * kept + 3] = ex[4 * j + 3];
+            ++kept;
+          }
+          S.tmp_u32[2] = kept;
+          S.tmp_u32[3] = shift;
+          if (shift > slack) fault(kFaultRngWindow);
+        }
+      }
+      cta.sync();
     }
-    cta.sync();
     const u32 kept = S.tmp_u32[2];
     sub_lap(kPhMvExceptions);
     const double rev_sd = P.rev_std, fwd_sd = P.fwd_std;
@@ -1404,6 +1484,43 @@ struct CellSim {
   // adjust_moves_of_consecutive_extr_units (simulation.cpp:350-407) + clamp_moves (:332-347).
   // The two neighbour recurrences are min-plus prefix scans; the handful of units close enough
   // to an interval end for the reference's "skip" rule to fire are finished serially.
+  // Hinted forms for callers that query increasing thresholds: `from` is a lower bound of the
+  // answer (the previous answer); a few linear steps, then binary search on what is left.
+  MB_FN u32 count_rev_le_from(u64 thr, u32 from) const {
+    u32 a = from;
+    const u32 n = S.num_active;
+    for (int step = 0; step < 4; ++step) {
+      if (a >= n || u64(A.rev[A.rr[a]]) > thr) return a;
+      ++a;
+    }
+    u32 b = n;
+    while (a < b) {
+      const u32 m = (a + b) >> 1;
+      if (u64(A.rev[A.rr[m]]) <= thr) {
+        a = m + 1;
+      } else {
+        b = m;
+      }
+    }
+    return a;
+  }
+  MB_FN u32 count_fwd_lt_from(u64 thr, u32 from, u32 limit) const {  // over ranks [0, limit)
+    u32 a = from;
+    for (int step = 0; step < 4; ++step) {
+      if (a >= limit || u64(A.fwd[A.fr[a]]) >= thr) return a;
+      ++a;
+    }
+    u32 b = limit;
+    while (a < b) {
+      const u32 m = (a + b) >> 1;
+      if (u64(A.fwd[A.fr[m]]) < thr) {
+        a = m + 1;
+      } else {
+        b = m;
+      }
+    }
+    return a;
+  }
   MB_FN u32 count_rev_le(u64 thr) const {  // number of rev ranks with pos <= thr (binary search)
     u32 a = 0, b = S.num_active;
     while (a < b) {
@@ -1630,10 +1747,13 @@ struct CellSim {
   // tests exactly one unit: the first rev unit downstream of it / the last fwd unit upstream of
   // it; the closest successful barrier wins. Bernoulli draws (fractional pblock only) are taken
   // in barrier order, rev pass (ascending) then fwd pass (descending).
-  MB_FN bool lef_bar_candidate_rev(u32 b, u32 j0, u32* unit) const {
+  // *hint: answer of the previous (smaller or equal) barrier position handled by this thread,
+  // 0xFFFFFFFF = none yet
+  MB_FN bool lef_bar_candidate_rev(u32 b, u32 j0, u32* unit, u32* hint) const {
     const u32 n = S.num_active;
     const u32 bp = A.bar_pos[b];
-    u32 j = count_rev_le(bp);  // first rank with pos > bp
+    u32 j = *hint == 0xFFFFFFFFu ? count_rev_le(bp) : count_rev_le_from(bp, *hint);
+    *hint = j;  // first rank with pos > bp
     if (j < j0) j = j0;
     if (j >= n) return false;
     const u32 idx = A.rr[j];
@@ -1642,9 +1762,11 @@ struct CellSim {
     *unit = idx;
     return pos - bp <= A.rm[idx];
   }
-  MB_FN bool lef_bar_candidate_fwd(u32 b, u32 jend, u32* unit) const {
+  MB_FN bool lef_bar_candidate_fwd(u32 b, u32 jend, u32* unit, u32* hint) const {
     const u32 bp = A.bar_pos[b];
-    const u32 c = count_fwd_lt(bp);  // ranks [0, c) have pos < bp
+    const u32 c = *hint == 0xFFFFFFFFu ? count_fwd_lt(bp)
+                                       : count_fwd_lt_from(bp, *hint, S.num_active);
+    *hint = c;  // ranks [0, c) have pos < bp
     if (c == 0) return false;
     u32 j = c - 1;
     if (j > jend) j = jend;
@@ -1666,14 +1788,17 @@ struct CellSim {
     const bool frac_min = pmin != 0.0 && pmin != 1.0;
     const u32 tmp_ev = kEvTmp | kEvCollision | kEvLefBar;
     if (!frac_maj && !frac_min) {
+      // (independent full binary searches per barrier: measured faster than walking each
+      // thread's barriers in order with the previous answer as a hint)
       MB_REGION(cta, tid) {
         for (u32 b = tid; b < nb; b += cta.nt()) {
           if (!A.bar_active[b]) continue;
           const bool brev = bar_blocks_rev(b);
           u32 unit;
-          if ((brev ? pmaj : pmin) == 1.0 && lef_bar_candidate_rev(b, j0, &unit))
+          u32 nohint_r = 0xFFFFFFFFu, nohint_f = 0xFFFFFFFFu;
+          if ((brev ? pmaj : pmin) == 1.0 && lef_bar_candidate_rev(b, j0, &unit, &nohint_r))
             MB_ATOMIC_MAX_U32(&A.rc[unit], coll_make(b, tmp_ev));
-          if ((brev ? pmin : pmaj) == 1.0 && lef_bar_candidate_fwd(b, jend, &unit))
+          if ((brev ? pmin : pmaj) == 1.0 && lef_bar_candidate_fwd(b, jend, &unit, &nohint_f))
             MB_ATOMIC_MAX_U32(&A.fc[unit], coll_make(nb - 1 - b, tmp_ev));
         }
       }
@@ -1692,8 +1817,9 @@ struct CellSim {
             const bool brev = bar_blocks_rev(b);
             const double pb = (pass == 0) == brev ? pmaj : pmin;
             u32 unit;
-            const bool cand = pass == 0 ? lef_bar_candidate_rev(b, j0, &unit)
-                                        : lef_bar_candidate_fwd(b, jend, &unit);
+            u32 nohint = 0xFFFFFFFFu;
+            const bool cand = pass == 0 ? lef_bar_candidate_rev(b, j0, &unit, &nohint)
+                                        : lef_bar_candidate_fwd(b, jend, &unit, &nohint);
             if (cand && pb != 0.0 && pb != 1.0) ++c;
           }
           cnt[tid] = c;
@@ -1710,8 +1836,9 @@ struct CellSim {
             const bool brev = bar_blocks_rev(b);
             const double pb = (pass == 0) == brev ? pmaj : pmin;
             u32 unit;
-            const bool cand = pass == 0 ? lef_bar_candidate_rev(b, j0, &unit)
-                                        : lef_bar_candidate_fwd(b, jend, &unit);
+            u32 nohint = 0xFFFFFFFFu;
+            const bool cand = pass == 0 ? lef_bar_candidate_rev(b, j0, &unit, &nohint)
+                                        : lef_bar_candidate_fwd(b, jend, &unit, &nohint);
             if (!cand) continue;
             bool hit;
             if (pb == 1.0) {
@@ -1768,19 +1895,13 @@ struct CellSim {
   // pairs are the places of the merged 5'->3' order where a fwd unit is directly followed by a
   // rev unit; pairs are disjoint, so they are resolved independently. Bernoulli(1-bypass) draws
   // go to the geometrically colliding pairs in ascending order.
-  MB_FN bool primary_pair(u32 j, u32 n5, u32 i2, u32* r_out, u32* f_out) const {
+  // *hint: the fwd rank found for the previous (lower) rev rank of this thread, 0xFFFFFFFF = none
+  MB_FN bool primary_pair(u32 j, u32 n5, u32 i2, u32* r_out, u32* f_out, u32* hint) const {
     const u32 r = A.rr[j];
     const u32 rp = A.rev[r];
     // first fwd rank in [0, i2) with pos >= rp
-    u32 a = 0, b = i2;
-    while (a < b) {
-      const u32 m = (a + b) >> 1;
-      if (A.fwd[A.fr[m]] < rp) {
-        a = m + 1;
-      } else {
-        b = m;
-      }
-    }
+    const u32 a = count_fwd_lt_from(rp, *hint == 0xFFFFFFFFu ? 0u : *hint, i2);
+    *hint = a;
     if (a == i2 || a == 0) return false;
     const u32 f = A.fr[a - 1];
     if (j > n5 && A.rev[A.rr[j - 1]] > A.fwd[f]) return false;
@@ -1833,9 +1954,12 @@ struct CellSim {
         u32 lo, hi;
         chunk(tid, M, &lo, &hi);
         u64 c = 0;
+        u32 hint = 0xFFFFFFFFu;
         for (u32 m = lo; m < hi; ++m) {
           u32 r, f;
-          c += primary_pair(n5 + m, n5, i2, &r, &f);
+          const bool is_pair = primary_pair(n5 + m, n5, i2, &r, &f, &hint);
+          A.scratch[m] = is_pair ? f : 0xFFFFFFFFu;  // remembered for the pass that draws
+          c += is_pair;
         }
         cnt[tid] = c;
       }
@@ -1846,10 +1970,17 @@ struct CellSim {
       u32 lo, hi;
       chunk(tid, M, &lo, &hi);
       u64 o = S.rng_pos + (draws ? cnt[tid] : 0);
+      u32 hint = 0xFFFFFFFFu;
       for (u32 m = lo; m < hi; ++m) {
         u32 r, f;
-        if (!primary_pair(n5 + m, n5, i2, &r, &f)) continue;
-        if (draws && !bernoulli_raw(raw(o++), 1.0 - P.p_bypass)) continue;
+        if (draws) {
+          f = A.scratch[m];
+          if (f == 0xFFFFFFFFu) continue;
+          r = A.rr[n5 + m];
+          if (!bernoulli_raw(raw(o++), 1.0 - P.p_bypass)) continue;
+        } else if (!primary_pair(n5 + m, n5, i2, &r, &f, &hint)) {
+          continue;
+        }
         primary_apply(r, f);
       }
     }

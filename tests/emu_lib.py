@@ -114,3 +114,18 @@ def rank_lefs(rev, fwd, ep, rr, fr, virtual_threads=7):
     _check(lib().emu_rank_lefs(rev.ctypes.data, fwd.ctypes.data, ep.ctypes.data, rr.ctypes.data,
                                fr.ctypes.data, len(rev), virtual_threads))
     return rr, fr
+
+
+def sample_moves(state, n, speed, sd, virtual_threads=64, staging=0):
+    """n moves round(max(0, Normal(speed, sd))) through the kernel's draw_normal_moves; returns
+    (moves, raw draws consumed)."""
+    L = lib()
+    L.emu_sample_moves.restype = C.c_longlong
+    L.emu_sample_moves.argtypes = [C.POINTER(C.c_uint64), C.c_size_t, C.c_double, C.c_double,
+                                   C.c_void_p, C.c_int, C.c_int]
+    st = (C.c_uint64 * 4)(*[int(x) for x in state])
+    out = np.zeros(n, dtype=np.uint64)
+    rc = L.emu_sample_moves(st, n, speed, sd, out.ctypes.data, virtual_threads, staging)
+    if rc < 0:
+        raise RuntimeError(f"emu_sample_moves failed: {rc} {L.emu_last_error().decode()}")
+    return out, int(rc)

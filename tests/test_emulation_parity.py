@@ -147,3 +147,19 @@ def test_rank_lefs_fuzz_with_ties():
         a = pyoracle.rank_lefs(rev, fwd, ep, rr0, fr0)
         b = emu_lib.rank_lefs(rev, fwd, ep, rr0, fr0)
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), seed
+
+
+@pytest.mark.parametrize("n,vt", [(300, 64), (5000, 512), (10000, 512), (10000, 16), (777, 1)])
+@pytest.mark.parametrize("seed", [1, 20260117])
+def test_move_generation_stream_order(n, vt, seed):
+    """draw_normal_moves (parallel over the raw stream, slow ziggurat paths stitched in) against
+    the oracle's sequential Normal draws: same moves, same number of raw draws. The large cases
+    hold > 100 slow-path draws, some of them swallowed by an earlier slow path."""
+    from modle_b200 import host
+
+    state = host.rng_seed(seed)
+    z, _, draws = pyoracle.sample("normal", n, state, 4000.0, 200.0)
+    expect = np.floor(np.maximum(z, 0.0) + 0.5).astype(np.uint64)  # == std::round for x >= 0 here
+    moves, used = emu_lib.sample_moves(state, n, 4000.0, 200.0, virtual_threads=vt)
+    assert used == draws
+    assert np.array_equal(moves, expect)
