@@ -42,6 +42,9 @@ struct CtaScratch {
   u64 warp_u64[kMaxWarps];
   u64 warp_u64b[kMaxWarps];
   u64 warp_u64c[kMaxWarps];
+  u64 warp_u64d[kMaxWarps];
+  u64 warp_u64e[kMaxWarps];
+  u64 warp_u64f[kMaxWarps];
   double warp_f64[kMaxWarps];
   u64 bcast_u64;
   double bcast_f64;
@@ -251,6 +254,58 @@ struct Cta {
     return res;
   }
 
+  // Two independent MinPlus scans in one go (same barriers, twice the payload).
+  MB_FN void exscan_minplus2(MinPlus& va, MinPlus& vb) const {
+    const int tid = first();
+    const int lane = tid & 31, warp = tid >> 5, nw = (nt() + 31) >> 5;
+    MinPlus ia = va, ib = vb;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      MinPlus oa, ob;
+      oa.a = __shfl_up_sync(0xffffffffu, ia.a, d);
+      oa.b = __shfl_up_sync(0xffffffffu, ia.b, d);
+      ob.a = __shfl_up_sync(0xffffffffu, ib.a, d);
+      ob.b = __shfl_up_sync(0xffffffffu, ib.b, d);
+      if (lane >= d) {
+        ia = minplus_then(oa, ia);
+        ib = minplus_then(ob, ib);
+      }
+    }
+    if (lane == 31) {
+      scr->warp_u64[warp] = static_cast<u64>(ia.a);
+      scr->warp_u64b[warp] = static_cast<u64>(ia.b);
+      scr->warp_u64c[warp] = static_cast<u64>(ib.a);
+      scr->warp_u64d[warp] = static_cast<u64>(ib.b);
+    }
+    __syncthreads();
+    if (tid < 2) {
+      u64* a = tid == 0 ? scr->warp_u64 : scr->warp_u64c;
+      u64* b = tid == 0 ? scr->warp_u64b : scr->warp_u64d;
+      MinPlus acc = minplus_identity();
+      for (int w = 0; w < nw; ++w) {
+        const MinPlus cur{static_cast<i64>(a[w]), static_cast<i64>(b[w])};
+        a[w] = static_cast<u64>(acc.a);
+        b[w] = static_cast<u64>(acc.b);
+        acc = minplus_then(acc, cur);
+      }
+    }
+    __syncthreads();
+    const MinPlus wa{static_cast<i64>(scr->warp_u64[warp]), static_cast<i64>(scr->warp_u64b[warp])};
+    const MinPlus wb{static_cast<i64>(scr->warp_u64c[warp]), static_cast<i64>(scr->warp_u64d[warp])};
+    MinPlus ea, eb;
+    ea.a = __shfl_up_sync(0xffffffffu, ia.a, 1);
+    ea.b = __shfl_up_sync(0xffffffffu, ia.b, 1);
+    eb.a = __shfl_up_sync(0xffffffffu, ib.a, 1);
+    eb.b = __shfl_up_sync(0xffffffffu, ib.b, 1);
+    if (lane == 0) {
+      ea = minplus_identity();
+      eb = minplus_identity();
+    }
+    va = minplus_then(wa, ea);
+    vb = minplus_then(wb, eb);
+    __syncthreads();
+  }
+
   // ---- collectives over PerThread values (uniform results returned to every thread) ----
   MB_FN u64 exscan_sum(PerThread<u64>& v) const {
     u64 total;
@@ -264,6 +319,71 @@ struct Cta {
     return reduce_sum_f64(first(), v.val);
   }
   MB_FN void exscan_minplus(PerThread<MinPlus>& v) const { v.val = exscan_minplus(first(), v.val); }
+  MB_FN void exscan_minplus2(PerThread<MinPlus>& a, PerThread<MinPlus>& b) const {
+    exscan_minplus2(a.val, b.val);
+  }
+
+  // Two independent SecOp scans in one go (same barriers, twice the payload).
+  MB_FN void exscan_secop2(PerThread<SecOp>& pa, PerThread<SecOp>& pb) const {
+    const int tid = first();
+    const int lane = tid & 31, warp = tid >> 5, nw = (nt() + 31) >> 5;
+    SecOp ia = pa.val, ib = pb.val;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      SecOp oa, ob;
+      oa.T = __shfl_up_sync(0xffffffffu, ia.T, d);
+      oa.a = __shfl_up_sync(0xffffffffu, ia.a, d);
+      oa.b = __shfl_up_sync(0xffffffffu, ia.b, d);
+      ob.T = __shfl_up_sync(0xffffffffu, ib.T, d);
+      ob.a = __shfl_up_sync(0xffffffffu, ib.a, d);
+      ob.b = __shfl_up_sync(0xffffffffu, ib.b, d);
+      if (lane >= d) {
+        ia = secop_then(oa, ia);
+        ib = secop_then(ob, ib);
+      }
+    }
+    if (lane == 31) {
+      scr->warp_u64[warp] = static_cast<u64>(ia.T);
+      scr->warp_u64b[warp] = static_cast<u64>(ia.a);
+      scr->warp_u64c[warp] = static_cast<u64>(ia.b);
+      scr->warp_u64d[warp] = static_cast<u64>(ib.T);
+      scr->warp_u64e[warp] = static_cast<u64>(ib.a);
+      scr->warp_u64f[warp] = static_cast<u64>(ib.b);
+    }
+    __syncthreads();
+    if (tid < 2) {  // thread 0 chains the first scan's warp totals, thread 1 the second's
+      u64* t = tid == 0 ? scr->warp_u64 : scr->warp_u64d;
+      u64* a = tid == 0 ? scr->warp_u64b : scr->warp_u64e;
+      u64* b = tid == 0 ? scr->warp_u64c : scr->warp_u64f;
+      SecOp acc = secop_identity();
+      for (int w = 0; w < nw; ++w) {
+        const SecOp cur{static_cast<i64>(t[w]), static_cast<i64>(a[w]), static_cast<i64>(b[w])};
+        t[w] = static_cast<u64>(acc.T);
+        a[w] = static_cast<u64>(acc.a);
+        b[w] = static_cast<u64>(acc.b);
+        acc = secop_then(acc, cur);
+      }
+    }
+    __syncthreads();
+    const SecOp wa{static_cast<i64>(scr->warp_u64[warp]), static_cast<i64>(scr->warp_u64b[warp]),
+                   static_cast<i64>(scr->warp_u64c[warp])};
+    const SecOp wb{static_cast<i64>(scr->warp_u64d[warp]), static_cast<i64>(scr->warp_u64e[warp]),
+                   static_cast<i64>(scr->warp_u64f[warp])};
+    SecOp ea, eb;
+    ea.T = __shfl_up_sync(0xffffffffu, ia.T, 1);
+    ea.a = __shfl_up_sync(0xffffffffu, ia.a, 1);
+    ea.b = __shfl_up_sync(0xffffffffu, ia.b, 1);
+    eb.T = __shfl_up_sync(0xffffffffu, ib.T, 1);
+    eb.a = __shfl_up_sync(0xffffffffu, ib.a, 1);
+    eb.b = __shfl_up_sync(0xffffffffu, ib.b, 1);
+    if (lane == 0) {
+      ea = secop_identity();
+      eb = secop_identity();
+    }
+    pa.val = secop_then(wa, ea);
+    pb.val = secop_then(wb, eb);
+    __syncthreads();
+  }
 
   // Exclusive scan of SecOp elements in thread order (composition of all lower threads).
   MB_FN void exscan_secop(PerThread<SecOp>& pv) const {
@@ -378,6 +498,14 @@ struct Cta {
       v[t] = acc;
       acc = minplus_then(acc, x);
     }
+  }
+  void exscan_minplus2(PerThread<MinPlus>& a, PerThread<MinPlus>& b) const {
+    exscan_minplus(a);
+    exscan_minplus(b);
+  }
+  void exscan_secop2(PerThread<SecOp>& a, PerThread<SecOp>& b) const {
+    exscan_secop(a);
+    exscan_secop(b);
   }
   void exscan_secop(PerThread<SecOp>& v) const {
     SecOp acc = secop_identity();

@@ -45,6 +45,9 @@ struct LaunchArgs {
 #ifndef MODLE_B200_SMALL_MIN_BLOCKS
 #define MODLE_B200_SMALL_MIN_BLOCKS 3
 #endif
+#ifndef MODLE_B200_LARGE_THREADS
+#define MODLE_B200_LARGE_THREADS 512
+#endif
 template <int kThreads, int kMinBlocks>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
     k_simulate_cells(const __grid_constant__ LaunchArgs a) {
@@ -260,8 +263,8 @@ int modle_b200_init(modle_b200_context** out, int device) {
     CUDA_TRY(cudaFuncSetAttribute(k_simulate_cells<256, MODLE_B200_SMALL_MIN_BLOCKS>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(ctx->max_smem_optin - fa.sharedSizeBytes)));
-    CUDA_TRY(cudaFuncGetAttributes(&fa, k_simulate_cells<512, 1>));
-    CUDA_TRY(cudaFuncSetAttribute(k_simulate_cells<512, 1>,
+    CUDA_TRY(cudaFuncGetAttributes(&fa, k_simulate_cells<MODLE_B200_LARGE_THREADS, 1>));
+    CUDA_TRY(cudaFuncSetAttribute(k_simulate_cells<MODLE_B200_LARGE_THREADS, 1>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(ctx->max_smem_optin - fa.sharedSizeBytes)));
     ctx->max_smem_optin -= fa.sharedSizeBytes;
@@ -380,7 +383,7 @@ int launch_simulate(modle_b200_context* ctx, const modle_b200_sim_params* params
   // grid: persistent CTAs, as many as fit
   const bool small = sc.cta_threads == 256;
   void (*kernel)(const LaunchArgs) =
-      small ? k_simulate_cells<256, MODLE_B200_SMALL_MIN_BLOCKS> : k_simulate_cells<512, 1>;
+      small ? k_simulate_cells<256, MODLE_B200_SMALL_MIN_BLOCKS> : k_simulate_cells<MODLE_B200_LARGE_THREADS, 1>;
   int per_sm = 0;
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel,
                                                          static_cast<int>(sc.cta_threads), smem));

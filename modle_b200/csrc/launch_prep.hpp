@@ -57,7 +57,12 @@ struct ZigguratTables {
 struct StagingConfig {
   u32 cta_threads, gen_threads, per_thread, window, jump_slot;
 };
-inline StagingConfig staging_large() { return StagingConfig{512, 256, 128, 256 * 128, 0}; }
+#ifndef MODLE_B200_LARGE_THREADS
+#define MODLE_B200_LARGE_THREADS 512
+#endif
+inline StagingConfig staging_large() {
+  return StagingConfig{MODLE_B200_LARGE_THREADS, 256, 128, 256 * 128, 0};
+}
 inline StagingConfig staging_small() { return StagingConfig{256, 64, 128, 64 * 128, 1}; }
 
 // Byte-indexed table of T^window (layout: see sim_core.hpp xs_jump): entry (k, v) is the XOR of
@@ -141,6 +146,16 @@ inline std::string prepare_interval(const modle_b200_sim_params& p, const modle_
   k.lef_binding_rate_burnin = static_cast<double>(iv.num_lefs) /
                               static_cast<double>(p.burnin_target_epochs_for_lef_activation);
   k.debug_max_epochs = p.debug_max_epochs;
+  {
+    // speed + 64 sigma: no draw of the ziggurat sampler gets there in practice; the kernel still
+    // checks every move against it and falls back to the true maximum when one does
+    const double hi = std::max({k.rev_speed + 64.0 * k.rev_std, k.fwd_speed + 64.0 * k.fwd_std,
+                                k.rev_speed_burnin + 64.0 * k.rev_std,
+                                k.fwd_speed_burnin + 64.0 * k.fwd_std}) + 2.0;
+    if (!(hi < 16000000.0))
+      return "extrusion speed too large: moves must stay below 2^24 bp per epoch";
+    k.move_bound = static_cast<u32>(hi);
+  }
   k.rng_gen_threads = sc.gen_threads;
   k.rng_per_thread = sc.per_thread;
   k.rng_window = sc.window;

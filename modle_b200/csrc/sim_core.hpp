@@ -528,6 +528,7 @@ struct CellSim {
         S.hist_len = 0;
         S.hist_head = 0;
         S.done = 0;
+        S.move_bound_hit = 0;
         for (int k = 0; k < kNumPhases; ++k) S.phase_cycles[k] = 0;
         if (P.burnin_history > kMaxBurninHistory || P.burnin_window + 1 >= P.burnin_history)
           fault(kFaultBurninHistory);
@@ -1438,12 +1439,15 @@ struct CellSim {
       }
       u32 e = a;
       u32 shift = e ? ex[4 * (e - 1) + 1] : 0;
+      bool over = false;
       auto store = [&](u32 item, double z) {
+        u32 mv;
         if (item < n_rev) {
-          A.rm[item] = move_from_z(z, rev_speed, rev_sd);
+          A.rm[item] = mv = move_from_z(z, rev_speed, rev_sd);
         } else {
-          A.fm[item - n_rev] = move_from_z(z, fwd_speed, fwd_sd);
+          A.fm[item - n_rev] = mv = move_from_z(z, fwd_speed, fwd_sd);
         }
+        over |= mv > P.move_bound;
       };
       u32 i = lo;
       while (i < hi) {
@@ -1472,6 +1476,7 @@ struct CellSim {
           ++i;
         }
       }
+      if (over) S.move_bound_hit = 1;
     }
     cta.sync();
     MB_REGION(cta, tid) {
@@ -1548,22 +1553,38 @@ struct CellSim {
 
   MB_FN void adjust_and_clamp_moves() {
     const u32 n = S.num_active;
-    PerThread<u64> mx(cta.nt());
-    MB_REGION(cta, tid) {
-      u64 m = 0;
-      for (u32 i = tid; i < n; i += cta.nt()) {
-        const u64 a = A.rm[i], b = A.fm[i];
-        m = a > m ? a : m;
-        m = b > m ? b : m;
+    // Upper bound of every move: the static bound the generator checked its output against
+    // (S.move_bound_hit is set when a draw exceeded it), else the true maximum.
+    u64 mmax = P.move_bound;
+    if (S.move_bound_hit) {
+      PerThread<u64> mx(cta.nt());
+      MB_REGION(cta, tid) {
+        u64 m = 0;
+        for (u32 i = tid; i < n; i += cta.nt()) {
+          const u64 a = A.rm[i], b = A.fm[i];
+          m = a > m ? a : m;
+          m = b > m ? b : m;
+        }
+        mx[tid] = m;
       }
-      mx[tid] = m;
+      mmax = cta.reduce_max(mx);
+      MB_REGION(cta, tid) {
+        if (cta.leader(tid)) {
+          S.move_bound_hit = 0;
+          // the secondary pass parks moves in 24-bit collision indices
+          if (mmax >= (u64(1) << 24)) fault(kFaultMoveRange);
+        }
+      }
+      cta.sync();
     }
-    const u64 mmax = cta.reduce_max(mx);
     if (n >= 2) {
-      // ---- rev units, walked 3'->5': q'[k-1] = min(q[k-1], q'[k] - 1)
-      const u32 k_near = count_rev_le(u64(P.start) + mmax + n);  // ranks < k_near: serial part
-      const u32 M = n - k_near;                                  // ranks [k_near, n) in parallel
-      PerThread<MinPlus> f(cta.nt());
+      // rev units, walked 3'->5': q'[k-1] = min(q[k-1], q'[k] - 1); fwd units, walked 5'->3':
+      // q'[k] = max(q[k], q'[k-1] + 1) (negated: min-plus). Both scans run together.
+      const u32 k_near = count_rev_le(u64(P.start) + mmax + n);  // rev ranks < k_near: serial part
+      const u32 M = n - k_near;                                  // rev ranks [k_near, n) in parallel
+      const u64 far_thr = u64(P.end) - 1 > mmax + n ? u64(P.end) - 1 - mmax - n : 0;
+      const u32 k_far = count_fwd_lt(far_thr);  // fwd ranks [0, k_far) in parallel
+      PerThread<MinPlus> f(cta.nt()), g(cta.nt());
       MB_REGION(cta, tid) {
         u32 lo, hi;
         chunk(tid, M, &lo, &hi);
@@ -1574,8 +1595,16 @@ struct CellSim {
           acc = minplus_then(acc, MinPlus{q, -1});
         }
         f[tid] = acc;
+        chunk(tid, k_far, &lo, &hi);
+        acc = minplus_identity();
+        for (u32 k = lo; k < hi; ++k) {
+          const u32 idx = A.fr[k];
+          const i64 q = i64(A.fwd[idx]) + i64(A.fm[idx]);
+          acc = minplus_then(acc, MinPlus{-q, -1});
+        }
+        g[tid] = acc;
       }
-      cta.exscan_minplus(f);
+      cta.exscan_minplus2(f, g);
       MB_REGION(cta, tid) {
         u32 lo, hi;
         chunk(tid, M, &lo, &hi);
@@ -1587,10 +1616,22 @@ struct CellSim {
           x = q < cap ? q : cap;
           A.rm[idx] = static_cast<u32>(i64(A.rev[idx]) - x);
         }
+        chunk(tid, k_far, &lo, &hi);
+        x = minplus_apply(g[tid], kMinPlusInf);
+        for (u32 k = lo; k < hi; ++k) {
+          const u32 idx = A.fr[k];
+          const i64 nq = -(i64(A.fwd[idx]) + i64(A.fm[idx]));
+          const i64 cap = x - 1;
+          x = nq < cap ? nq : cap;
+          A.fm[idx] = static_cast<u32>(-x - i64(A.fwd[idx]));
+        }
       }
       cta.sync();
+      // the few units close enough to an interval end for the reference's "skip" rule to fire:
+      // thread 0 finishes the rev side, thread 1 (when there is one) the fwd side
       MB_REGION(cta, tid) {
-        if (cta.leader(tid)) {
+        const bool two = cta.nt() > 1;
+        if (tid == 0) {
           for (u32 i = (k_near < n - 1 ? k_near : n - 1); i > 0; --i) {
             const u32 i1 = A.rr[i - 1], i2 = A.rr[i];
             if (u64(A.rev[i1]) <= u64(P.start) + A.rm[i1] ||
@@ -1601,38 +1642,7 @@ struct CellSim {
             if (p2 <= p1) A.rm[i1] += (p1 - p2) + 1;
           }
         }
-      }
-      cta.sync();
-      // ---- fwd units, walked 5'->3': q'[k] = max(q[k], q'[k-1] + 1)  (negated: min-plus)
-      const u64 far_thr = u64(P.end) - 1 > mmax + n ? u64(P.end) - 1 - mmax - n : 0;
-      const u32 k_far = count_fwd_lt(far_thr);  // ranks [0, k_far) in parallel
-      MB_REGION(cta, tid) {
-        u32 lo, hi;
-        chunk(tid, k_far, &lo, &hi);
-        MinPlus acc = minplus_identity();
-        for (u32 k = lo; k < hi; ++k) {
-          const u32 idx = A.fr[k];
-          const i64 q = i64(A.fwd[idx]) + i64(A.fm[idx]);
-          acc = minplus_then(acc, MinPlus{-q, -1});
-        }
-        f[tid] = acc;
-      }
-      cta.exscan_minplus(f);
-      MB_REGION(cta, tid) {
-        u32 lo, hi;
-        chunk(tid, k_far, &lo, &hi);
-        i64 x = minplus_apply(f[tid], kMinPlusInf);
-        for (u32 k = lo; k < hi; ++k) {
-          const u32 idx = A.fr[k];
-          const i64 nq = -(i64(A.fwd[idx]) + i64(A.fm[idx]));
-          const i64 cap = x - 1;
-          x = nq < cap ? nq : cap;
-          A.fm[idx] = static_cast<u32>(-x - i64(A.fwd[idx]));
-        }
-      }
-      cta.sync();
-      MB_REGION(cta, tid) {
-        if (cta.leader(tid)) {
+        if (tid == (two ? 1 : 0)) {
           for (u32 i = (k_far > 1 ? k_far : 1); i < n; ++i) {
             const u32 i1 = A.fr[i - 1], i2 = A.fr[i];
             if (u64(A.fwd[i1]) + A.fm[i1] > u64(P.end) - 1 ||
@@ -2049,93 +2059,169 @@ struct CellSim {
   // State of the walk after scan position m: `alive` = the unit at m ends the epoch stalled
   // (collided before this pass, or stalled by this pass assuming its trial succeeds), v = its
   // final position. A free unit at m is a candidate when alive(m-1) and q[m] <= v(m-1).
-  // One scan over SecOp elements gives every thread the state at the start of its chunk.
+  // One scan over SecOp elements gives every thread the state at the start of its chunk. The
+  // rev pass (5'->3' over rev ranks) and the fwd pass (3'->5' over fwd ranks) touch disjoint
+  // arrays, so both run through the same steps together; only the draws couple them (the fwd
+  // pass draws after the rev pass), and those are resolved in one walk over the concatenated
+  // candidate list.
+  struct SecDir {
+    u32 first, M;
+    u32* cand;   // by scan position: the unit is a candidate
+    u32* head1;  // by scan position: ... directly behind an already stalled unit
+  };
+
   template <bool kRevPass>
-  MB_FN void secondary_pass(u32 first, u32 M) {
-    if (M < 2) return;
+  MB_FN SecOp sec_compose(const SecDir& d, int tid) const {
+    const u32* coll = kRevPass ? A.rc : A.fc;
+    u32 lo, hi;
+    chunk(tid, d.M, &lo, &hi);
+    SecOp acc = secop_identity();
+    for (u32 m = lo; m < hi; ++m) {
+      const u32 idx = sec_idx<kRevPass>(d.first, m);
+      if (coll_occurred(coll[idx])) {
+        acc = secop_const(sec_q<kRevPass>(idx));
+      } else {
+        acc = secop_then(acc, SecOp{sec_q<kRevPass>(idx), sec_pos<kRevPass>(idx), 1});
+      }
+    }
+    return acc;
+  }
+
+  // Marks this thread's candidates and parks each candidate's move-if-stalled in the index bits
+  // of its (so far empty) collision word. Returns the number of candidates.
+  template <bool kRevPass>
+  MB_FN u32 sec_classify(const SecDir& d, int tid, const SecOp& prefix) const {
+    u32* coll = kRevPass ? A.rc : A.fc;
+    u32 lo, hi;
+    chunk(tid, d.M, &lo, &hi);
+    bool alive = prefix.b == kSecConst;
+    i64 v = prefix.a;
+    bool prev_head =
+        lo > 0 && lo < hi && coll_occurred(coll[sec_idx<kRevPass>(d.first, lo - 1)]);
+    u32 c = 0;
+    for (u32 m = lo; m < hi; ++m) {
+      const u32 idx = sec_idx<kRevPass>(d.first, m);
+      if (coll_occurred(coll[idx])) {
+        alive = true;
+        v = sec_q<kRevPass>(idx);
+        prev_head = true;
+        continue;
+      }
+      if (alive && sec_q<kRevPass>(idx) <= v) {
+        const i64 p = sec_pos<kRevPass>(idx);
+        const i64 mv = p - v;  // distance to the blocker's site
+        coll[idx] = static_cast<u32>(mv > 0 ? mv - 1 : 0);  // event bits stay 0
+        MB_ATOMIC_OR_U32(&d.cand[m >> 5], 1u << (m & 31));
+        if (prev_head) MB_ATOMIC_OR_U32(&d.head1[m >> 5], 1u << (m & 31));
+        v = p < v + 1 ? p : v + 1;
+        ++c;
+      } else {
+        alive = false;
+      }
+      prev_head = false;
+    }
+    return c;
+  }
+
+  // Copies the first-in-run flags of this thread's candidates to their candidate numbers.
+  MB_FN void sec_number_firsts(const SecDir& d, int tid, u32 c, u32* firstc) const {
+    u32 lo, hi;
+    chunk(tid, d.M, &lo, &hi);
+    for (u32 m = lo; m < hi; ++m) {
+      if (!((d.cand[m >> 5] >> (m & 31)) & 1u)) continue;
+      if ((d.head1[m >> 5] >> (m & 31)) & 1u) MB_ATOMIC_OR_U32(&firstc[c >> 5], 1u << (c & 31));
+      ++c;
+    }
+  }
+
+  // mode 0: outcomes from the reached / ok bitmaps; 1: every candidate stalls (bypass == 0);
+  // 2: trials never succeed and draw nothing (bypass == 1): only run heads are reached.
+  template <bool kRevPass>
+  MB_FN void sec_apply(const SecDir& d, int tid, u32 c, int mode, const u32* reached_bits,
+                       const u32* ok_bits) const {
     u32* coll = kRevPass ? A.rc : A.fc;
     u32* moves = kRevPass ? A.rm : A.fm;
+    u32 lo, hi;
+    chunk(tid, d.M, &lo, &hi);
+    for (u32 m = lo; m < hi; ++m) {
+      if (!((d.cand[m >> 5] >> (m & 31)) & 1u)) continue;
+      bool reached, ok;
+      if (mode == 0) {
+        reached = (reached_bits[c >> 5] >> (c & 31)) & 1u;
+        ok = (ok_bits[c >> 5] >> (c & 31)) & 1u;
+      } else if (mode == 2) {
+        reached = (d.head1[m >> 5] >> (m & 31)) & 1u;
+        ok = false;
+      } else {
+        reached = ok = true;
+      }
+      ++c;
+      const u32 idx = sec_idx<kRevPass>(d.first, m);
+      if (!reached) {
+        coll[idx] = 0;
+        continue;
+      }
+      const u32 blocker = sec_idx<kRevPass>(d.first, m - 1);
+      if (ok) {
+        moves[idx] = coll[idx];  // parked by sec_classify
+        coll[idx] = coll_make(blocker, kEvCollision | kEvSecondary);
+      } else {
+        coll[idx] = coll_make(blocker, kEvSecondary);
+      }
+    }
+  }
+
+  // process_secondary_lef_lef_collisions (simulation_detect_collisions.cpp:400-515)
+  MB_FN void process_secondary_lef_lef_collisions() {
+    const u32 n = S.num_active;
     const bool never = P.p_bypass != 0.0 && 1.0 - P.p_bypass == 0.0;  // trials fail, no draws
     const bool draws = P.p_bypass != 0.0 && !never;
-    const u32 nwords = (M + 31) / 32 + 2;
-    u32* vbuf = A.scratch;                  // candidates only: v(m-1) + bias
-    u32* bits_cand = A.bits;                // by scan position: the unit is a candidate
-    u32* bits_first = A.bits + nwords;      // ... directly behind an already stalled unit
-    u32* bits_firstc = A.bits + 2 * nwords;  // by candidate number: first of its run
-    u32* bits_reached = A.bits + 3 * nwords;
-    u32* bits_ok = A.bits + 4 * nwords;
-    u32* bits_fail = A.bits + 5 * nwords;   // by draw
-    // stored value = v + bias: rev values are positions (>= 0), fwd values are negated
-    // positions (> -(2^32 - 1))
-    const i64 bias = kRevPass ? i64(0) : i64(0xFFFFFFFFll);
+    const u32 nwords = (n + 31) / 32 + 2;
+    SecDir R, F;
+    const u32 k0 = S.n5 > 1 ? S.n5 : 1;  // the rev pass looks at rank pairs (k-1, k), k >= k0
+    R.first = k0 - 1;
+    R.M = k0 < n ? n - (k0 - 1) : 0;
+    const u32 sat3 = S.n3 ? S.n3 - 1 : 0;
+    F.first = n - sat3 - 1;  // the fwd pass starts from this rank and walks down
+    F.M = F.first + 1;
+    if (R.M < 2) R.M = 0;
+    if (F.M < 2) F.M = 0;
+    if (R.M == 0 && F.M == 0) return;
+    R.cand = A.bits;
+    R.head1 = A.bits + nwords;
+    F.cand = A.bits + 2 * nwords;
+    F.head1 = A.bits + 3 * nwords;
+    u32* bits_firstc = A.bits + 4 * nwords;   // by candidate number (rev candidates, then fwd)
+    u32* bits_reached = A.bits + 6 * nwords;
+    u32* bits_ok = A.bits + 8 * nwords;
+    u32* bits_fail = A.bits + 10 * nwords;    // by draw
 
-    PerThread<SecOp> f(cta.nt());
     sub_begin();
+    PerThread<SecOp> fr(cta.nt()), ff(cta.nt());
     MB_REGION(cta, tid) {
-      u32 lo, hi;
-      chunk(tid, M, &lo, &hi);
-      SecOp acc = secop_identity();
-      for (u32 m = lo; m < hi; ++m) {
-        const u32 idx = sec_idx<kRevPass>(first, m);
-        if (coll_occurred(coll[idx])) {
-          acc = secop_const(sec_q<kRevPass>(idx));
-        } else {
-          acc = secop_then(acc, SecOp{sec_q<kRevPass>(idx), sec_pos<kRevPass>(idx), 1});
-        }
-      }
-      f[tid] = acc;
-      for (u32 w = tid; w < 6 * nwords; w += cta.nt()) A.bits[w] = 0;
+      fr[tid] = sec_compose<true>(R, tid);
+      ff[tid] = sec_compose<false>(F, tid);
+      for (u32 w = tid; w < 12 * nwords; w += cta.nt()) A.bits[w] = 0;
     }
-    cta.sync();
     sub_lap(kPhSecCompose);
-    cta.exscan_secop(f);
+    cta.exscan_secop2(fr, ff);
     sub_lap(kPhSecScan);
-    PerThread<u64> cnt(cta.nt());
+    PerThread<u64> cnt(cta.nt());  // low word: rev candidates, high word: fwd candidates
     MB_REGION(cta, tid) {
-      u32 lo, hi;
-      chunk(tid, M, &lo, &hi);
-      bool alive = f[tid].b == kSecConst;
-      i64 v = f[tid].a;
-      bool prev_head = lo > 0 && lo < hi && coll_occurred(coll[sec_idx<kRevPass>(first, lo - 1)]);
-      u32 c = 0;
-      for (u32 m = lo; m < hi; ++m) {
-        const u32 idx = sec_idx<kRevPass>(first, m);
-        if (coll_occurred(coll[idx])) {
-          alive = true;
-          v = sec_q<kRevPass>(idx);
-          prev_head = true;
-          continue;
-        }
-        if (alive && sec_q<kRevPass>(idx) <= v) {
-          vbuf[m] = static_cast<u32>(v + bias);
-          MB_ATOMIC_OR_U32(&bits_cand[m >> 5], 1u << (m & 31));
-          if (prev_head) MB_ATOMIC_OR_U32(&bits_first[m >> 5], 1u << (m & 31));
-          const i64 p = sec_pos<kRevPass>(idx);
-          v = p < v + 1 ? p : v + 1;
-          ++c;
-        } else {
-          alive = false;
-        }
-        prev_head = false;
-      }
-      cnt[tid] = c;
+      const u32 cr = sec_classify<true>(R, tid, fr[tid]);
+      const u32 cf = sec_classify<false>(F, tid, ff[tid]);
+      cnt[tid] = u64(cr) | (u64(cf) << 32);
     }
-    const u32 npot = static_cast<u32>(cta.exscan_sum(cnt));  // cnt[tid]: candidates before mine
+    const u64 tot = cta.exscan_sum(cnt);  // cnt[tid]: candidates before this thread's
+    const u32 npot_r = static_cast<u32>(tot & 0xFFFFFFFFu);
+    const u32 npot = npot_r + static_cast<u32>(tot >> 32);
     sub_lap(kPhSecClassify);
     if (npot == 0) return;
     if (draws) {
       rng_ensure(S.rng_pos + npot);
       MB_REGION(cta, tid) {
-        // first-in-run flags by candidate number; failed-trial flags by draw
-        u32 lo, hi;
-        chunk(tid, M, &lo, &hi);
-        u32 c = static_cast<u32>(cnt[tid]);
-        for (u32 m = lo; m < hi; ++m) {
-          if (!((bits_cand[m >> 5] >> (m & 31)) & 1u)) continue;
-          if ((bits_first[m >> 5] >> (m & 31)) & 1u)
-            MB_ATOMIC_OR_U32(&bits_firstc[c >> 5], 1u << (c & 31));
-          ++c;
-        }
+        sec_number_firsts(R, tid, static_cast<u32>(cnt[tid] & 0xFFFFFFFFu), bits_firstc);
+        sec_number_firsts(F, tid, npot_r + static_cast<u32>(cnt[tid] >> 32), bits_firstc);
         for (u32 d = tid; d < npot; d += cta.nt()) {
           if (!bernoulli_raw(raw(S.rng_pos + d), 1.0 - P.p_bypass))
             MB_ATOMIC_OR_U32(&bits_fail[d >> 5], 1u << (d & 31));
@@ -2143,9 +2229,10 @@ struct CellSim {
       }
       cta.sync();
       sub_lap(kPhSecDraws);
-      // Walk the candidates in order. A candidate is reached when it is the first of its run or
-      // the previous one was reached and its trial succeeded; only reached candidates draw, so
-      // the d-th draw belongs to the d-th reached candidate.
+      // Walk the candidates in order (all rev candidates, then all fwd candidates; the first
+      // fwd candidate always starts a run). A candidate is reached when it is the first of its
+      // run or the previous one was reached and its trial succeeded; only reached candidates
+      // draw, so the d-th draw belongs to the d-th reached candidate.
       const u32 ncw = (npot + 31) / 32;
 #if MB_DEVICE_BUILD
       // Warp 0, one lane per candidate, 32 candidates at a time: start from "every candidate
@@ -2157,28 +2244,28 @@ struct CellSim {
         const u32 lt = (1u << lane) - 1u;
         u32 d = 0, alive_in = 0;
         for (u32 w = 0; w < ncw; ++w) {
-          const u32 F = bits_firstc[w];
+          const u32 Fw = bits_firstc[w];
           const u32 nvalid = npot - 32 * w < 32 ? npot - 32 * w : 32;
-          const u32 Fle = F & (lt | (1u << lane));
+          const u32 Fle = Fw & (lt | (1u << lane));
           const u32 s = Fle ? 31u - static_cast<u32>(__clz(static_cast<int>(Fle))) : 0u;
           const u32 range = lt & ~((1u << s) - 1u);  // candidates of my run before me
           const bool can = lane < nvalid && (Fle != 0 || alive_in != 0);
-          u32 R = __ballot_sync(0xffffffffu, can);
+          u32 Rm = __ballot_sync(0xffffffffu, can);
           u32 bad = 0;
           for (int it = 0; it < 34; ++it) {
-            const u32 dd = d + static_cast<u32>(__popc(R & lt));
+            const u32 dd = d + static_cast<u32>(__popc(Rm & lt));
             const u32 fbit = (bits_fail[dd >> 5] >> (dd & 31)) & 1u;
-            bad = __ballot_sync(0xffffffffu, ((R >> lane) & 1u) && fbit);
+            bad = __ballot_sync(0xffffffffu, ((Rm >> lane) & 1u) && fbit);
             const u32 Rn = __ballot_sync(0xffffffffu, can && (bad & range) == 0);
-            if (Rn == R) break;
-            R = Rn;
+            if (Rn == Rm) break;
+            Rm = Rn;
           }
           if (lane == 0) {
-            bits_reached[w] = R;
-            bits_ok[w] = R & ~bad;
+            bits_reached[w] = Rm;
+            bits_ok[w] = Rm & ~bad;
           }
-          d += static_cast<u32>(__popc(R));
-          alive_in = ((R & ~bad) >> 31) & 1u;
+          d += static_cast<u32>(__popc(Rm));
+          alive_in = ((Rm & ~bad) >> 31) & 1u;
         }
         if (lane == 0) S.tmp_u32[4] = d;
       }
@@ -2186,17 +2273,17 @@ struct CellSim {
       {
         u32 d = 0, alive = 0;
         for (u32 w = 0; w < ncw; ++w) {
-          const u32 F = bits_firstc[w];
+          const u32 Fw = bits_firstc[w];
           const u32 lim = npot - 32 * w < 32 ? npot - 32 * w : 32;
-          u32 R = 0, OK = 0;
+          u32 Rm = 0, OK = 0;
           for (u32 i = 0; i < lim; ++i) {
-            const u32 reach = ((F >> i) & 1u) | alive;
+            const u32 reach = ((Fw >> i) & 1u) | alive;
             alive = reach & ~(bits_fail[d >> 5] >> (d & 31)) & 1u;
-            R |= reach << i;
+            Rm |= reach << i;
             OK |= alive << i;
             d += reach;
           }
-          bits_reached[w] = R;
+          bits_reached[w] = Rm;
           bits_ok[w] = OK;
         }
         S.tmp_u32[4] = d;
@@ -2205,50 +2292,15 @@ struct CellSim {
       cta.sync();
       sub_lap(kPhSecLeader);
     }
-    // apply. Without draws: bypass == 0 -> every candidate is reached and stalls; bypass == 1 ->
-    // only the first candidate behind a stalled unit is reached, and it passes.
+    const int mode = draws ? 0 : (never ? 2 : 1);
     MB_REGION(cta, tid) {
-      u32 lo, hi;
-      chunk(tid, M, &lo, &hi);
-      u32 c = static_cast<u32>(cnt[tid]);
-      for (u32 m = lo; m < hi; ++m) {
-        if (!((bits_cand[m >> 5] >> (m & 31)) & 1u)) continue;
-        bool reached, ok;
-        if (draws) {
-          reached = (bits_reached[c >> 5] >> (c & 31)) & 1u;
-          ok = (bits_ok[c >> 5] >> (c & 31)) & 1u;
-        } else if (never) {
-          reached = (bits_first[m >> 5] >> (m & 31)) & 1u;
-          ok = false;
-        } else {
-          reached = ok = true;
-        }
-        ++c;
-        if (!reached) continue;
-        const u32 idx = sec_idx<kRevPass>(first, m);
-        const u32 blocker = sec_idx<kRevPass>(first, m - 1);
-        if (ok) {
-          const i64 vprev = i64(vbuf[m]) - bias;
-          const i64 mv = sec_pos<kRevPass>(idx) - vprev;  // distance to the blocker's site
-          moves[idx] = static_cast<u32>(mv > 0 ? mv - 1 : 0);
-          coll[idx] = coll_make(blocker, kEvCollision | kEvSecondary);
-        } else {
-          coll[idx] = coll_make(blocker, kEvSecondary);
-        }
-      }
+      sec_apply<true>(R, tid, static_cast<u32>(cnt[tid] & 0xFFFFFFFFu), mode, bits_reached, bits_ok);
+      sec_apply<false>(F, tid, npot_r + static_cast<u32>(cnt[tid] >> 32), mode, bits_reached,
+                       bits_ok);
       if (draws && cta.leader(tid)) S.rng_pos += S.tmp_u32[4];
     }
     cta.sync();
     sub_lap(kPhSecApply);
-  }
-
-  MB_FN void process_secondary_lef_lef_collisions() {
-    const u32 n = S.num_active;
-    const u32 k0 = S.n5 > 1 ? S.n5 : 1;
-    if (k0 < n) secondary_pass<true>(k0 - 1, n - (k0 - 1));
-    const u32 sat3 = S.n3 ? S.n3 - 1 : 0;
-    const u32 kf = n - sat3 - 1;  // rank the fwd pass starts from
-    secondary_pass<false>(kf, kf + 1);
   }
 
   // fix_secondary_lef_lef_collisions (simulation_detect_collisions.cpp:517-644). Avoided markers

@@ -34,6 +34,7 @@ enum : u32 {
   kFaultUnboundLef = 2,     // an active LEF was unbound inside the epoch body
   kFaultBurninHistory = 3,  // burn-in history longer than the shared-memory ring
   kFaultSerialDraws = 4,    // a serial sampler ran out of its draw budget
+  kFaultMoveRange = 5,      // a move of 2^24 bp or more in one epoch (collision words hold 24 bits)
 };
 
 constexpr int kMaxBurninHistory = 256;
@@ -91,6 +92,7 @@ struct KernelParams {
   u64 min_burnin_epochs, max_burnin_epochs;
   double lef_binding_rate_burnin;  // n_lefs / burnin_target_epochs_for_lef_activation
   u64 debug_max_epochs;
+  u32 move_bound;  // every generated move is <= this unless CellShared::move_bound_hit says so
   // RNG staging configuration
   u32 rng_gen_threads;  // G: threads that own a generator sub-stream
   u32 rng_per_thread;   // l: consecutive draws per generator thread per window
@@ -142,6 +144,7 @@ struct CellShared {
   u32 n5, n3;
   u32 hist_len, hist_head;  // burn-in history ring
   u32 done;
+  u32 move_bound_hit;  // a generated move exceeded KernelParams::move_bound
   u32 tmp_u32[8];
   u64 tmp_u64[4];
   u64 phase_cycles[kNumPhases];  // SM clock cycles spent per phase of the epoch loop (thread 0)
@@ -157,7 +160,7 @@ struct CellArrays {
   u32 *rm, *fm;         // moves
   u32 *rc, *fc;         // collision words
   u32* scratch;         // max(n_lefs, n_bar) + 64 words
-  u32* bits;            // 6 * (n_lefs/32 + 3) words: bitmaps of the secondary-collision pass
+  u32* bits;            // 12 * (n_lefs/32 + 3) words: bitmaps of the secondary-collision pass
   u32* bar_pos;         // n_bar (copy of IntervalData::bar_pos)
   u8* bar_active;       // n_bar bytes (0/1)
   double* zig_nx;       // 129 (copy)
@@ -170,7 +173,7 @@ struct CellArrays {
 MB_HD size_t cell_scratch_words(u32 n_lefs, u32 n_bar) {
   return size_t(n_lefs > n_bar ? n_lefs : n_bar) + 64;
 }
-MB_HD size_t cell_bits_words(u32 n_lefs) { return size_t(6) * (n_lefs / 32 + 3); }
+MB_HD size_t cell_bits_words(u32 n_lefs) { return size_t(12) * (n_lefs / 32 + 3); }
 MB_HD size_t cell_array_bytes(u32 n_lefs, u32 n_bar) {
   size_t w = 0;
   w += 260;                                // zig_nx: 129 doubles (+ pad)
