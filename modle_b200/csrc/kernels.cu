@@ -46,7 +46,7 @@ struct LaunchArgs {
 #define MODLE_B200_SMALL_MIN_BLOCKS 3
 #endif
 #ifndef MODLE_B200_LARGE_THREADS
-#define MODLE_B200_LARGE_THREADS 512
+#define MODLE_B200_LARGE_THREADS 1024
 #endif
 template <int kThreads, int kMinBlocks>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)

@@ -58,7 +58,7 @@ struct StagingConfig {
   u32 cta_threads, gen_threads, per_thread, window, jump_slot;
 };
 #ifndef MODLE_B200_LARGE_THREADS
-#define MODLE_B200_LARGE_THREADS 512
+#define MODLE_B200_LARGE_THREADS 1024
 #endif
 inline StagingConfig staging_large() {
   return StagingConfig{MODLE_B200_LARGE_THREADS, 256, 128, 256 * 128, 0};

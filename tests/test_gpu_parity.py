@@ -153,3 +153,95 @@ def test_unsupported_inputs_fail_loudly(gpu_ctx):
     with pytest.raises(ModleB200Error) as e:
         gpu_ctx.simulate_interval(p2, iv2, bars2, tasks2)
     assert e.value.code in (-4,)
+
+
+def _small_genome():
+    from modle_b200 import workloads
+
+    sizes = [("chrA", 9_000_000, 160), ("chrB", 4_000_000, 70), ("chrC", 2_500_000, 0),
+             ("chrD", 30_000_000, 500), ("chrE", 1_000_000, 12)]
+    return [(n, s, 0, s, workloads.synthetic_barrier_records(s, nb, seed=77 + k))
+            for k, (n, s, nb) in enumerate(sizes)]
+
+
+def _oracle_genome(cfg, genome):
+    from modle_b200 import abi, host
+
+    out = {}
+    p = cfg.params
+    for name, size, start, end, recs in genome:
+        bars = host.barriers_from_records(recs, p)
+        if len(bars) == 0:
+            continue
+        iv = abi.Interval(size, start, end, host.compute_num_lefs(p, end - start))
+        tasks = host.make_cell_tasks(p, name, iv)
+        out[name] = pyoracle.simulate_interval(p, iv, bars, tasks, nthreads=8)
+    return out
+
+
+def test_run_simulate_with_worker_threads_matches_oracle(product_lib):
+    """The public host path: Simulation.run_simulate with 3 worker contexts (overlapping
+    launches on one GPU) gives, per interval, exactly the oracle's matrices; intervals without
+    barriers are skipped like the reference does."""
+    from modle_b200.simulation import Config, Simulation
+
+    cfg = Config(num_cells=12, target_contact_density=0.01).transform()
+    genome = _small_genome()
+    sim = Simulation(cfg, genome)
+    try:
+        for _ in range(2):  # the second call reuses the contexts and must not accumulate
+            for iv in sim.intervals:
+                iv.contacts = None
+                iv.lef_1d_occupancy = None
+            sim.run_simulate(num_workers=3)
+    finally:
+        sim.close()
+    ora = _oracle_genome(cfg, genome)
+    for iv in sim.intervals:
+        if iv.chrom_name not in ora:
+            assert iv.contacts is None
+            continue
+        band, occ, stats, missed = ora[iv.chrom_name]
+        assert np.array_equal(iv.contacts, band), iv.chrom_name
+        assert np.array_equal(iv.lef_1d_occupancy, occ), iv.chrom_name
+        assert iv.missed_updates == missed
+        assert np.array_equal(iv.stats["num_rng_draws"], stats["num_rng_draws"])
+
+
+def test_device_engine_sharded_runner_matches_oracle(product_lib):
+    """modle_b200.distributed on one GPU: an interval split into three cell ranges that run on
+    different streams and add into one device band."""
+    from modle_b200 import distributed
+    from modle_b200.simulation import Config, Simulation
+
+    cfg = Config(num_cells=12, target_contact_density=0.01).transform()
+    genome = _small_genome()
+    sim = Simulation(cfg, genome)
+    S = distributed.Shard
+    shards = [S(0, 0, 5, 0, 5.0), S(0, 5, 6, 0, 1.0), S(0, 6, 12, 0, 6.0), S(1, 0, 12, 0, 4.0),
+              S(3, 0, 12, 0, 30.0), S(4, 0, 12, 0, 1.0)]
+    eng = distributed.DeviceEngine(0, num_streams=3)
+    try:
+        out = distributed.run_sharded(eng, cfg.params, sim.intervals, 0, 1, None, shards=shards)
+        ora = _oracle_genome(cfg, genome)
+        for idx, o in out.items():
+            band, occ, stats, missed = ora[sim.intervals[idx].chrom_name]
+            assert np.array_equal(o["band"].cpu().numpy().view(np.uint32), band)
+            assert np.array_equal(o["occ1d"].cpu().numpy().view(np.uint64)[:len(occ)], occ)
+            assert int(o["missed"].item()) == missed
+            got = np.concatenate(o["stats"])
+            assert int(got["num_contacts"].sum()) == int(stats["num_contacts"].sum())
+            assert int(got["device_fault"].max()) == 0
+    finally:
+        eng.close()
+
+
+def test_phase_cycles_are_reported(gpu_ctx):
+    p, iv, bars, tasks = make_case(size=3_000_000, ncells=4, target_contact_density=0.01)
+    gpu_ctx.phase_cycles(reset=True)
+    gpu_ctx.simulate_interval(p, iv, bars, tasks)
+    ph = gpu_ctx.phase_cycles(reset=True)
+    assert ph["total"] > 0 and ph["secondary"] > 0 and ph["moves_generate"] > 0
+    main = sum(v for k, v in ph.items() if "." not in k and k not in ("total", "rng_refill(nested)"))
+    assert 0.5 * ph["total"] < main <= 1.01 * ph["total"]
+    assert all(v == 0 for v in gpu_ctx.phase_cycles().values())
