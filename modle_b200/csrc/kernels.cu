@@ -13,6 +13,8 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -148,6 +150,152 @@ __global__ void __launch_bounds__(256) k_register_contacts(const u32* __restrict
               static_cast<unsigned long long>(warp_missed));
 }
 
+// ---- binned contact register (bands much larger than the L2) ---------------------------------
+// A band that does not fit the L2 turns every contact into a random DRAM read-modify-write
+// (one 32-byte sector in, one out). The binned path first groups the contacts by 32 MB tile of
+// the band (a counting pass, then a scatter of the 4-byte pixel indices through per-CTA
+// shared-memory staging so that each tile receives coalesced runs), then replays the grouped
+// indices in order: the tile being updated is L2 resident, so DRAM sees each tile once.
+constexpr u32 kTileShift = 23;  // 2^23 pixels = 32 MB
+constexpr u32 kMaxTiles = 512;  // 2^32 pixels / 2^23
+constexpr u32 kBinBatch = 16;   // contacts per thread per batch of k_bin_scatter
+
+__device__ __forceinline__ u32 band_pixel(u32 b1, u32 b2, u32 nrows) {
+  const u32 i = b1 > b2 ? b1 - b2 : b2 - b1;
+  const u32 j = b1 > b2 ? b1 : b2;
+  return i >= nrows ? 0xFFFFFFFFu : j * nrows + i;
+}
+
+__global__ void __launch_bounds__(256) k_bin_count(const u32* __restrict__ bin1,
+                                                   const u32* __restrict__ bin2, size_t n, u32 nrows,
+                                                   u32* __restrict__ tile_counts,
+                                                   u64* __restrict__ missed) {
+  __shared__ u32 hist[kMaxTiles];
+  for (u32 t = threadIdx.x; t < kMaxTiles; t += blockDim.x) hist[t] = 0;
+  __syncthreads();
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  u32 my_missed = 0;
+  for (size_t e = size_t(blockIdx.x) * blockDim.x + threadIdx.x; e < n; e += stride) {
+    const u32 p = band_pixel(__ldcs(bin1 + e), __ldcs(bin2 + e), nrows);
+    if (p == 0xFFFFFFFFu) {
+      ++my_missed;
+    } else {
+      atomicAdd(&hist[p >> kTileShift], 1u);
+    }
+  }
+  __syncthreads();
+  for (u32 t = threadIdx.x; t < kMaxTiles; t += blockDim.x)
+    if (hist[t]) atomicAdd(&tile_counts[t], hist[t]);
+  const u32 warp_missed = __reduce_add_sync(0xffffffffu, my_missed);
+  if ((threadIdx.x & 31) == 0 && warp_missed)
+    atomicAdd(reinterpret_cast<unsigned long long*>(missed),
+              static_cast<unsigned long long>(warp_missed));
+}
+
+// exclusive scan of the tile counts into the tile cursors (one CTA, kMaxTiles threads);
+// tile_cursor[kMaxTiles] receives the total
+__global__ void __launch_bounds__(kMaxTiles) k_bin_offsets(const u32* __restrict__ tile_counts,
+                                                           u32* __restrict__ tile_cursor) {
+  __shared__ u32 sh[kMaxTiles];
+  const u32 t = threadIdx.x;
+  sh[t] = tile_counts[t];
+  __syncthreads();
+  for (u32 d = 1; d < kMaxTiles; d <<= 1) {
+    const u32 v = t >= d ? sh[t - d] : 0;
+    __syncthreads();
+    sh[t] += v;
+    __syncthreads();
+  }
+  tile_cursor[t] = sh[t] - tile_counts[t];
+  if (t == kMaxTiles - 1) tile_cursor[kMaxTiles] = sh[t];
+}
+
+__global__ void __launch_bounds__(256) k_bin_scatter(const u32* __restrict__ bin1,
+                                                     const u32* __restrict__ bin2, size_t n,
+                                                     u32 nrows, u32* __restrict__ tile_cursor,
+                                                     u32* __restrict__ binned) {
+  // Per batch of 256 x kBinBatch contacts: count per tile, exclusive scan of the counts (start of
+  // each tile's run inside the batch), one global reservation per non-empty tile, sort the batch
+  // by tile in shared memory, then copy it out so that consecutive threads write consecutive
+  // addresses of a tile's run.
+  __shared__ u32 cnt[kMaxTiles];     // contacts of this batch per tile, then fill cursor
+  __shared__ u32 start[kMaxTiles];   // first slot of the tile's run in `sorted`
+  __shared__ u32 gbase[kMaxTiles];   // where the run goes in `binned`
+  __shared__ u32 sorted[256 * kBinBatch];
+  __shared__ u16 sorted_tile[256 * kBinBatch];
+  __shared__ u32 warp_tot[8];
+  const size_t batch = size_t(blockDim.x) * kBinBatch;
+  const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (size_t b0 = size_t(blockIdx.x) * batch; b0 < n; b0 += size_t(gridDim.x) * batch) {
+    for (u32 t = threadIdx.x; t < kMaxTiles; t += blockDim.x) cnt[t] = 0;
+    __syncthreads();
+    u32 px[kBinBatch];
+#pragma unroll
+    for (u32 k = 0; k < kBinBatch; ++k) {
+      const size_t e = b0 + size_t(k) * blockDim.x + threadIdx.x;  // coalesced reads
+      px[k] = e < n ? band_pixel(__ldcs(bin1 + e), __ldcs(bin2 + e), nrows) : 0xFFFFFFFFu;
+      if (px[k] != 0xFFFFFFFFu) atomicAdd(&cnt[px[k] >> kTileShift], 1u);
+    }
+    __syncthreads();
+    // exclusive scan of cnt[0..512) with 256 threads (2 tiles each)
+    const u32 c0 = cnt[2 * threadIdx.x], c1 = cnt[2 * threadIdx.x + 1];
+    u32 inc = c0 + c1;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const u32 o = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= static_cast<u32>(d)) inc += o;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    u32 wbase = 0;
+    for (u32 w = 0; w < warp; ++w) wbase += warp_tot[w];
+    const u32 ex = wbase + inc - (c0 + c1);
+    start[2 * threadIdx.x] = ex;
+    start[2 * threadIdx.x + 1] = ex + c0;
+    gbase[2 * threadIdx.x] = c0 ? atomicAdd(&tile_cursor[2 * threadIdx.x], c0) : 0u;
+    gbase[2 * threadIdx.x + 1] = c1 ? atomicAdd(&tile_cursor[2 * threadIdx.x + 1], c1) : 0u;
+    u32 total = 0;
+    for (u32 w = 0; w < 8; ++w) total += warp_tot[w];
+    __syncthreads();
+    cnt[2 * threadIdx.x] = 0;
+    cnt[2 * threadIdx.x + 1] = 0;
+    __syncthreads();
+#pragma unroll
+    for (u32 k = 0; k < kBinBatch; ++k) {
+      if (px[k] == 0xFFFFFFFFu) continue;
+      const u32 t = px[k] >> kTileShift;
+      const u32 slot = start[t] + atomicAdd(&cnt[t], 1u);
+      sorted[slot] = px[k];
+      sorted_tile[slot] = static_cast<u16>(t);
+    }
+    __syncthreads();
+    for (u32 q = threadIdx.x; q < total; q += blockDim.x) {
+      const u32 t = sorted_tile[q];
+      binned[gbase[t] + (q - start[t])] = sorted[q];
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) k_scatter_binned(const u32* __restrict__ binned,
+                                                        const u32* __restrict__ total,
+                                                        u32* __restrict__ band) {
+  // consecutive CTAs take consecutive slices, so the whole grid works on one or two tiles at a time
+  const size_t n = *total;
+  const size_t per_iter = size_t(gridDim.x) * blockDim.x * 4;
+  for (size_t e0 = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) * 4; e0 < n; e0 += per_iter) {
+    if (e0 + 3 < n) {
+      const uint4 v = __ldcs(reinterpret_cast<const uint4*>(binned + e0));
+      atomicAdd(band + v.x, 1u);
+      atomicAdd(band + v.y, 1u);
+      atomicAdd(band + v.z, 1u);
+      atomicAdd(band + v.w, 1u);
+    } else {
+      for (size_t e = e0; e < n; ++e) atomicAdd(band + binned[e], 1u);
+    }
+  }
+}
+
 }  // namespace modle_b200
 
 using namespace modle_b200;
@@ -222,6 +370,9 @@ struct modle_b200_context {
   int next_slot = 0;
   DevBuf d_tasks, d_band, d_occ1d, d_stats, d_missed, d_snap_u64, d_snap_bar;
   PinnedBuf h_stage;  // band | occ1d | stats | missed of the host-buffer entry point
+  DevBuf d_binned, d_tiles;  // binned contact register: pixel indices by tile, counts + cursors
+  cudaEvent_t binned_done = nullptr;
+  size_t l2_bytes = 0;
   uint64_t launches = 0;
 };
 
@@ -244,6 +395,8 @@ int modle_b200_init(modle_b200_context** out, int device) {
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   ctx->num_sms = prop.multiProcessorCount;
+  ctx->l2_bytes = static_cast<size_t>(prop.l2CacheSize);
+  CUDA_TRY(cudaEventCreateWithFlags(&ctx->binned_done, cudaEventDisableTiming));
   ctx->max_smem_optin = prop.sharedMemPerBlockOptin;
   CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   CUDA_TRY(ctx->d_zig.reserve(sizeof(double) * (129 * 2 + 257 * 2)));
@@ -279,6 +432,7 @@ void modle_b200_destroy(modle_b200_context* ctx) {
   cudaDeviceSynchronize();
   for (auto& sl : ctx->slots)
     if (sl.done) cudaEventDestroy(sl.done);
+  if (ctx->binned_done) cudaEventDestroy(ctx->binned_done);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -599,6 +753,35 @@ int modle_b200_register_contacts_device(modle_b200_context* ctx, const uint32_t*
   cudaStream_t stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
   if (n == 0) return MODLE_B200_OK;
   const int threads = 256;
+  const u64 npx = nrows * ncols + 1;
+  // binned when the band is larger than the L2 and dense enough for tiles to be reused
+  // (MODLE_B200_REGISTER_PATH=direct|binned overrides, for measurements)
+  bool use_binned = npx * 4 > ctx->l2_bytes && n >= npx / 4 && n >= (size_t(1) << 20);
+  if (const char* force = std::getenv("MODLE_B200_REGISTER_PATH")) {
+    if (std::strcmp(force, "direct") == 0) use_binned = false;
+    if (std::strcmp(force, "binned") == 0) use_binned = n >= 1;
+  }
+  if (use_binned && n < (size_t(1) << 32)) {
+    // binned path (see k_bin_scatter). Its scratch is shared by the calls on this context.
+    CUDA_TRY(cudaEventSynchronize(ctx->binned_done));
+    CUDA_TRY(ctx->d_binned.reserve(sizeof(u32) * (n + 4)));
+    CUDA_TRY(ctx->d_tiles.reserve(sizeof(u32) * (2 * kMaxTiles + 1)));
+    u32* counts = static_cast<u32*>(ctx->d_tiles.p);
+    u32* cursor = counts + kMaxTiles;
+    u32* d_binned = static_cast<u32*>(ctx->d_binned.p);
+    const u32 grid = static_cast<u32>(ctx->num_sms) * 8;
+    CUDA_TRY(cudaMemsetAsync(counts, 0, sizeof(u32) * (2 * kMaxTiles + 1), stream));
+    k_bin_count<<<grid, threads, 0, stream>>>(d_bin1, d_bin2, n, static_cast<u32>(nrows), counts,
+                                              d_missed_updates);
+    k_bin_offsets<<<1, kMaxTiles, 0, stream>>>(counts, cursor);
+    k_bin_scatter<<<grid, threads, 0, stream>>>(d_bin1, d_bin2, n, static_cast<u32>(nrows), cursor,
+                                                d_binned);
+    k_scatter_binned<<<grid, threads, 0, stream>>>(d_binned, cursor + kMaxTiles, d_band);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(ctx->binned_done, stream));
+    ctx->launches += 4;
+    return MODLE_B200_OK;
+  }
   const int vec_ok = (reinterpret_cast<uintptr_t>(d_bin1) % 16 == 0) &&
                      (reinterpret_cast<uintptr_t>(d_bin2) % 16 == 0);
   const size_t items = vec_ok ? (n + 3) / 4 : n;

@@ -29,7 +29,7 @@ def main():
 
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default="")
-    ap.add_argument("--contacts", type=int, default=1 << 27)
+    ap.add_argument("--contacts", type=int, default=0)
     ap.add_argument("--reps", type=int, default=5)
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
@@ -48,7 +48,9 @@ def main():
     for case, nrows, ncols in (("c5_hbm", 3000, 242_194), ("c1_l2", 600, 12_889)):
         band = torch.zeros(nrows * ncols + 1, dtype=torch.int32, device=dev)
         missed = torch.zeros(1, dtype=torch.int64, device=dev)
-        n = args.contacts
+        # C5 at its real density (1 contact per pixel) unless --contacts says otherwise
+        n = args.contacts if (args.contacts or case != "c5_hbm") else nrows * ncols
+        n = n or (1 << 27)
         for kind in ("loop", "uniform"):
             b2 = torch.randint(0, ncols, (n,), device=dev, generator=g, dtype=torch.int64)
             if kind == "loop":
@@ -63,7 +65,7 @@ def main():
             del d
             times = []
             with torch.cuda.stream(stream):
-                for r in range(args.reps + 2):
+                for r in range(max(1, args.reps) + 2):
                     band.zero_()
                     missed.zero_()
                     e0 = torch.cuda.Event(enable_timing=True)
@@ -82,6 +84,7 @@ def main():
             rate = n / (ms * 1e-3)
             results.append({
                 "case": case, "stream": kind, "nrows": nrows, "ncols": ncols,
+                "path": os.environ.get("MODLE_B200_REGISTER_PATH", "auto"),
                 "band_bytes": 4 * (nrows * ncols + 1), "contacts": n, "ms": ms,
                 "contacts_per_s": rate,
                 "algorithmic_GBps": 8 * rate / 1e9,

@@ -245,3 +245,37 @@ def test_phase_cycles_are_reported(gpu_ctx):
     main = sum(v for k, v in ph.items() if "." not in k and k not in ("total", "rng_refill(nested)"))
     assert 0.5 * ph["total"] < main <= 1.01 * ph["total"]
     assert all(v == 0 for v in gpu_ctx.phase_cycles().values())
+
+
+def test_register_contacts_binned_path(gpu_ctx):
+    """Bands larger than the L2 go through the binned path (count, scatter by 32 MB tile,
+    replay); the result is the same histogram."""
+    import torch
+
+    rng = np.random.default_rng(5)
+    nrows, ncols = 3000, 20_000  # 240 MB band
+    n = 60_000_000 // 4 + 77     # dense enough for the binned path (>= a quarter of the pixels)
+    b2 = rng.integers(0, ncols, n, dtype=np.int64)
+    d = rng.integers(0, nrows + 40, n, dtype=np.int64)  # some pairs fall outside the band
+    b1 = np.clip(b2 - d, 0, None)
+    swap = rng.random(n) < 0.5
+    x1 = np.where(swap, b2, b1).astype(np.uint32)
+    x2 = np.where(swap, b1, b2).astype(np.uint32)
+    i = np.abs(x1.astype(np.int64) - x2.astype(np.int64))
+    j = np.maximum(x1, x2).astype(np.int64)
+    ok = i < nrows
+    expect = np.bincount(j[ok] * nrows + i[ok], minlength=nrows * ncols + 1).astype(np.uint32)
+    d1 = torch.from_numpy(x1.view(np.int32)).cuda()
+    d2 = torch.from_numpy(x2.view(np.int32)).cuda()
+    band = torch.zeros(nrows * ncols + 1, dtype=torch.int32, device="cuda")
+    missed = torch.zeros(1, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    launches0 = gpu_ctx.kernel_launches()
+    for _ in range(2):  # twice: the scratch is reused, counts must double
+        gpu_ctx.register_contacts_device(d1.data_ptr(), d2.data_ptr(), n, nrows, ncols,
+                                         band.data_ptr(), missed.data_ptr())
+    gpu_ctx.synchronize()
+    torch.cuda.synchronize()
+    assert gpu_ctx.kernel_launches() - launches0 == 8  # 4 kernels per binned call
+    assert np.array_equal(band.cpu().numpy().view(np.uint32), 2 * expect)
+    assert int(missed.item()) == 2 * int((~ok).sum())
