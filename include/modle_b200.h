@@ -237,6 +237,38 @@ int modle_b200_register_contacts_device(modle_b200_context* ctx, const uint32_t*
                                         uint64_t ncols, uint32_t* d_band,
                                         uint64_t* d_missed_updates, void* cuda_stream);
 
+/* ---- band -> sorted COO pixels: the hand-off to the .cool writer -------------------------------
+ * Replaces the pixel loop of modle::io::internal::append_contact_matrix_to_cooler
+ * (src/libmodle_io/contact_matrix_dense_io_impl.hpp:50-71): for i in [0, ncols), j in
+ * [i, min(ncols, i + nrows)), every non-zero matrix.unsafe_get(i, j) becomes
+ * {bin_offset + i, bin_offset + j, int32(count)}, in that (bin1, bin2)-sorted order. bin_offset is
+ * what emplace_pixel adds (:30-43): first bin id of the chromosome + interval start / bin size.
+ * modle_b200_pixel has the memory layout of hictk::ThinPixel<std::int32_t> (two uint64 bin ids,
+ * int32 count, 4 bytes of tail padding), so the output can be handed to
+ * hictk::cooler::File::append_pixels as is.                                                      */
+typedef struct modle_b200_pixel {
+  uint64_t bin1_id;
+  uint64_t bin2_id;
+  int32_t count;
+  int32_t reserved_; /* tail padding of ThinPixel<int32_t>; written as 0 */
+} modle_b200_pixel;
+
+/* Device-resident, asynchronous on `cuda_stream`. Step 1 fills d_row_offsets[0..ncols] (ncols+1
+ * uint64): d_row_offsets[r] = index of the first pixel of row r, d_row_offsets[ncols] = number of
+ * non-zero pixels. Step 2 writes the pixels (at most `capacity`; size it from step 1).          */
+int modle_b200_count_pixels_device(modle_b200_context* ctx, const uint32_t* d_band, uint64_t nrows,
+                                   uint64_t ncols, uint64_t* d_row_offsets, void* cuda_stream);
+int modle_b200_fill_pixels_device(modle_b200_context* ctx, const uint32_t* d_band, uint64_t nrows,
+                                  uint64_t ncols, uint64_t bin_offset,
+                                  const uint64_t* d_row_offsets, modle_b200_pixel* d_pixels,
+                                  uint64_t capacity, void* cuda_stream);
+/* HOST buffers in and out (copies included). *num_pixels_out is always set to the number of
+ * non-zero pixels; with pixels_out == NULL and capacity == 0 the call is a size query, with a
+ * too small capacity it fails with MODLE_B200_ERR_INVALID_ARGUMENT and writes nothing.          */
+int modle_b200_band_to_pixels(modle_b200_context* ctx, const uint32_t* band, uint64_t nrows,
+                              uint64_t ncols, uint64_t bin_offset, modle_b200_pixel* pixels_out,
+                              uint64_t capacity, uint64_t* num_pixels_out);
+
 /* Profiling aid (the reference has none; --skip-output + perf is its recipe, cli.cpp:182-186):
  * SM-clock cycles the simulate kernel spent in each phase of the per-cell loop, summed over all
  * cells simulated on this context since the last reset. Slots, in order: init, burn-in, bind,

@@ -119,6 +119,24 @@ class CellSnapshot(C.Structure):
     ]
 
 
+class Pixel(C.Structure):
+    """hictk::ThinPixel<std::int32_t> layout."""
+    _fields_ = [
+        ("bin1_id", C.c_uint64),
+        ("bin2_id", C.c_uint64),
+        ("count", C.c_int32),
+        ("reserved_", C.c_int32),
+    ]
+
+
+def pixel_dtype():
+    import numpy as np
+
+    dt = np.dtype([("bin1_id", "<u8"), ("bin2_id", "<u8"), ("count", "<i4"), ("reserved_", "<i4")])
+    assert dt.itemsize == C.sizeof(Pixel) == 24
+    return dt
+
+
 # numpy structured dtypes with the same layout (for zero-copy views of arrays of structs)
 def np_dtypes():
     import numpy as np

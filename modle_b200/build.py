@@ -6,16 +6,16 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmodle_b200.so")
-SOURCES = ["host.cpp", "kernels.cu"]
+SOURCES = ["host.cpp", "kernels.cu", "pixels.cu"]
 HEADERS = ["cta.hpp", "sim_types.hpp", "sim_core.hpp", "launch_prep.hpp", "host_rng.hpp",
-           "status.hpp", os.path.join("..", "..", "include", "modle_b200.h")]
+           "status.hpp", "context.hpp", os.path.join("..", "..", "include", "modle_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     # strict IEEE double arithmetic: no FMA contraction, so results match the CPU oracle
     # (built with -ffp-contract=off) operation for operation
     "-fmad=false",
-    "-Xcompiler", "-fPIC,-O2,-ffp-contract=off", "-shared", "-cudart", "static",
+    "-Xcompiler", "-fPIC,-O2,-ffp-contract=off", "-shared", "-cudart", "static", "--threads", "0",
 ]
 
 

@@ -14,7 +14,7 @@ namespace modle_b200 {
 // tbl[(k * 256 + v) * 4 + w] = word w of T^W applied to the state whose k-th byte is v (all other
 // bytes 0); T^W g is the XOR of the 32 entries selected by the bytes of g. One table (256 KB) per
 // staging configuration, built on the host (launch_prep.hpp) and kept in global memory.
-constexpr int kJumpSlots = 2;
+
 constexpr size_t kJumpTableWords = size_t(32) * 256 * 4;
 #if MB_DEVICE_BUILD
 // The RNG ring lives in global memory and is written and read by the same CTA with a CTA

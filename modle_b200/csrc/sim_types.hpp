@@ -72,6 +72,9 @@ enum : int {
   kNumPhases
 };
 
+// number of RNG staging configurations (jump tables) a context keeps; see sim_core.hpp
+constexpr int kJumpSlots = 2;
+
 // Everything the kernel needs to know about the run; one per launch, in global memory.
 struct KernelParams {
   u32 start, end;  // interval [start, end)

@@ -73,6 +73,14 @@ def lib():
         L.modle_b200_register_contacts_device.argtypes = [
             C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_void_p,
             C.c_void_p, C.c_void_p]
+        L.modle_b200_count_pixels_device.argtypes = [
+            C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
+        L.modle_b200_fill_pixels_device.argtypes = [
+            C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p,
+            C.c_uint64, C.c_void_p]
+        L.modle_b200_band_to_pixels.argtypes = [
+            C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64,
+            u64p]
         _LIB = L
     return _LIB
 
@@ -87,6 +95,7 @@ EXPORTED_SYMBOLS = [
     "modle_b200_simulate_interval", "modle_b200_simulate_interval_device",
     "modle_b200_synchronize", "modle_b200_snapshot_cell", "modle_b200_register_contacts_device",
     "modle_b200_kernel_launches", "modle_b200_phase_cycles",
+    "modle_b200_count_pixels_device", "modle_b200_fill_pixels_device", "modle_b200_band_to_pixels",
 ]
 
 PHASE_NAMES = ["init", "burnin", "bind", "rank", "contacts", "moves_generate", "moves_adjust",

@@ -152,6 +152,36 @@ class Context:
             C.c_void_p(d_missed), C.c_void_p(stream) if stream else None)
         host.check(rc)
 
+    # -- band -> sorted COO pixels (the .cool writer hand-off) ---------------------------------
+    def band_to_pixels(self, band, nrows, ncols, bin_offset=0):
+        """append_contact_matrix_to_cooler's pixel loop (contact_matrix_dense_io_impl.hpp:50-71)
+        on the GPU: host band in, array of ThinPixel<int32>-layout records out."""
+        band = np.ascontiguousarray(band, dtype=np.uint32)
+        if band.size < nrows * ncols + 1:
+            raise ValueError("band buffer smaller than nrows*ncols+1")
+        n = C.c_uint64(0)
+        L = host.lib()
+        host.check(L.modle_b200_band_to_pixels(self._h, band.ctypes.data, nrows, ncols, bin_offset,
+                                               None, 0, C.byref(n)))
+        out = np.zeros(int(n.value), dtype=abi.pixel_dtype())
+        if n.value:
+            host.check(L.modle_b200_band_to_pixels(self._h, band.ctypes.data, nrows, ncols,
+                                                   bin_offset, out.ctypes.data, len(out),
+                                                   C.byref(n)))
+        return out
+
+    def count_pixels_device(self, d_band, nrows, ncols, d_row_offsets, stream=None):
+        host.check(host.lib().modle_b200_count_pixels_device(
+            self._h, C.c_void_p(d_band), nrows, ncols, C.c_void_p(d_row_offsets),
+            C.c_void_p(stream) if stream else None))
+
+    def fill_pixels_device(self, d_band, nrows, ncols, bin_offset, d_row_offsets, d_pixels,
+                           capacity, stream=None):
+        host.check(host.lib().modle_b200_fill_pixels_device(
+            self._h, C.c_void_p(d_band), nrows, ncols, bin_offset, C.c_void_p(d_row_offsets),
+            C.c_void_p(d_pixels) if d_pixels else None, capacity,
+            C.c_void_p(stream) if stream else None))
+
     def snapshot_cell(self, params, interval, barriers, task):
         n = int(interval.num_lefs)
         nb = len(barriers)

@@ -333,4 +333,31 @@ int oracle_snapshot_cell(const modle_b200_sim_params* params, const modle_b200_i
   return 0;
 }
 
+// Pixel loop of modle::io::internal::append_contact_matrix_to_cooler
+// (src/libmodle_io/contact_matrix_dense_io_impl.hpp:50-71) with emplace_pixel's bin offset
+// (:30-43) and ContactMatrixDense::unsafe_get (contact_matrix_dense_unsafe_impl.hpp:33-42:
+// transpose_coords, "i >= nrows -> 0", encode_idx = col * nrows + row). Returns the number of
+// non-zero pixels; writes at most `capacity` of them (pixels may be NULL when capacity is 0).
+u64 oracle_band_to_pixels(const u32* band, u64 nrows, u64 ncols, u64 bin_offset,
+                          modle_b200_pixel* pixels, u64 capacity) {
+  const auto unsafe_get = [&](u64 row, u64 col) -> u32 {
+    const u64 i = row > col ? row - col : col - row;  // transpose_coords
+    const u64 j = row > col ? row : col;
+    if (i >= nrows) return 0;
+    return band[j * nrows + i];
+  };
+  u64 n_out = 0;
+  for (u64 i = 0; i < ncols; ++i) {
+    for (u64 j = i; j < ncols && j - i < nrows; ++j) {
+      if (const u32 n = unsafe_get(i, j); n != 0) {
+        if (n_out < capacity)
+          pixels[n_out] = modle_b200_pixel{bin_offset + i, bin_offset + j,
+                                           static_cast<std::int32_t>(n), 0};
+        ++n_out;
+      }
+    }
+  }
+  return n_out;
+}
+
 }  // extern "C"

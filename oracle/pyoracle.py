@@ -203,6 +203,21 @@ def simulate_interval(params, interval, barriers, tasks, nthreads=1, want_occ=Tr
     return band, occ, stats, int(missed.value)
 
 
+def band_to_pixels(band, nrows, ncols, bin_offset=0):
+    """CPU counterpart of modle_b200_band_to_pixels (the reference's .cool pixel loop)."""
+    band = np.ascontiguousarray(band, dtype=np.uint32)
+    assert band.size >= nrows * ncols + 1
+    L = lib()
+    L.oracle_band_to_pixels.restype = C.c_uint64
+    L.oracle_band_to_pixels.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64,
+                                        C.c_void_p, C.c_uint64]
+    n = int(L.oracle_band_to_pixels(band.ctypes.data, nrows, ncols, bin_offset, None, 0))
+    out = np.zeros(n, dtype=abi.pixel_dtype())
+    if n:
+        L.oracle_band_to_pixels(band.ctypes.data, nrows, ncols, bin_offset, out.ctypes.data, n)
+    return out
+
+
 def snapshot_cell(params, interval, barriers, task):
     n = int(interval.num_lefs)
     nb = len(barriers)
