@@ -190,6 +190,35 @@ int modle_b200_make_cell_tasks(const modle_b200_sim_params* p, const char* chrom
                                size_t name_len, const modle_b200_interval* interval,
                                modle_b200_cell_task* tasks);
 
+/* ---- genome import: chrom.sizes + barrier BED6 (+ genomic-intervals BED3) -> intervals ---------
+ * Host-only. Reproduces Genome::Genome (src/libmodle/internal/genome.cpp:299-330) with the
+ * parsers it uses (chrom_sizes::Parser, src/libmodle_io/chrom_sizes.cpp:24-66; bed::Parser and
+ * bed::BED, src/libmodle_io/bed.cpp:44-330,411-590), Genome::map_barriers_to_intervals /
+ * generate_barriers_from_bed_records (genome.cpp:423-488: pos = (start + end + 1) / 2, '.' strands
+ * skipped, score -> occupancy -> stp) and Simulation's --extrusion-barrier-occupancy override
+ * (src/libmodle/cpu/simulation.cpp:51-60). Plain-text files only (no libarchive here). Intervals
+ * come out in the reference's processing order (chromosomes in chrom.sizes order, intervals by
+ * start), barriers sorted by position; malformed input fails with
+ * MODLE_B200_ERR_INVALID_ARGUMENT and the reference's diagnostic in modle_b200_last_error().
+ * path_to_genomic_intervals may be NULL or "" (whole chromosomes).                              */
+typedef struct modle_b200_genome modle_b200_genome;
+int modle_b200_genome_import(const char* path_to_chrom_sizes, const char* path_to_extr_barriers,
+                             const char* path_to_genomic_intervals,
+                             const modle_b200_sim_params* params,
+                             int interpret_name_field_as_puu, modle_b200_genome** out);
+void modle_b200_genome_free(modle_b200_genome* genome);
+size_t modle_b200_genome_num_chromosomes(const modle_b200_genome* genome);
+size_t modle_b200_genome_num_intervals(const modle_b200_genome* genome);
+uint64_t modle_b200_genome_num_barriers(const modle_b200_genome* genome);
+/* The i-th interval. Any output pointer may be NULL. *chrom_name and *barriers stay valid until
+ * modle_b200_genome_free. *bin_offset is what append_contact_matrix_to_cooler adds to the
+ * interval's pixel coordinates (first bin of the chromosome + start / bin_size).               */
+int modle_b200_genome_get_interval(const modle_b200_genome* genome, size_t i,
+                                   const char** chrom_name, size_t* chrom_id,
+                                   uint64_t* chrom_size, uint64_t* start, uint64_t* end,
+                                   const modle_b200_barrier** barriers, size_t* num_barriers,
+                                   uint64_t* bin_offset);
+
 /* ---- device path ------------------------------------------------------------------------ */
 
 /* Binds a context to CUDA device `device`; fails without a GPU (no CPU fallback). */

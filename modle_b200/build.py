@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmodle_b200.so")
-SOURCES = ["host.cpp", "kernels.cu", "pixels.cu"]
+SOURCES = ["host.cpp", "genome.cpp", "kernels.cu", "pixels.cu"]
 HEADERS = ["cta.hpp", "sim_types.hpp", "sim_core.hpp", "launch_prep.hpp", "host_rng.hpp",
            "status.hpp", "context.hpp", os.path.join("..", "..", "include", "modle_b200.h")]
 

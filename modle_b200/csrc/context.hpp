@@ -67,6 +67,7 @@ struct LaunchSlot {
   bool in_flight = false;
 };
 constexpr int kLaunchSlots = 4;
+constexpr int kPxSyncSlots = 8;
 
 struct modle_b200_context {
   int device = 0;
@@ -84,6 +85,8 @@ struct modle_b200_context {
   DevBuf d_binned, d_tiles;  // binned contact register: pixel indices by tile, counts + cursors
   cudaEvent_t binned_done = nullptr;
   DevBuf d_px_band, d_px_rows, d_px_out;  // band -> pixels (pixels.cu), host-buffer entry point
+  DevBuf d_px_sync[kPxSyncSlots];         // look-back scratch of k_count_row_pixels
+  uint64_t px_calls = 0;
   size_t l2_bytes = 0;
   uint64_t launches = 0;
 };

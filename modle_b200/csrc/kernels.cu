@@ -42,8 +42,9 @@ struct LaunchArgs {
   u8* snap_bar;   // n_bar
 };
 
-// Two instantiations: <256, kSmallMinBlocks> for intervals whose state leaves room for several
-// CTAs per SM, <512, 1> for the large ones (one CTA owns the SM's shared memory).
+// Three instantiations: <256, kSmallMinBlocks> for intervals whose state leaves room for three
+// CTAs per SM, <512, 2> for two, <1024, 1> for the large ones (one CTA owns the SM's shared
+// memory). Co-resident CTAs hide each other's CTA-barrier stalls.
 #ifndef MODLE_B200_SMALL_MIN_BLOCKS
 #define MODLE_B200_SMALL_MIN_BLOCKS 3
 #endif
@@ -156,9 +157,11 @@ __global__ void __launch_bounds__(256) k_register_contacts(const u32* __restrict
 // the band (a counting pass, then a scatter of the 4-byte pixel indices through per-CTA
 // shared-memory staging so that each tile receives coalesced runs), then replays the grouped
 // indices in order: the tile being updated is L2 resident, so DRAM sees each tile once.
-constexpr u32 kTileShift = 23;  // 2^23 pixels = 32 MB
-constexpr u32 kMaxTiles = 512;  // 2^32 pixels / 2^23
-constexpr u32 kBinBatch = 16;   // contacts per thread per batch of k_bin_scatter
+constexpr u32 kMaxTiles = 512;       // 2^32 pixels / 2^23 (tiles are at least 32 MB)
+constexpr u32 kMinTileShift = 23;
+constexpr u32 kBinThreads = 512;     // k_bin_scatter: one tile counter per thread
+constexpr u32 kBinBatch = 16;        // contacts per thread per batch of k_bin_scatter
+static_assert(kBinThreads == kMaxTiles, "k_bin_scatter scans one tile counter per thread");
 
 __device__ __forceinline__ u32 band_pixel(u32 b1, u32 b2, u32 nrows) {
   const u32 i = b1 > b2 ? b1 - b2 : b2 - b1;
@@ -168,7 +171,7 @@ __device__ __forceinline__ u32 band_pixel(u32 b1, u32 b2, u32 nrows) {
 
 __global__ void __launch_bounds__(256) k_bin_count(const u32* __restrict__ bin1,
                                                    const u32* __restrict__ bin2, size_t n, u32 nrows,
-                                                   u32* __restrict__ tile_counts,
+                                                   u32 tile_shift, u32* __restrict__ tile_counts,
                                                    u64* __restrict__ missed) {
   __shared__ u32 hist[kMaxTiles];
   for (u32 t = threadIdx.x; t < kMaxTiles; t += blockDim.x) hist[t] = 0;
@@ -180,7 +183,7 @@ __global__ void __launch_bounds__(256) k_bin_count(const u32* __restrict__ bin1,
     if (p == 0xFFFFFFFFu) {
       ++my_missed;
     } else {
-      atomicAdd(&hist[p >> kTileShift], 1u);
+      atomicAdd(&hist[p >> tile_shift], 1u);
     }
   }
   __syncthreads();
@@ -192,107 +195,124 @@ __global__ void __launch_bounds__(256) k_bin_count(const u32* __restrict__ bin1,
               static_cast<unsigned long long>(warp_missed));
 }
 
-// exclusive scan of the tile counts into the tile cursors (one CTA, kMaxTiles threads);
-// tile_cursor[kMaxTiles] receives the total
-__global__ void __launch_bounds__(kMaxTiles) k_bin_offsets(const u32* __restrict__ tile_counts,
-                                                           u32* __restrict__ tile_cursor) {
-  __shared__ u32 sh[kMaxTiles];
-  const u32 t = threadIdx.x;
-  sh[t] = tile_counts[t];
-  __syncthreads();
-  for (u32 d = 1; d < kMaxTiles; d <<= 1) {
-    const u32 v = t >= d ? sh[t - d] : 0;
-    __syncthreads();
-    sh[t] += v;
-    __syncthreads();
+// Exclusive scan of one value per thread over a CTA of kBinThreads threads; *total = the sum.
+// Ends with the scratch free for reuse after the caller's next __syncthreads().
+__device__ __forceinline__ u32 tiles_exscan(u32 mine, u32* warp_tot, u32* total) {
+  const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  u32 inc = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const u32 o = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= static_cast<u32>(d)) inc += o;
   }
-  tile_cursor[t] = sh[t] - tile_counts[t];
-  if (t == kMaxTiles - 1) tile_cursor[kMaxTiles] = sh[t];
+  if (lane == 31) warp_tot[warp] = inc;
+  __syncthreads();
+  u32 wbase = 0, tot = 0;
+#pragma unroll
+  for (u32 w = 0; w < kBinThreads / 32; ++w) {
+    const u32 v = warp_tot[w];
+    if (w < warp) wbase += v;
+    tot += v;
+  }
+  *total = tot;
+  return wbase + inc - mine;
 }
 
-__global__ void __launch_bounds__(256) k_bin_scatter(const u32* __restrict__ bin1,
-                                                     const u32* __restrict__ bin2, size_t n,
-                                                     u32 nrows, u32* __restrict__ tile_cursor,
-                                                     u32* __restrict__ binned) {
-  // Per batch of 256 x kBinBatch contacts: count per tile, exclusive scan of the counts (start of
+// exclusive scan of the tile counts into the tile cursors (one CTA, one tile per thread);
+// tile_cursor[kMaxTiles] receives the total
+__global__ void __launch_bounds__(kBinThreads) k_bin_offsets(const u32* __restrict__ tile_counts,
+                                                             u32* __restrict__ tile_cursor) {
+  __shared__ u32 warp_tot[kBinThreads / 32];
+  const u32 c = tile_counts[threadIdx.x];
+  u32 total;
+  tile_cursor[threadIdx.x] = tiles_exscan(c, warp_tot, &total);
+  if (threadIdx.x == 0) tile_cursor[kMaxTiles] = total;
+}
+
+__global__ void __launch_bounds__(kBinThreads) k_bin_scatter(const u32* __restrict__ bin1,
+                                                             const u32* __restrict__ bin2, size_t n,
+                                                             u32 nrows, u32 tile_shift,
+                                                             u32* __restrict__ tile_cursor,
+                                                             u32* __restrict__ binned) {
+  // Per batch of 512 x kBinBatch contacts: count per tile, exclusive scan of the counts (start of
   // each tile's run inside the batch), one global reservation per non-empty tile, sort the batch
   // by tile in shared memory, then copy it out so that consecutive threads write consecutive
-  // addresses of a tile's run.
+  // addresses of a tile's run (~24 contacts per run at 350 tiles).
   __shared__ u32 cnt[kMaxTiles];     // contacts of this batch per tile, then fill cursor
   __shared__ u32 start[kMaxTiles];   // first slot of the tile's run in `sorted`
   __shared__ u32 gbase[kMaxTiles];   // where the run goes in `binned`
-  __shared__ u32 sorted[256 * kBinBatch];
-  __shared__ u16 sorted_tile[256 * kBinBatch];
-  __shared__ u32 warp_tot[8];
-  const size_t batch = size_t(blockDim.x) * kBinBatch;
-  const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ u32 sorted[kBinThreads * kBinBatch];
+  __shared__ u32 warp_tot[kBinThreads / 32];
+  const size_t batch = size_t(kBinThreads) * kBinBatch;
+  cnt[threadIdx.x] = 0;
+  __syncthreads();
   for (size_t b0 = size_t(blockIdx.x) * batch; b0 < n; b0 += size_t(gridDim.x) * batch) {
-    for (u32 t = threadIdx.x; t < kMaxTiles; t += blockDim.x) cnt[t] = 0;
-    __syncthreads();
     u32 px[kBinBatch];
 #pragma unroll
     for (u32 k = 0; k < kBinBatch; ++k) {
-      const size_t e = b0 + size_t(k) * blockDim.x + threadIdx.x;  // coalesced reads
+      const size_t e = b0 + size_t(k) * kBinThreads + threadIdx.x;  // coalesced reads
       px[k] = e < n ? band_pixel(__ldcs(bin1 + e), __ldcs(bin2 + e), nrows) : 0xFFFFFFFFu;
-      if (px[k] != 0xFFFFFFFFu) atomicAdd(&cnt[px[k] >> kTileShift], 1u);
     }
-    __syncthreads();
-    // exclusive scan of cnt[0..512) with 256 threads (2 tiles each)
-    const u32 c0 = cnt[2 * threadIdx.x], c1 = cnt[2 * threadIdx.x + 1];
-    u32 inc = c0 + c1;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const u32 o = __shfl_up_sync(0xffffffffu, inc, d);
-      if (lane >= static_cast<u32>(d)) inc += o;
-    }
-    if (lane == 31) warp_tot[warp] = inc;
+    for (u32 k = 0; k < kBinBatch; ++k)
+      if (px[k] != 0xFFFFFFFFu) atomicAdd(&cnt[px[k] >> tile_shift], 1u);
     __syncthreads();
-    u32 wbase = 0;
-    for (u32 w = 0; w < warp; ++w) wbase += warp_tot[w];
-    const u32 ex = wbase + inc - (c0 + c1);
-    start[2 * threadIdx.x] = ex;
-    start[2 * threadIdx.x + 1] = ex + c0;
-    gbase[2 * threadIdx.x] = c0 ? atomicAdd(&tile_cursor[2 * threadIdx.x], c0) : 0u;
-    gbase[2 * threadIdx.x + 1] = c1 ? atomicAdd(&tile_cursor[2 * threadIdx.x + 1], c1) : 0u;
-    u32 total = 0;
-    for (u32 w = 0; w < 8; ++w) total += warp_tot[w];
-    __syncthreads();
-    cnt[2 * threadIdx.x] = 0;
-    cnt[2 * threadIdx.x + 1] = 0;
+    const u32 c = cnt[threadIdx.x];
+    cnt[threadIdx.x] = 0;
+    u32 total;
+    const u32 ex = tiles_exscan(c, warp_tot, &total);
+    start[threadIdx.x] = ex;
+    gbase[threadIdx.x] = c ? atomicAdd(&tile_cursor[threadIdx.x], c) : 0u;
     __syncthreads();
 #pragma unroll
     for (u32 k = 0; k < kBinBatch; ++k) {
       if (px[k] == 0xFFFFFFFFu) continue;
-      const u32 t = px[k] >> kTileShift;
-      const u32 slot = start[t] + atomicAdd(&cnt[t], 1u);
-      sorted[slot] = px[k];
-      sorted_tile[slot] = static_cast<u16>(t);
+      const u32 t = px[k] >> tile_shift;
+      sorted[start[t] + atomicAdd(&cnt[t], 1u)] = px[k];
     }
     __syncthreads();
-    for (u32 q = threadIdx.x; q < total; q += blockDim.x) {
-      const u32 t = sorted_tile[q];
-      binned[gbase[t] + (q - start[t])] = sorted[q];
+    cnt[threadIdx.x] = 0;
+    for (u32 q = threadIdx.x; q < total; q += kBinThreads) {
+      const u32 v = sorted[q];
+      const u32 t = v >> tile_shift;
+      binned[gbase[t] + (q - start[t])] = v;
     }
     __syncthreads();
   }
 }
 
+// Replays the grouped indices tile by tile. The grid is launched cooperatively (all CTAs are
+// resident) and paced by an arrival counter: a CTA starts tile k only after every CTA has finished
+// tile k-2, so at most two tiles are being updated at any time and they stay L2 resident -- DRAM
+// sees each tile's sectors once in and once out. Without the pacing the CTAs drift apart, the
+// working set outgrows the L2 and every reduction becomes a DRAM round trip again.
 __global__ void __launch_bounds__(256) k_scatter_binned(const u32* __restrict__ binned,
-                                                        const u32* __restrict__ total,
-                                                        u32* __restrict__ band) {
-  // consecutive CTAs take consecutive slices, so the whole grid works on one or two tiles at a time
-  const size_t n = *total;
-  const size_t per_iter = size_t(gridDim.x) * blockDim.x * 4;
-  for (size_t e0 = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) * 4; e0 < n; e0 += per_iter) {
-    if (e0 + 3 < n) {
-      const uint4 v = __ldcs(reinterpret_cast<const uint4*>(binned + e0));
-      atomicAdd(band + v.x, 1u);
-      atomicAdd(band + v.y, 1u);
-      atomicAdd(band + v.z, 1u);
-      atomicAdd(band + v.w, 1u);
-    } else {
-      for (size_t e = e0; e < n; ++e) atomicAdd(band + binned[e], 1u);
+                                                        const u32* __restrict__ tile_counts,
+                                                        const u32* __restrict__ tile_end,
+                                                        u32 ntiles, u32* __restrict__ band,
+                                                        u32* __restrict__ arrivals) {
+  u32 k = 0;  // non-empty tiles done so far (the same sequence in every CTA)
+  for (u32 t = 0; t < ntiles; ++t) {
+    const u32 cnt = tile_counts[t];
+    if (cnt == 0) continue;
+    if (k >= 2) {
+      if (threadIdx.x == 0) {
+        const u32 want = (k - 1) * gridDim.x;
+        u32 seen;
+        do {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(arrivals) : "memory");
+          if (seen < want) __nanosleep(64);
+        } while (seen < want);
+      }
+      __syncthreads();
     }
+    const u64 lo = u64(tile_end[t]) - cnt;
+    const u64 a = lo + u64(cnt) * blockIdx.x / gridDim.x;
+    const u64 z = lo + u64(cnt) * (blockIdx.x + 1) / gridDim.x;
+    for (u64 e = a + threadIdx.x; e < z; e += blockDim.x) atomicAdd(band + __ldcs(binned + e), 1u);
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(arrivals, 1u);
+    ++k;
   }
 }
 
@@ -344,6 +364,10 @@ int modle_b200_init(modle_b200_context** out, int device) {
                                   static_cast<int>(ctx->max_smem_optin - fa.sharedSizeBytes)));
     CUDA_TRY(cudaFuncGetAttributes(&fa, k_simulate_cells<MODLE_B200_LARGE_THREADS, 1>));
     CUDA_TRY(cudaFuncSetAttribute(k_simulate_cells<MODLE_B200_LARGE_THREADS, 1>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(ctx->max_smem_optin - fa.sharedSizeBytes)));
+    CUDA_TRY(cudaFuncGetAttributes(&fa, k_simulate_cells<512, 2>));
+    CUDA_TRY(cudaFuncSetAttribute(k_simulate_cells<512, 2>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(ctx->max_smem_optin - fa.sharedSizeBytes)));
     ctx->max_smem_optin -= fa.sharedSizeBytes;
@@ -407,7 +431,8 @@ int launch_simulate(modle_b200_context* ctx, const modle_b200_sim_params* params
   const std::string err =
       prepare_interval(*params, *interval, h_barriers, num_barriers, sc, &kp, &hd);
   if (!err.empty()) return fail(MODLE_B200_ERR_UNSUPPORTED, err);
-  const size_t smem = ((sizeof(CellShared) + 15) / 16) * 16 + cell_array_bytes(kp.n_lefs, kp.n_bar);
+  const size_t smem =
+      ((sizeof(CellShared) + 15) / 16) * 16 + cell_array_bytes(kp.n_lefs, kp.n_bar);
   if (smem > ctx->max_smem_optin)
     return fail(MODLE_B200_ERR_UNSUPPORTED,
                 "interval needs " + std::to_string(smem) +
@@ -461,9 +486,10 @@ int launch_simulate(modle_b200_context* ctx, const modle_b200_sim_params* params
                            sizeof(u32) * hd.bar_dir_rev.size(), cudaMemcpyHostToDevice, stream));
 
   // grid: persistent CTAs, as many as fit
-  const bool small = sc.cta_threads == 256;
   void (*kernel)(const LaunchArgs) =
-      small ? k_simulate_cells<256, MODLE_B200_SMALL_MIN_BLOCKS> : k_simulate_cells<MODLE_B200_LARGE_THREADS, 1>;
+      sc.cta_threads == 256   ? k_simulate_cells<256, MODLE_B200_SMALL_MIN_BLOCKS>
+      : sc.cta_threads == 512 ? k_simulate_cells<512, 2>
+                              : k_simulate_cells<MODLE_B200_LARGE_THREADS, 1>;
   int per_sm = 0;
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel,
                                                          static_cast<int>(sc.cta_threads), smem));
@@ -691,18 +717,36 @@ int modle_b200_register_contacts_device(modle_b200_context* ctx, const uint32_t*
     // binned path (see k_bin_scatter). Its scratch is shared by the calls on this context.
     CUDA_TRY(cudaEventSynchronize(ctx->binned_done));
     CUDA_TRY(ctx->d_binned.reserve(sizeof(u32) * (n + 4)));
-    CUDA_TRY(ctx->d_tiles.reserve(sizeof(u32) * (2 * kMaxTiles + 1)));
+    CUDA_TRY(ctx->d_tiles.reserve(sizeof(u32) * (2 * kMaxTiles + 2)));
     u32* counts = static_cast<u32*>(ctx->d_tiles.p);
     u32* cursor = counts + kMaxTiles;
     u32* d_binned = static_cast<u32*>(ctx->d_binned.p);
     const u32 grid = static_cast<u32>(ctx->num_sms) * 8;
-    CUDA_TRY(cudaMemsetAsync(counts, 0, sizeof(u32) * (2 * kMaxTiles + 1), stream));
-    k_bin_count<<<grid, threads, 0, stream>>>(d_bin1, d_bin2, n, static_cast<u32>(nrows), counts,
-                                              d_missed_updates);
-    k_bin_offsets<<<1, kMaxTiles, 0, stream>>>(counts, cursor);
-    k_bin_scatter<<<grid, threads, 0, stream>>>(d_bin1, d_bin2, n, static_cast<u32>(nrows), cursor,
-                                                d_binned);
-    k_scatter_binned<<<grid, threads, 0, stream>>>(d_binned, cursor + kMaxTiles, d_band);
+    u32* arrivals = cursor + kMaxTiles + 1;
+    CUDA_TRY(cudaMemsetAsync(counts, 0, sizeof(u32) * (2 * kMaxTiles + 2), stream));
+    // tile = 2^tile_shift pixels; the tiles being replayed at any moment must fit the L2
+    u32 tile_shift = kMinTileShift;
+    if (const char* ts = std::getenv("MODLE_B200_TILE_SHIFT")) tile_shift = static_cast<u32>(std::atoi(ts));
+    tile_shift = std::min(26u, std::max(kMinTileShift, tile_shift));
+    while ((npx >> tile_shift) >= kMaxTiles) ++tile_shift;
+    k_bin_count<<<grid, threads, 0, stream>>>(d_bin1, d_bin2, n, static_cast<u32>(nrows),
+                                              tile_shift, counts, d_missed_updates);
+    k_bin_offsets<<<1, kBinThreads, 0, stream>>>(counts, cursor);
+    k_bin_scatter<<<static_cast<u32>(ctx->num_sms) * 2, kBinThreads, 0, stream>>>(
+        d_bin1, d_bin2, n, static_cast<u32>(nrows), tile_shift, cursor, d_binned);
+    {
+      // after k_bin_scatter cursor[t] is the END of tile t's run
+      int per_sm = 0;
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scatter_binned, threads, 0));
+      const u32 coop_grid = static_cast<u32>(ctx->num_sms) * static_cast<u32>(std::min(per_sm, 8));
+      const u32* c_binned = d_binned;
+      const u32* c_counts = counts;
+      const u32* c_end = cursor;
+      u32 ntiles = static_cast<u32>(((npx - 1) >> tile_shift) + 1);
+      void* args[] = {&c_binned, &c_counts, &c_end, &ntiles, &d_band, &arrivals};
+      CUDA_TRY(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_scatter_binned),
+                                           dim3(coop_grid), dim3(threads), args, 0, stream));
+    }
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(ctx->binned_done, stream));
     ctx->launches += 4;

@@ -4,6 +4,7 @@
 #pragma once
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -64,6 +65,7 @@ inline StagingConfig staging_large() {
   return StagingConfig{MODLE_B200_LARGE_THREADS, 256, 128, 256 * 128, 0};
 }
 inline StagingConfig staging_small() { return StagingConfig{256, 64, 128, 64 * 128, 1}; }
+inline StagingConfig staging_mid() { return StagingConfig{512, 128, 128, 128 * 128, 2}; }
 
 // Byte-indexed table of T^window (layout: see sim_core.hpp xs_jump): entry (k, v) is the XOR of
 // the matrix columns 8k+b over the set bits b of v.
@@ -193,7 +195,17 @@ inline StagingConfig pick_staging(u32 n_lefs, u32 n_bar) {
   const size_t bytes = cell_array_bytes(n_lefs, n_bar) + sizeof(CellShared);
   const StagingConfig s = staging_small();
   const u64 worst = worst_phase_draws(n_lefs);
-  if (bytes <= 100 * 1024 && worst <= s.window && u64(n_bar) + 64 <= s.window) return s;
+  // shared memory per CTA that still lets 3 / 2 CTAs share an SM (228 KB per SM, 1 KB reserved
+  // per CTA): 75 KB / 113 KB
+  static const int mid_mode = [] {
+    const char* e = std::getenv("MODLE_B200_MID");
+    return e ? std::atoi(e) : 1;
+  }();
+  const size_t small_limit = mid_mode ? size_t(75) * 1024 : size_t(100) * 1024;
+  if (bytes <= small_limit && worst <= s.window && u64(n_bar) + 64 <= s.window) return s;
+  const StagingConfig m = staging_mid();
+  if (mid_mode && bytes <= size_t(113) * 1024 && worst <= m.window && u64(n_bar) + 64 <= m.window)
+    return m;
   return staging_large();
 }
 

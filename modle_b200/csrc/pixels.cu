@@ -15,8 +15,8 @@
 // rows (one per lane while loading: every warp load is one 128-byte run), stages 32 x 256 tiles in
 // shared memory and compacts each row from there (ballot + popc, coalesced 24-byte records).
 //
-//   k_count_row_pixels   non-zeros per pixel row            reads 4 B/pixel
-//   k_scan_row_counts    exclusive scan -> row offsets      (ncols + 1 words)
+//   k_count_row_pixels   non-zeros per pixel row + their exclusive scan (decoupled look-back
+//                        over the CTAs) -> row offsets      reads 4 B/pixel, writes 8 B/row
 //   k_fill_pixels        writes the pixels                  reads 4 B/pixel, writes 24 B/non-zero
 #include <cuda_runtime.h>
 
@@ -45,12 +45,23 @@ __device__ __forceinline__ u32 load_pixel(const u32* __restrict__ band, u32 nrow
   return valid ? __ldg(band + (u64(c) * (u64(nrows) + 1) - r)) : 0u;
 }
 
+// Counts the non-zero pixels of 32 rows per CTA and turns the counts into row offsets in the same
+// pass: CTAs take their row block from a ticket (so a CTA only ever waits for CTAs that already
+// run) and chain their totals with a decoupled look-back -- flags[b] = status << 62 | value,
+// status 1 = this block's total, 2 = inclusive prefix up to and including this block.
+// `sync` = {ticket, flags[nblocks]} as 64-bit words, zeroed before the launch.
 __global__ void __launch_bounds__(kPxThreads)
     k_count_row_pixels(const u32* __restrict__ band, u32 nrows, u32 ncols,
-                       u64* __restrict__ row_counts) {
+                       u64* __restrict__ row_offsets, u64* __restrict__ sync) {
   __shared__ u32 part[kPxWarps][kPxRows];
+  __shared__ u32 s_block;
   const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const u32 r0 = blockIdx.x * kPxRows;
+  if (threadIdx.x == 0)
+    s_block = static_cast<u32>(atomicAdd(reinterpret_cast<unsigned long long*>(sync), 1ull));
+  __syncthreads();
+  const u32 block = s_block;
+  u64* flags = sync + 1;
+  const u32 r0 = block * kPxRows;
   const u32 r = r0 + lane;
   const u64 cend = min(u64(ncols), u64(r0) + kPxRows - 1 + nrows);
   u32 cnt = 0;
@@ -65,51 +76,40 @@ __global__ void __launch_bounds__(kPxThreads)
   for (; c < cend; c += kPxWarps) cnt += load_pixel(band, nrows, ncols, r, u32(c)) != 0;
   part[warp][lane] = cnt;
   __syncthreads();
-  if (warp == 0 && r < ncols) {
-    u32 s = 0;
+  if (warp != 0) return;
+  u32 mine = 0;
 #pragma unroll
-    for (int w = 0; w < kPxWarps; ++w) s += part[w][lane];
-    row_counts[r] = s;
-  }
-}
-
-// In-place exclusive scan of counts[0 .. n) with the total left in counts[n] (one CTA; n is the
-// number of pixel rows, at most a few hundred thousand).
-__global__ void __launch_bounds__(1024) k_scan_row_counts(u64* __restrict__ counts, u32 n) {
-  __shared__ u64 warp_sums[32];
-  __shared__ u64 carry;
-  const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const u32 chunk = (n + blockDim.x - 1) / blockDim.x;
-  const u32 lo = min(n, tid * chunk), hi = min(n, lo + chunk);
-  u64 s = 0;
-  for (u32 i = lo; i < hi; ++i) s += counts[i];
-  u64 incl = s;
+  for (int w = 0; w < kPxWarps; ++w) mine += part[w][lane];
+  u32 inc = mine;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
-    const u64 t = __shfl_up_sync(0xffffffffu, incl, d);
-    if (lane >= u32(d)) incl += t;
+    const u32 o = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= u32(d)) inc += o;
   }
-  if (lane == 31) warp_sums[warp] = incl;
-  __syncthreads();
-  if (warp == 0) {
-    const u64 w = warp_sums[lane];
-    u64 wi = w;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const u64 t = __shfl_up_sync(0xffffffffu, wi, d);
-      if (lane >= u32(d)) wi += t;
+  const u64 total = __shfl_sync(0xffffffffu, inc, 31);
+  u64 prefix = 0;
+  if (lane == 0) {
+    constexpr u64 kValue = (u64(1) << 62) - 1;
+    if (block != 0) {
+      asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(flags + block),
+                   "l"((u64(1) << 62) | total)
+                   : "memory");
+      for (u32 i = block; i-- > 0;) {
+        u64 f;
+        do {
+          asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(f) : "l"(flags + i) : "memory");
+        } while ((f >> 62) == 0);
+        prefix += f & kValue;
+        if ((f >> 62) == 2) break;
+      }
     }
-    warp_sums[lane] = wi - w;
-    if (lane == 31) carry = wi;
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(flags + block),
+                 "l"((u64(2) << 62) | (prefix + total))
+                 : "memory");
   }
-  __syncthreads();
-  u64 run = warp_sums[warp] + incl - s;
-  for (u32 i = lo; i < hi; ++i) {
-    const u64 v = counts[i];
-    counts[i] = run;
-    run += v;
-  }
-  if (tid == 0) counts[n] = carry;
+  prefix = __shfl_sync(0xffffffffu, prefix, 0);
+  if (r < ncols) row_offsets[r] = prefix + inc - mine;
+  if (lane == 31 && r0 + kPxRows >= ncols) row_offsets[ncols] = prefix + total;
 }
 
 __global__ void __launch_bounds__(kPxThreads)
@@ -187,11 +187,20 @@ int modle_b200_count_pixels_device(modle_b200_context* ctx, const uint32_t* d_ba
   CUDA_TRY(cudaSetDevice(ctx->device));
   cudaStream_t stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
   const u32 grid = static_cast<u32>((ncols + kPxRows - 1) / kPxRows);
+  // look-back scratch (ticket + one flag per CTA); a few of them so that calls issued on
+  // different streams of one context do not share one
+  DevBuf& sync = ctx->d_px_sync[ctx->px_calls++ % kPxSyncSlots];
+  const size_t sync_bytes = sizeof(u64) * (size_t(grid) + 1);
+  if (sync.cap < sync_bytes) {
+    CUDA_TRY(cudaStreamSynchronize(stream));  // the previous user of this slot may still run
+    CUDA_TRY(sync.reserve(std::max(sync_bytes, size_t(1) << 16)));
+  }
+  CUDA_TRY(cudaMemsetAsync(sync.p, 0, sync_bytes, stream));
   k_count_row_pixels<<<grid, kPxThreads, 0, stream>>>(d_band, static_cast<u32>(nrows),
-                                                      static_cast<u32>(ncols), d_row_offsets);
-  k_scan_row_counts<<<1, 1024, 0, stream>>>(d_row_offsets, static_cast<u32>(ncols));
+                                                      static_cast<u32>(ncols), d_row_offsets,
+                                                      static_cast<u64*>(sync.p));
   CUDA_TRY(cudaGetLastError());
-  ctx->launches += 2;
+  ++ctx->launches;
   return MODLE_B200_OK;
 }
 

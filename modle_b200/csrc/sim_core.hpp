@@ -1707,6 +1707,9 @@ struct CellSim {
           A.bar_active[i] = 0;
         }
       }
+    }
+    cta.sync();  // every thread has read `base` before the leader moves the stream position
+    MB_REGION(cta, tid) {
       if (cta.leader(tid)) S.rng_pos = base + P.n_bar;
     }
     cta.sync();
@@ -2418,9 +2421,14 @@ struct CellSim {
         A.fwd[i] = fwd;
         A.ep[i] = ep;
       }
-      if (cta.leader(tid) && draws) S.rng_pos = base + n;
     }
-    cta.sync();
+    cta.sync();  // every thread has read `base` before the leader moves the stream position
+    if (draws) {
+      MB_REGION(cta, tid) {
+        if (cta.leader(tid)) S.rng_pos = base + n;
+      }
+      cta.sync();
+    }
   }
 
   // ------------------------------------------------------------------------------ main loop

@@ -73,7 +73,7 @@ enum : int {
 };
 
 // number of RNG staging configurations (jump tables) a context keeps; see sim_core.hpp
-constexpr int kJumpSlots = 2;
+constexpr int kJumpSlots = 3;
 
 // Everything the kernel needs to know about the run; one per launch, in global memory.
 struct KernelParams {

@@ -81,6 +81,19 @@ def lib():
         L.modle_b200_band_to_pixels.argtypes = [
             C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64,
             u64p]
+        L.modle_b200_genome_import.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, P, C.c_int,
+                                               C.POINTER(C.c_void_p)]
+        L.modle_b200_genome_free.argtypes = [C.c_void_p]
+        L.modle_b200_genome_free.restype = None
+        L.modle_b200_genome_num_chromosomes.argtypes = [C.c_void_p]
+        L.modle_b200_genome_num_chromosomes.restype = C.c_size_t
+        L.modle_b200_genome_num_intervals.argtypes = [C.c_void_p]
+        L.modle_b200_genome_num_intervals.restype = C.c_size_t
+        L.modle_b200_genome_num_barriers.argtypes = [C.c_void_p]
+        L.modle_b200_genome_num_barriers.restype = C.c_uint64
+        L.modle_b200_genome_get_interval.argtypes = [
+            C.c_void_p, C.c_size_t, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), u64p, u64p, u64p,
+            C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), u64p]
         _LIB = L
     return _LIB
 
@@ -96,6 +109,9 @@ EXPORTED_SYMBOLS = [
     "modle_b200_synchronize", "modle_b200_snapshot_cell", "modle_b200_register_contacts_device",
     "modle_b200_kernel_launches", "modle_b200_phase_cycles",
     "modle_b200_count_pixels_device", "modle_b200_fill_pixels_device", "modle_b200_band_to_pixels",
+    "modle_b200_genome_import", "modle_b200_genome_free", "modle_b200_genome_num_chromosomes",
+    "modle_b200_genome_num_intervals", "modle_b200_genome_num_barriers",
+    "modle_b200_genome_get_interval",
 ]
 
 PHASE_NAMES = ["init", "burnin", "bind", "rank", "contacts", "moves_generate", "moves_adjust",
@@ -193,3 +209,36 @@ def barriers_from_records(records, p):
             stp_a, stp_i = p.barrier_occupied_stp, p.barrier_not_occupied_stp
         out[i] = (pos, stp_a, stp_i, abi.DIR_REV if strand == "+" else abi.DIR_FWD, 0)
     return out
+
+
+def import_genome(path_to_chrom_sizes, path_to_extr_barriers, p, path_to_genomic_intervals="",
+                  interpret_name_field_as_puu=False):
+    """Genome::Genome (src/libmodle/internal/genome.cpp:299-330) through the C ABI. Returns a list
+    of dicts: chrom_name, chrom_id, chrom_size, start, end, barriers (abi barrier dtype, sorted by
+    position), bin_offset. Raises ModleB200Error with the parser's diagnostic on malformed input."""
+    barrier_dt, _, _ = abi.np_dtypes()
+    L = lib()
+    g = C.c_void_p()
+    check(L.modle_b200_genome_import(
+        os.fsencode(path_to_chrom_sizes), os.fsencode(path_to_extr_barriers),
+        os.fsencode(path_to_genomic_intervals) if path_to_genomic_intervals else None,
+        C.byref(p), int(interpret_name_field_as_puu), C.byref(g)))
+    try:
+        out = []
+        for i in range(L.modle_b200_genome_num_intervals(g)):
+            name, cid, nb = C.c_char_p(), C.c_size_t(), C.c_size_t()
+            size, start, end, off = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+            bars = C.c_void_p()
+            check(L.modle_b200_genome_get_interval(
+                g, i, C.byref(name), C.byref(cid), C.byref(size), C.byref(start), C.byref(end),
+                C.byref(bars), C.byref(nb), C.byref(off)))
+            arr = np.zeros(nb.value, dtype=barrier_dt)
+            if nb.value:
+                C.memmove(arr.ctypes.data, bars.value, nb.value * barrier_dt.itemsize)
+            out.append(dict(chrom_name=name.value.decode(), chrom_id=int(cid.value),
+                            chrom_size=int(size.value), start=int(start.value), end=int(end.value),
+                            barriers=arr, bin_offset=int(off.value)))
+        assert sum(len(o["barriers"]) for o in out) == L.modle_b200_genome_num_barriers(g)
+        return out
+    finally:
+        L.modle_b200_genome_free(g)

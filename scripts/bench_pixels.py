@@ -51,7 +51,8 @@ def main():
         npx = nrows * ncols
         band = torch.zeros(npx + 1, dtype=torch.int32, device=dev)
         if kind == "dense":
-            band[:npx] = torch.randint(1, 1000, (npx,), device=dev, generator=g, dtype=torch.int32)
+            band[:npx] = torch.randint(1, 1000, (npx,), device=dev, generator=g,
+                                       dtype=torch.int32)
             # pixels the matrix cannot hold (distance > column) stay zero
             body = band[:npx].view(ncols, nrows)
             ii = torch.arange(nrows, device=dev)[None, :]
@@ -68,6 +69,7 @@ def main():
                 d = d.to(torch.int64).clamp_(0, nrows - 1)
                 b1 = (b2 - d).clamp_(min=0).to(torch.int32).contiguous()
                 b2 = b2.to(torch.int32).contiguous()
+                torch.cuda.synchronize()  # the context's stream does not wait for torch's
                 ctx.register_contacts_device(b1.data_ptr(), b2.data_ptr(), n, nrows, ncols,
                                              band.data_ptr(), missed.data_ptr(),
                                              torch.cuda.current_stream(dev).cuda_stream)

@@ -49,6 +49,11 @@ CASES = {
                         target_contact_density=0.005),
     "c1_chr20_shape": dict(size=64_444_167, ncells=6, nbar=1132, target_contact_density=0.002,
                            name="chr20"),
+    # two CTAs per SM (k_simulate_cells<512, 2>); chr8 is the smallest shape that needs <1024, 1>
+    "mid_chr13_shape": dict(size=114_364_328, ncells=3, nbar=943, target_contact_density=0.0008,
+                            name="chr13"),
+    "large_chr8_shape": dict(size=145_138_636, ncells=3, nbar=1772,
+                                 target_contact_density=0.0006, name="chr8"),
     "c3_chr1_shape": dict(size=248_956_422, ncells=3, nbar=3518, target_contact_density=0.0004,
                           name="chr1"),
 }
