@@ -42,6 +42,17 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+def ncu_traffic_per_lef_update():
+    """DRAM bytes (read + written) per LEF-update of k_simulate_cells from the committed
+    `ncu --set full` capture (profiles/ncu_traffic.json; one launch of the chr1 shape). The
+    bench scales it by the LEF-updates of an average launch."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        return float(d["k_simulate_cells"]["dram_bytes_per_lef_update"]), d["k_simulate_cells"]["source"]
+    except Exception:
+        return None, None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -306,6 +317,8 @@ def run_ours(args, rank, world, local_rank):
     # launches overlap (several streams), so the kernel's rate is taken over the timed region
     my_ms = t_start.elapsed_time(t_end)
     achieved = (alg_bytes * args.steps / 1e9) / (my_ms * 1e-3) if my_ms > 0 else 0.0
+    dram_per_lu, traffic_src = ncu_traffic_per_lef_update()
+    traffic = dram_per_lu * lef_updates / max(1, len(mine)) if dram_per_lu else None
 
     # ---- end to end through the public API (host buffers; copies inside the timed region) ------
     h2d = sum(e["ntasks"] * task_dt.itemsize + len(e["iv"].barriers) * barrier_dt.itemsize
@@ -365,7 +378,8 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_simulate_cells", "achieved": achieved,
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                         "frac": achieved / peak if peak else None, "traffic": None,
+                         "frac": achieved / peak if peak else None, "traffic": traffic,
+                         "traffic_source": traffic_src,
                          "avg_launch_ms": sum(launch_ms) / max(1, len(launch_ms)),
                          "algorithmic_bytes_per_step": int(alg_bytes),
                          "note": "cell state is shared-memory resident by design, so this kernel "

@@ -61,11 +61,34 @@ struct StagingConfig {
 #ifndef MODLE_B200_LARGE_THREADS
 #define MODLE_B200_LARGE_THREADS 1024
 #endif
-inline StagingConfig staging_large() {
-  return StagingConfig{MODLE_B200_LARGE_THREADS, 256, 128, 256 * 128, 0};
+// Draws per generator thread per window (l). The window sizes (and with them the jump matrices)
+// are fixed per configuration; a smaller l spreads a refill over more generator threads.
+inline u32 staging_per_thread() {
+  static const u32 l = [] {
+    const char* e = std::getenv("MODLE_B200_GEN_PER_THREAD");
+    const int v = e ? std::atoi(e) : 128;
+    return (v == 32 || v == 64 || v == 128) ? static_cast<u32>(v) : 128u;
+  }();
+  return l;
 }
-inline StagingConfig staging_small() { return StagingConfig{256, 64, 128, 64 * 128, 1}; }
-inline StagingConfig staging_mid() { return StagingConfig{512, 128, 128, 128 * 128, 2}; }
+// one jump table per window size: 32768 -> slot 0, 8192 -> slot 1, 16384 -> slot 2
+inline StagingConfig staging_with_window(u32 cta_threads, u32 window) {
+  const u32 l = staging_per_thread();
+  const u32 jump_slot = window == 32768 ? 0u : (window == 8192 ? 1u : 2u);
+  return StagingConfig{cta_threads, window / l, l, window, jump_slot};
+}
+inline StagingConfig staging_large() {
+  // MODLE_B200_LARGE_WINDOW=16384 halves the ring (it then stays L2 resident more easily); only
+  // valid while the worst phase of the interval still fits (prepare_interval checks)
+  static const u32 w = [] {
+    const char* e = std::getenv("MODLE_B200_LARGE_WINDOW");
+    const int v = e ? std::atoi(e) : 32768;
+    return v == 16384 ? 16384u : 32768u;
+  }();
+  return staging_with_window(MODLE_B200_LARGE_THREADS, w);
+}
+inline StagingConfig staging_small() { return staging_with_window(256, 8192); }
+inline StagingConfig staging_mid() { return staging_with_window(512, 16384); }
 
 // Byte-indexed table of T^window (layout: see sim_core.hpp xs_jump): entry (k, v) is the XOR of
 // the matrix columns 8k+b over the set bits b of v.

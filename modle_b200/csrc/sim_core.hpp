@@ -2311,59 +2311,81 @@ struct CellSim {
   MB_FN void fix_secondary_lef_lef_collisions() {
     const u32 n = S.num_active;
     const u32 k0 = S.n5 > 1 ? S.n5 : 1;
-    MB_REGION(cta, tid) {
-      for (u32 i = k0 + tid; i < n; i += cta.nt()) {
-        const u32 idx2 = A.rr[i];
-        if (!coll_avoided(A.rc[idx2], kEvSecondary)) continue;
-        const u32 idx1 = A.rr[i - 1];
-        const u32 pos1 = A.rev[idx1] - A.rm[idx1];
-        u32 mv2 = 0;
-        if (A.rev[idx2] > pos1 + 1) mv2 = A.rev[idx2] - (pos1 + 1);
-        const u32 c2 = coll_make(idx1, kEvCollision | kEvSecondary);
-        const u32 p1 = A.rev[idx1], p2 = A.rev[idx2];
-        A.rev[idx1] = A.fwd[idx1] < p2 ? A.fwd[idx1] : p2;
-        A.rev[idx2] = A.fwd[idx2] < p1 ? A.fwd[idx2] : p1;
-        // swap collisions, moves and rank slots
-        const u32 c1 = A.rc[idx1], m1 = A.rm[idx1];
-        A.rc[idx1] = c2;
-        A.rc[idx2] = c1;
-        A.rm[idx1] = mv2;
-        A.rm[idx2] = m1;
-        A.rr[i - 1] = static_cast<u16>(idx2);
-        A.rr[i] = static_cast<u16>(idx1);
-        const u32 cap1 = A.rev[idx1] - P.start, cap2 = A.rev[idx2] - P.start;
-        if (A.rm[idx1] > cap1) A.rm[idx1] = cap1;
-        if (A.rm[idx2] > cap2) A.rm[idx2] = cap2;
-      }
-    }
-    cta.sync();
     const u32 sat3 = S.n3 ? S.n3 - 1 : 0;
     const u32 naf = n - sat3;
-    MB_REGION(cta, tid) {
-      for (u32 i = tid; i + 1 < naf; i += cta.nt()) {
-        const u32 idx1 = A.fr[i];
-        if (!coll_avoided(A.fc[idx1], kEvSecondary)) continue;
-        const u32 idx2 = A.fr[i + 1];
-        const u32 pos2 = A.fwd[idx2] + A.fm[idx2];
-        u32 mv1 = 0;
-        if (pos2 > A.fwd[idx1] + 1) mv1 = pos2 - (A.fwd[idx1] + 1);
-        const u32 c1 = coll_make(idx2, kEvCollision | kEvSecondary);
-        const u32 p1 = A.fwd[idx1], p2 = A.fwd[idx2];
-        A.fwd[idx1] = A.rev[idx1] > p2 ? A.rev[idx1] : p2;
-        A.fwd[idx2] = A.rev[idx2] > p1 ? A.rev[idx2] : p1;
-        const u32 c2 = A.fc[idx2], m2 = A.fm[idx2];
-        A.fc[idx1] = c2;
-        A.fc[idx2] = c1;
-        A.fm[idx1] = m2;
-        A.fm[idx2] = mv1;
-        A.fr[i] = static_cast<u16>(idx2);
-        A.fr[i + 1] = static_cast<u16>(idx1);
-        const u32 cap1 = P.end - 1 - A.fwd[idx1], cap2 = P.end - 1 - A.fwd[idx2];
-        if (A.fm[idx1] > cap1) A.fm[idx1] = cap1;
-        if (A.fm[idx2] > cap2) A.fm[idx2] = cap2;
+    // Detection and application are separate regions: a swap rewrites rank slots and collision
+    // words that the neighbouring threads read while looking for their own markers. A thread
+    // remembers the markers of up to 64 of its strided ranks per round (one round on the device).
+    const u32 per_round = 64u * static_cast<u32>(cta.nt());
+    const u32 span = n > naf ? n : naf;
+    PerThread<u64> marks_r(cta.nt()), marks_f(cta.nt());
+    for (u32 base = 0; base < span; base += per_round) {
+      MB_REGION(cta, tid) {
+        u64 mr = 0, mf = 0;
+        u32 it = 0;
+        for (u32 i = base + k0 + tid; i < n && it < 64; i += cta.nt(), ++it)
+          if (coll_avoided(A.rc[A.rr[i]], kEvSecondary)) mr |= u64(1) << it;
+        it = 0;
+        for (u32 i = base + tid; i + 1 < naf && it < 64; i += cta.nt(), ++it)
+          if (coll_avoided(A.fc[A.fr[i]], kEvSecondary)) mf |= u64(1) << it;
+        marks_r[tid] = mr;
+        marks_f[tid] = mf;
       }
+      cta.sync();
+      MB_REGION(cta, tid) {
+        u64 mr = marks_r[tid];
+        for (u32 i = base + k0 + tid; mr != 0; i += cta.nt(), mr >>= 1) {
+          if (!(mr & 1)) continue;
+          const u32 idx2 = A.rr[i];
+          const u32 idx1 = A.rr[i - 1];
+          const u32 pos1 = A.rev[idx1] - A.rm[idx1];
+          u32 mv2 = 0;
+          if (A.rev[idx2] > pos1 + 1) mv2 = A.rev[idx2] - (pos1 + 1);
+          const u32 c2 = coll_make(idx1, kEvCollision | kEvSecondary);
+          const u32 p1 = A.rev[idx1], p2 = A.rev[idx2];
+          A.rev[idx1] = A.fwd[idx1] < p2 ? A.fwd[idx1] : p2;
+          A.rev[idx2] = A.fwd[idx2] < p1 ? A.fwd[idx2] : p1;
+          // swap collisions, moves and rank slots
+          const u32 c1 = A.rc[idx1], m1 = A.rm[idx1];
+          A.rc[idx1] = c2;
+          A.rc[idx2] = c1;
+          A.rm[idx1] = mv2;
+          A.rm[idx2] = m1;
+          A.rr[i - 1] = static_cast<u16>(idx2);
+          A.rr[i] = static_cast<u16>(idx1);
+          const u32 cap1 = A.rev[idx1] - P.start, cap2 = A.rev[idx2] - P.start;
+          if (A.rm[idx1] > cap1) A.rm[idx1] = cap1;
+          if (A.rm[idx2] > cap2) A.rm[idx2] = cap2;
+        }
+      }
+      cta.sync();  // the fwd pass reads rev positions the rev pass may just have rewritten
+      MB_REGION(cta, tid) {
+        u64 mf = marks_f[tid];
+        for (u32 i = base + tid; mf != 0; i += cta.nt(), mf >>= 1) {
+          if (!(mf & 1)) continue;
+          const u32 idx1 = A.fr[i];
+          const u32 idx2 = A.fr[i + 1];
+          const u32 pos2 = A.fwd[idx2] + A.fm[idx2];
+          u32 mv1 = 0;
+          if (pos2 > A.fwd[idx1] + 1) mv1 = pos2 - (A.fwd[idx1] + 1);
+          const u32 c1 = coll_make(idx2, kEvCollision | kEvSecondary);
+          const u32 p1 = A.fwd[idx1], p2 = A.fwd[idx2];
+          A.fwd[idx1] = A.rev[idx1] > p2 ? A.rev[idx1] : p2;
+          A.fwd[idx2] = A.rev[idx2] > p1 ? A.rev[idx2] : p1;
+          const u32 c2 = A.fc[idx2], m2 = A.fm[idx2];
+          A.fc[idx1] = c2;
+          A.fc[idx2] = c1;
+          A.fm[idx1] = m2;
+          A.fm[idx2] = mv1;
+          A.fr[i] = static_cast<u16>(idx2);
+          A.fr[i + 1] = static_cast<u16>(idx1);
+          const u32 cap1 = P.end - 1 - A.fwd[idx1], cap2 = P.end - 1 - A.fwd[idx2];
+          if (A.fm[idx1] > cap1) A.fm[idx1] = cap1;
+          if (A.fm[idx2] > cap2) A.fm[idx2] = cap2;
+        }
+      }
+      cta.sync();
     }
-    cta.sync();
   }
 
   // Simulation::process_collisions (simulation.cpp:763-793)
