@@ -125,6 +125,11 @@ def build_workload(name, cells):
         cfg, genome = workloads.config_c2(cells or 512)
         desc = "C2 GRCh38 genome-wide shape (24 chromosomes, 38,815 synthetic barriers), " \
                "%d cells, 5 kb bins, default parameters"
+    chroms = os.environ.get("MODLE_B200_BENCH_CHROMS")  # diagnostics: restrict the genome
+    if chroms:
+        keep = set(chroms.split(","))
+        genome = [g for g in genome if g[0] in keep]
+        desc += " [only " + chroms + "]"
     return cfg, genome, desc % int(cfg.num_cells)
 
 

@@ -251,6 +251,42 @@ int modle_b200_simulate_interval_device(modle_b200_context* ctx,
                                         void* cuda_stream);
 int modle_b200_synchronize(modle_b200_context* ctx);
 
+/* ---- internal-state log (Config::log_model_internal_state) --------------------------------------
+ * One record per simulated epoch of a cell: the quantities Simulation::dump_stats
+ * (src/libmodle/cpu/simulation.cpp:995-1056) writes, taken where the reference takes them (after
+ * extrude, before release_lefs, :968-974). The text columns it adds (task id, cell id, chromosome,
+ * start, end) are known to the caller; effective_barrier_occupancy = barriers_occupied /
+ * num_barriers and avg_loop_size = loop_size_sum / num_lefs (the integer sum is exact in double,
+ * so the reference's left-to-right double accumulation gives the same value).                   */
+typedef struct modle_b200_epoch_record {
+  uint64_t epoch;
+  uint64_t loop_size_sum;
+  uint32_t burnin; /* 1 while the cell is in its burn-in phase */
+  uint32_t num_lefs; /* active LEFs (lefs.size() in dump_stats) */
+  uint32_t barriers_occupied;
+  uint32_t lefs_stalled_rev;
+  uint32_t lefs_stalled_fwd;
+  uint32_t lefs_stalled_both;
+  uint32_t lef_bar_collisions;
+  uint32_t lef_lef_primary_collisions;
+  uint32_t lef_lef_secondary_collisions;
+  uint32_t reserved_;
+} modle_b200_epoch_record;
+
+/* modle_b200_simulate_interval plus the log: cell k's record of epoch e goes to
+ * log_out[k * log_capacity_per_cell + e] for e < log_capacity_per_cell (later epochs are not
+ * logged; stats_out[k].num_epochs says how many there were). HOST buffers.                     */
+int modle_b200_simulate_interval_logged(modle_b200_context* ctx,
+                                        const modle_b200_sim_params* params,
+                                        const modle_b200_interval* interval,
+                                        const modle_b200_barrier* barriers, size_t num_barriers,
+                                        const modle_b200_cell_task* tasks, size_t num_cells,
+                                        uint32_t* band_out, uint64_t* occ1d_out,
+                                        modle_b200_cell_stats* stats_out,
+                                        uint64_t* missed_updates_out,
+                                        modle_b200_epoch_record* log_out,
+                                        size_t log_capacity_per_cell);
+
 /* Runs one cell for params->debug_max_epochs epochs and returns its state (parity bisection). */
 int modle_b200_snapshot_cell(modle_b200_context* ctx, const modle_b200_sim_params* params,
                              const modle_b200_interval* interval,
@@ -297,6 +333,16 @@ int modle_b200_fill_pixels_device(modle_b200_context* ctx, const uint32_t* d_ban
 int modle_b200_band_to_pixels(modle_b200_context* ctx, const uint32_t* band, uint64_t nrows,
                               uint64_t ncols, uint64_t bin_offset, modle_b200_pixel* pixels_out,
                               uint64_t capacity, uint64_t* num_pixels_out);
+
+/* ---- 1D LEF occupancy profile: what write_lef_occupancy_to_bwig hands to the bigWig writer ------
+ * (src/libmodle/cpu/simulation.cpp:170-197): profile[i] = float(double(occ[i]) / double(max occ)).
+ * An all-zero track yields NaN (0/0), as in the reference. Device variant: d_scratch_max is one
+ * uint64 of scratch; asynchronous on `cuda_stream`.                                             */
+int modle_b200_lef_occupancy_profile_device(modle_b200_context* ctx, const uint64_t* d_occ1d,
+                                            size_t n, float* d_profile, uint64_t* d_scratch_max,
+                                            void* cuda_stream);
+int modle_b200_lef_occupancy_profile(modle_b200_context* ctx, const uint64_t* occ1d, size_t n,
+                                     float* profile_out);
 
 /* Profiling aid (the reference has none; --skip-output + perf is its recipe, cli.cpp:182-186):
  * SM-clock cycles the simulate kernel spent in each phase of the per-cell loop, summed over all

@@ -129,6 +129,19 @@ class Pixel(C.Structure):
     ]
 
 
+def epoch_record_dtype():
+    """modle_b200_epoch_record (the quantities Simulation::dump_stats logs per epoch)."""
+    import numpy as np
+
+    dt = np.dtype([("epoch", "<u8"), ("loop_size_sum", "<u8"), ("burnin", "<u4"),
+                   ("num_lefs", "<u4"), ("barriers_occupied", "<u4"), ("lefs_stalled_rev", "<u4"),
+                   ("lefs_stalled_fwd", "<u4"), ("lefs_stalled_both", "<u4"),
+                   ("lef_bar_collisions", "<u4"), ("lef_lef_primary_collisions", "<u4"),
+                   ("lef_lef_secondary_collisions", "<u4"), ("reserved_", "<u4")])
+    assert dt.itemsize == 56
+    return dt
+
+
 def pixel_dtype():
     import numpy as np
 

@@ -66,7 +66,7 @@ struct LaunchSlot {
   cudaEvent_t done = nullptr;
   bool in_flight = false;
 };
-constexpr int kLaunchSlots = 4;
+constexpr int kLaunchSlots = 16;
 constexpr int kPxSyncSlots = 8;
 
 struct modle_b200_context {
@@ -80,7 +80,7 @@ struct modle_b200_context {
   DevBuf d_phase;  // kNumPhases cycle accumulators
   LaunchSlot slots[kLaunchSlots];
   int next_slot = 0;
-  DevBuf d_tasks, d_band, d_occ1d, d_stats, d_missed, d_snap_u64, d_snap_bar;
+  DevBuf d_tasks, d_band, d_occ1d, d_stats, d_missed, d_snap_u64, d_snap_bar, d_log;
   PinnedBuf h_stage;  // band | occ1d | stats | missed of the host-buffer entry point
   DevBuf d_binned, d_tiles;  // binned contact register: pixel indices by tile, counts + cursors
   cudaEvent_t binned_done = nullptr;

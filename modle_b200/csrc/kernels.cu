@@ -76,7 +76,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks)
     for (int i = 0; i < 4; ++i) td.rng_state[i] = t.rng_state[i];
     if (has_work) {
       Cta cta{&S.scratch};
-      CellSim sim{a.kp, a.D, A, S, a.K, cta, td};
+      Sinks K = a.K;
+      if (K.log) K.log += size_t(cell) * K.log_cap;
+      CellSim sim{a.kp, a.D, A, S, K, cta, td};
       sim.run();
     }
     __syncthreads();
@@ -423,7 +425,8 @@ int launch_simulate(modle_b200_context* ctx, const modle_b200_sim_params* params
                     const modle_b200_interval* interval, const modle_b200_barrier* h_barriers,
                     size_t num_barriers, const modle_b200_cell_task* d_tasks, size_t num_cells,
                     u32* d_band, u64* d_occ1d, modle_b200_cell_stats* d_stats, u64* d_missed,
-                    cudaStream_t stream, u64* d_snap_u64, u8* d_snap_bar) {
+                    cudaStream_t stream, u64* d_snap_u64, u8* d_snap_bar,
+                    modle_b200_epoch_record* d_log = nullptr, u32 log_cap = 0) {
   const StagingConfig sc =
       pick_staging(static_cast<u32>(interval->num_lefs), static_cast<u32>(num_barriers));
   KernelParams kp;
@@ -517,6 +520,8 @@ int launch_simulate(modle_b200_context* ctx, const modle_b200_sim_params* params
   a.K.band = d_band;
   a.K.occ1d = kp.track_1d ? d_occ1d : nullptr;
   a.K.missed = d_missed;
+  a.K.log = d_log;
+  a.K.log_cap = log_cap;
   a.tasks = d_tasks;
   a.stats = d_stats;
   a.num_cells = static_cast<u32>(num_cells);
@@ -567,14 +572,18 @@ int modle_b200_simulate_interval_device(modle_b200_context* ctx,
                          d_occ1d, d_stats, d_missed_updates, stream, nullptr, nullptr);
 }
 
-int modle_b200_simulate_interval(modle_b200_context* ctx, const modle_b200_sim_params* params,
-                                 const modle_b200_interval* interval,
-                                 const modle_b200_barrier* barriers, size_t num_barriers,
-                                 const modle_b200_cell_task* tasks, size_t num_cells,
-                                 uint32_t* band_out, uint64_t* occ1d_out,
-                                 modle_b200_cell_stats* stats_out, uint64_t* missed_updates_out) {
+static int simulate_interval_host(modle_b200_context* ctx, const modle_b200_sim_params* params,
+                                  const modle_b200_interval* interval,
+                                  const modle_b200_barrier* barriers, size_t num_barriers,
+                                  const modle_b200_cell_task* tasks, size_t num_cells,
+                                  uint32_t* band_out, uint64_t* occ1d_out,
+                                  modle_b200_cell_stats* stats_out, uint64_t* missed_updates_out,
+                                  modle_b200_epoch_record* log_out, size_t log_cap) {
   if (!ctx || !params || !interval || !tasks || !band_out)
     return fail(MODLE_B200_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (log_cap != 0 && !log_out) return fail(MODLE_B200_ERR_INVALID_ARGUMENT, "log_out is NULL");
+  if (log_cap > 0xFFFFFFFFull)
+    return fail(MODLE_B200_ERR_INVALID_ARGUMENT, "log_capacity_per_cell too large");
   if (num_barriers && !barriers) return fail(MODLE_B200_ERR_INVALID_ARGUMENT, "barriers is NULL");
   CUDA_TRY(cudaSetDevice(ctx->device));
   u64 nrows = 0, ncols = 0;
@@ -593,13 +602,21 @@ int modle_b200_simulate_interval(modle_b200_context* ctx, const modle_b200_sim_p
   CUDA_TRY(cudaMemsetAsync(ctx->d_stats.p, 0,
                            sizeof(modle_b200_cell_stats) * std::max<size_t>(num_cells, 1), s));
   CUDA_TRY(cudaMemsetAsync(ctx->d_missed.p, 0, sizeof(u64), s));
+  const size_t log_bytes = sizeof(modle_b200_epoch_record) * log_cap * num_cells;
+  if (log_bytes) {
+    CUDA_TRY(ctx->d_log.reserve(log_bytes));
+    CUDA_TRY(cudaMemsetAsync(ctx->d_log.p, 0, log_bytes, s));
+  }
   const int rc = launch_simulate(
       ctx, params, interval, barriers, num_barriers,
       static_cast<const modle_b200_cell_task*>(ctx->d_tasks.p), num_cells,
       static_cast<u32*>(ctx->d_band.p), static_cast<u64*>(ctx->d_occ1d.p),
       static_cast<modle_b200_cell_stats*>(ctx->d_stats.p), static_cast<u64*>(ctx->d_missed.p), s,
-      nullptr, nullptr);
+      nullptr, nullptr, log_bytes ? static_cast<modle_b200_epoch_record*>(ctx->d_log.p) : nullptr,
+      static_cast<u32>(log_cap));
   if (rc != MODLE_B200_OK) return rc;
+  if (log_bytes)
+    CUDA_TRY(cudaMemcpyAsync(log_out, ctx->d_log.p, log_bytes, cudaMemcpyDeviceToHost, s));
   // results are ADDED to the caller's buffers (the reference accumulates into a shared matrix)
   const size_t off_occ = ((sizeof(u32) * npx + 63) / 64) * 64;
   const size_t off_stats = off_occ + ((sizeof(u64) * ncols + 63) / 64) * 64;
@@ -631,6 +648,31 @@ int modle_b200_simulate_interval(modle_b200_context* ctx, const modle_b200_sim_p
     return fail(MODLE_B200_ERR_DEVICE_FAULT,
                 "kernel reported fault code " + std::to_string(first_fault));
   return MODLE_B200_OK;
+}
+
+int modle_b200_simulate_interval(modle_b200_context* ctx, const modle_b200_sim_params* params,
+                                 const modle_b200_interval* interval,
+                                 const modle_b200_barrier* barriers, size_t num_barriers,
+                                 const modle_b200_cell_task* tasks, size_t num_cells,
+                                 uint32_t* band_out, uint64_t* occ1d_out,
+                                 modle_b200_cell_stats* stats_out, uint64_t* missed_updates_out) {
+  return simulate_interval_host(ctx, params, interval, barriers, num_barriers, tasks, num_cells,
+                                band_out, occ1d_out, stats_out, missed_updates_out, nullptr, 0);
+}
+
+int modle_b200_simulate_interval_logged(modle_b200_context* ctx,
+                                        const modle_b200_sim_params* params,
+                                        const modle_b200_interval* interval,
+                                        const modle_b200_barrier* barriers, size_t num_barriers,
+                                        const modle_b200_cell_task* tasks, size_t num_cells,
+                                        uint32_t* band_out, uint64_t* occ1d_out,
+                                        modle_b200_cell_stats* stats_out,
+                                        uint64_t* missed_updates_out,
+                                        modle_b200_epoch_record* log_out,
+                                        size_t log_capacity_per_cell) {
+  return simulate_interval_host(ctx, params, interval, barriers, num_barriers, tasks, num_cells,
+                                band_out, occ1d_out, stats_out, missed_updates_out, log_out,
+                                log_capacity_per_cell);
 }
 
 int modle_b200_snapshot_cell(modle_b200_context* ctx, const modle_b200_sim_params* params,

@@ -78,14 +78,20 @@ inline StagingConfig staging_with_window(u32 cta_threads, u32 window) {
   return StagingConfig{cta_threads, window / l, l, window, jump_slot};
 }
 inline StagingConfig staging_large() {
-  // MODLE_B200_LARGE_WINDOW=16384 halves the ring (it then stays L2 resident more easily); only
-  // valid while the worst phase of the interval still fits (prepare_interval checks)
+  // 16384 draws per window: the rings of all resident CTAs (2 windows each) then stay L2
+  // resident -- with 32768 every staged draw was written back to DRAM (19.4 GB instead of 2.4 GB
+  // for one chr1 launch, profiles/r01i_*), at the same speed. MODLE_B200_LARGE_WINDOW=32768
+  // restores the larger window (needed only above ~7,000 LEFs per cell, which does not fit the
+  // shared memory anyway).
   static const u32 w = [] {
     const char* e = std::getenv("MODLE_B200_LARGE_WINDOW");
-    const int v = e ? std::atoi(e) : 32768;
-    return v == 16384 ? 16384u : 32768u;
+    const int v = e ? std::atoi(e) : 16384;
+    return v == 32768 ? 32768u : 16384u;
   }();
   return staging_with_window(MODLE_B200_LARGE_THREADS, w);
+}
+inline StagingConfig staging_large_wide() {
+  return staging_with_window(MODLE_B200_LARGE_THREADS, 32768);
 }
 inline StagingConfig staging_small() { return staging_with_window(256, 8192); }
 inline StagingConfig staging_mid() { return staging_with_window(512, 16384); }
@@ -229,7 +235,9 @@ inline StagingConfig pick_staging(u32 n_lefs, u32 n_bar) {
   const StagingConfig m = staging_mid();
   if (mid_mode && bytes <= size_t(113) * 1024 && worst <= m.window && u64(n_bar) + 64 <= m.window)
     return m;
-  return staging_large();
+  const StagingConfig l = staging_large();
+  if (worst <= l.window && u64(n_bar) + 64 <= l.window) return l;
+  return staging_large_wide();  // e.g. more than 16k barriers in one interval
 }
 
 }  // namespace modle_b200

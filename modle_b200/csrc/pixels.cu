@@ -163,6 +163,30 @@ __global__ void __launch_bounds__(kPxThreads)
   }
 }
 
+// ---- 1D LEF occupancy profile -----------------------------------------------------------------
+// write_lef_occupancy_to_bwig (src/libmodle/cpu/simulation.cpp:170-197) before the bigWig call:
+// profile[i] = float(double(occ[i]) / double(max(occ))). An all-zero track gives 0/0 = NaN, as in
+// the reference.
+__global__ void __launch_bounds__(256) k_occ_max(const u64* __restrict__ occ, size_t n,
+                                                 u64* __restrict__ out_max) {
+  u64 m = 0;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += size_t(gridDim.x) * blockDim.x)
+    m = max(m, occ[i]);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(reinterpret_cast<unsigned long long*>(out_max), m);
+}
+
+__global__ void __launch_bounds__(256) k_occ_profile(const u64* __restrict__ occ, size_t n,
+                                                     const u64* __restrict__ max_v,
+                                                     float* __restrict__ out) {
+  const double denom = static_cast<double>(*max_v);
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += size_t(gridDim.x) * blockDim.x)
+    out[i] = static_cast<float>(static_cast<double>(occ[i]) / denom);
+}
+
 }  // namespace modle_b200
 
 namespace {
@@ -260,6 +284,42 @@ int modle_b200_band_to_pixels(modle_b200_context* ctx, const uint32_t* band, uin
     return rc;
   CUDA_TRY(cudaMemcpyAsync(pixels_out, d_px, sizeof(modle_b200_pixel) * nnz,
                            cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return MODLE_B200_OK;
+}
+
+int modle_b200_lef_occupancy_profile_device(modle_b200_context* ctx, const uint64_t* d_occ1d,
+                                            size_t n, float* d_profile, uint64_t* d_scratch_max,
+                                            void* cuda_stream) {
+  if (!ctx || !d_occ1d || !d_profile || !d_scratch_max)
+    return fail(MODLE_B200_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (n == 0) return MODLE_B200_OK;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  cudaStream_t stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
+  const u32 grid = static_cast<u32>(std::min<size_t>((n + 255) / 256, size_t(ctx->num_sms) * 8));
+  CUDA_TRY(cudaMemsetAsync(d_scratch_max, 0, sizeof(u64), stream));
+  k_occ_max<<<grid, 256, 0, stream>>>(d_occ1d, n, d_scratch_max);
+  k_occ_profile<<<grid, 256, 0, stream>>>(d_occ1d, n, d_scratch_max, d_profile);
+  CUDA_TRY(cudaGetLastError());
+  ctx->launches += 2;
+  return MODLE_B200_OK;
+}
+
+int modle_b200_lef_occupancy_profile(modle_b200_context* ctx, const uint64_t* occ1d, size_t n,
+                                     float* profile_out) {
+  if (!ctx || !occ1d || !profile_out) return fail(MODLE_B200_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (n == 0) return MODLE_B200_OK;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx->d_px_rows.reserve(sizeof(u64) * (n + 1)));
+  CUDA_TRY(ctx->d_px_out.reserve(sizeof(float) * n));
+  u64* d_occ = static_cast<u64*>(ctx->d_px_rows.p);
+  float* d_out = static_cast<float*>(ctx->d_px_out.p);
+  CUDA_TRY(cudaMemcpyAsync(d_occ, occ1d, sizeof(u64) * n, cudaMemcpyHostToDevice, ctx->stream));
+  if (const int rc = modle_b200_lef_occupancy_profile_device(ctx, d_occ, n, d_out, d_occ + n,
+                                                             ctx->stream))
+    return rc;
+  CUDA_TRY(cudaMemcpyAsync(profile_out, d_out, sizeof(float) * n, cudaMemcpyDeviceToHost,
+                           ctx->stream));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   return MODLE_B200_OK;
 }

@@ -2453,6 +2453,57 @@ struct CellSim {
     }
   }
 
+  // Simulation::dump_stats (simulation.cpp:995-1056), called where the reference calls it: after
+  // extrude, before release_lefs (:968-974). Runs before extrude_and_release here, so the loop
+  // sizes are taken from the positions the units are about to reach.
+  MB_FN void log_epoch_state() {
+    if (K.log == nullptr || S.epoch >= K.log_cap) return;
+    const u32 n = S.num_active;
+    PerThread<u64> a(cta.nt()), b(cta.nt()), c(cta.nt()), d(cta.nt());
+    MB_REGION(cta, tid) {
+      u64 st_rev = 0, st_fwd = 0, st_both = 0, bar = 0, prim = 0, sec = 0, loops = 0, occ = 0;
+      for (u32 i = tid; i < n; i += cta.nt()) {
+        const u32 rc = A.rc[i], fc = A.fc[i];
+        const bool r = coll_occurred(rc), f = coll_occurred(fc);
+        st_rev += r;
+        st_fwd += f;
+        st_both += r && f;
+        bar += coll_is(rc, kEvLefBar) + coll_is(fc, kEvLefBar);
+        prim += coll_is(rc, kEvPrimary) + coll_is(fc, kEvPrimary);
+        sec += coll_is(rc, kEvSecondary) + coll_is(fc, kEvSecondary);
+        if (A.rev[i] != kUnbound) loops += u64(A.fwd[i] + A.fm[i]) - u64(A.rev[i] - A.rm[i]);
+      }
+      for (u32 i = tid; i < P.n_bar; i += cta.nt()) occ += A.bar_active[i] != 0;
+      a[tid] = st_rev | (st_fwd << 21) | (st_both << 42);
+      b[tid] = bar | (prim << 21) | (sec << 42);
+      c[tid] = occ;
+      d[tid] = loops;
+    }
+    const u64 ta = cta.reduce_sum(a);
+    const u64 tb = cta.reduce_sum(b);
+    const u64 tc = cta.reduce_sum(c);
+    const u64 td = cta.reduce_sum(d);
+    MB_REGION(cta, tid) {
+      if (cta.leader(tid)) {
+        modle_b200_epoch_record rec;
+        rec.epoch = S.epoch;
+        rec.loop_size_sum = td;
+        rec.burnin = S.burnin_completed ? 0u : 1u;
+        rec.num_lefs = n;
+        rec.barriers_occupied = static_cast<u32>(tc);
+        rec.lefs_stalled_rev = static_cast<u32>(ta & 0x1FFFFFu);
+        rec.lefs_stalled_fwd = static_cast<u32>((ta >> 21) & 0x1FFFFFu);
+        rec.lefs_stalled_both = static_cast<u32>(ta >> 42);
+        rec.lef_bar_collisions = static_cast<u32>(tb & 0x1FFFFFu);
+        rec.lef_lef_primary_collisions = static_cast<u32>((tb >> 21) & 0x1FFFFFu);
+        rec.lef_lef_secondary_collisions = static_cast<u32>(tb >> 42);
+        rec.reserved_ = 0;
+        K.log[S.epoch] = rec;
+      }
+    }
+    cta.sync();
+  }
+
   // ------------------------------------------------------------------------------ main loop
   // Simulation::simulate_one_cell (simulation.cpp:896-986)
   MB_FN void run() {
@@ -2487,6 +2538,7 @@ struct CellSim {
       next_barrier_states();
       lap(kPhBarriers);
       process_collisions(true);
+      log_epoch_state();
       extrude_and_release();
       lap(kPhExtrudeRelease);
       MB_REGION(cta, tid) {

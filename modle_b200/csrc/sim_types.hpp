@@ -3,6 +3,7 @@
 // 248,956,422 bp); the all-ones value is the reference's "unbound" sentinel
 // (src/libmodle/internal/extrusion_factors_impl.hpp:96-98,120-124).
 #pragma once
+#include "../../include/modle_b200.h"
 #include "cta.hpp"
 
 namespace modle_b200 {
@@ -131,6 +132,8 @@ struct Sinks {
   u32* band;    // nrows*ncols+1
   u64* occ1d;   // ncols or null
   u64* missed;  // 1
+  modle_b200_epoch_record* log;  // this cell's internal-state log (log_cap records) or null
+  u32 log_cap;
 };
 
 // Small per-cell state that lives in shared memory next to the arrays.

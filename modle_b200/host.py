@@ -64,6 +64,9 @@ def lib():
         L.modle_b200_simulate_interval.argtypes = [
             C.c_void_p, P, C.POINTER(abi.Interval), C.c_void_p, C.c_size_t, C.c_void_p,
             C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, u64p]
+        L.modle_b200_simulate_interval_logged.argtypes = [
+            C.c_void_p, P, C.POINTER(abi.Interval), C.c_void_p, C.c_size_t, C.c_void_p,
+            C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, u64p, C.c_void_p, C.c_size_t]
         L.modle_b200_simulate_interval_device.argtypes = [
             C.c_void_p, P, C.POINTER(abi.Interval), C.c_void_p, C.c_size_t, C.c_void_p,
             C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -81,6 +84,10 @@ def lib():
         L.modle_b200_band_to_pixels.argtypes = [
             C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64,
             u64p]
+        L.modle_b200_lef_occupancy_profile_device.argtypes = [
+            C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.modle_b200_lef_occupancy_profile.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t,
+                                                       C.c_void_p]
         L.modle_b200_genome_import.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, P, C.c_int,
                                                C.POINTER(C.c_void_p)]
         L.modle_b200_genome_free.argtypes = [C.c_void_p]
@@ -105,10 +112,12 @@ EXPORTED_SYMBOLS = [
     "modle_b200_rng_seed", "modle_b200_rng_next", "modle_b200_rng_jump",
     "modle_b200_stp_active_from_occupancy", "modle_b200_occupancy_from_stp",
     "modle_b200_make_cell_tasks", "modle_b200_init", "modle_b200_destroy",
-    "modle_b200_simulate_interval", "modle_b200_simulate_interval_device",
+    "modle_b200_simulate_interval", "modle_b200_simulate_interval_logged",
+    "modle_b200_simulate_interval_device",
     "modle_b200_synchronize", "modle_b200_snapshot_cell", "modle_b200_register_contacts_device",
     "modle_b200_kernel_launches", "modle_b200_phase_cycles",
     "modle_b200_count_pixels_device", "modle_b200_fill_pixels_device", "modle_b200_band_to_pixels",
+    "modle_b200_lef_occupancy_profile_device", "modle_b200_lef_occupancy_profile",
     "modle_b200_genome_import", "modle_b200_genome_free", "modle_b200_genome_num_chromosomes",
     "modle_b200_genome_num_intervals", "modle_b200_genome_num_barriers",
     "modle_b200_genome_get_interval",

@@ -115,7 +115,10 @@ class Context:
         return int(host.lib().modle_b200_kernel_launches(self._h))
 
     # -- HOST buffers in, HOST buffers out (the reference-facing call) -----------------------
-    def simulate_interval(self, params, interval, barriers, tasks, band=None, occ1d=None):
+    def simulate_interval(self, params, interval, barriers, tasks, band=None, occ1d=None,
+                          log_capacity_per_cell=0):
+        """With log_capacity_per_cell > 0 the internal-state log (Simulation::dump_stats,
+        simulation.cpp:995-1056) is returned as a fifth element: records[cell][epoch]."""
         _, _, stats_dt = abi.np_dtypes()
         nrows, ncols = host.band_shape(params, int(interval.end - interval.start))
         if band is None:
@@ -126,6 +129,15 @@ class Context:
         missed = C.c_uint64(0)
         barriers = np.ascontiguousarray(barriers)
         tasks = np.ascontiguousarray(tasks)
+        if log_capacity_per_cell:
+            log = np.zeros((len(tasks), int(log_capacity_per_cell)), dtype=abi.epoch_record_dtype())
+            rc = host.lib().modle_b200_simulate_interval_logged(
+                self._h, C.byref(params), C.byref(interval),
+                barriers.ctypes.data if len(barriers) else None, len(barriers), tasks.ctypes.data,
+                len(tasks), band.ctypes.data, occ1d.ctypes.data, stats.ctypes.data,
+                C.byref(missed), log.ctypes.data, int(log_capacity_per_cell))
+            host.check(rc)
+            return band, occ1d, stats, int(missed.value), log
         rc = host.lib().modle_b200_simulate_interval(
             self._h, C.byref(params), C.byref(interval),
             barriers.ctypes.data if len(barriers) else None, len(barriers), tasks.ctypes.data,
@@ -181,6 +193,14 @@ class Context:
             self._h, C.c_void_p(d_band), nrows, ncols, bin_offset, C.c_void_p(d_row_offsets),
             C.c_void_p(d_pixels) if d_pixels else None, capacity,
             C.c_void_p(stream) if stream else None))
+
+    def lef_occupancy_profile(self, occ1d):
+        """write_lef_occupancy_to_bwig's normalisation (simulation.cpp:170-197) on the GPU."""
+        occ1d = np.ascontiguousarray(occ1d, dtype=np.uint64)
+        out = np.zeros(len(occ1d), dtype=np.float32)
+        host.check(host.lib().modle_b200_lef_occupancy_profile(
+            self._h, occ1d.ctypes.data, len(occ1d), out.ctypes.data))
+        return out
 
     def snapshot_cell(self, params, interval, barriers, task):
         n = int(interval.num_lefs)

@@ -261,12 +261,14 @@ void oracle_collision_steps(u32 steps, u64 start, u64 end, std::size_t n, u64* r
 // CPU counterpart of modle_b200_simulate_interval: `nthreads` worker threads pop cells from a
 // shared counter (one cell per task, as the reference's workers do) and add into the shared band
 // with atomic increments. Returns 0.
-int oracle_simulate_interval(const modle_b200_sim_params* params,
-                             const modle_b200_interval* interval,
-                             const modle_b200_barrier* barriers, std::size_t num_barriers,
-                             const modle_b200_cell_task* tasks, std::size_t num_cells,
-                             u32* band_out, u64* occ1d_out, modle_b200_cell_stats* stats_out,
-                             u64* missed_updates_out, int nthreads) {
+int oracle_simulate_interval_logged(const modle_b200_sim_params* params,
+                                    const modle_b200_interval* interval,
+                                    const modle_b200_barrier* barriers, std::size_t num_barriers,
+                                    const modle_b200_cell_task* tasks, std::size_t num_cells,
+                                    u32* band_out, u64* occ1d_out,
+                                    modle_b200_cell_stats* stats_out, u64* missed_updates_out,
+                                    int nthreads, modle_b200_epoch_record* log_out,
+                                    std::size_t log_cap) {
   const Params p = to_params(*params, interval->num_lefs);
   const Barriers B = to_barriers(barriers, num_barriers);
   const Interval iv{interval->start, interval->end};
@@ -287,6 +289,7 @@ int oracle_simulate_interval(const modle_b200_sim_params* params,
       const bool epochs_mode = p.stop_on_epochs != 0;
       if (epochs_mode || tasks[c].num_target_contacts != 0) {
         CellSim sim(p, iv, B, interval->num_lefs, to_task(tasks[c]), sink);
+        if (log_out && log_cap) sim.set_log(log_out + c * log_cap, log_cap);
         fill_stats(st, sim.run());
       }
       if (stats_out) stats_out[c] = st;
@@ -297,6 +300,17 @@ int oracle_simulate_interval(const modle_b200_sim_params* params,
   worker();
   for (auto& t : pool) t.join();
   return 0;
+}
+
+int oracle_simulate_interval(const modle_b200_sim_params* params,
+                             const modle_b200_interval* interval,
+                             const modle_b200_barrier* barriers, std::size_t num_barriers,
+                             const modle_b200_cell_task* tasks, std::size_t num_cells,
+                             u32* band_out, u64* occ1d_out, modle_b200_cell_stats* stats_out,
+                             u64* missed_updates_out, int nthreads) {
+  return oracle_simulate_interval_logged(params, interval, barriers, num_barriers, tasks,
+                                         num_cells, band_out, occ1d_out, stats_out,
+                                         missed_updates_out, nthreads, nullptr, 0);
 }
 
 // Runs one cell for params->debug_max_epochs epochs and dumps its state.

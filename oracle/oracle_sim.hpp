@@ -588,6 +588,39 @@ class CellSim {
     g_ = Rng::from_state(task.rng_state);
   }
 
+  // internal-state log (Config::log_model_internal_state): records [0, log_cap)
+  void set_log(modle_b200_epoch_record* log, std::size_t cap) {
+    log_ = log;
+    log_cap_ = cap;
+  }
+
+  // Simulation::dump_stats (simulation.cpp:995-1056): same quantities, same point of the epoch
+  void dump_stats() {
+    const CellState& s = s_;
+    if (!log_ || s.epoch >= log_cap_) return;
+    modle_b200_epoch_record r{};
+    r.epoch = s.epoch;
+    r.burnin = s.burnin_completed ? 0u : 1u;
+    r.num_lefs = static_cast<u32>(s.num_active);
+    for (std::size_t i = 0; i < bars_.size(); ++i) r.barriers_occupied += bars_.active[i] != 0;
+    double loop_sum = 0.0;  // stats::mean accumulates in double (descriptive_impl.hpp:22-31)
+    for (std::size_t i = 0; i < s.num_active; ++i) {
+      const bool rv = coll_occurred(s.rev_coll[i]), fw = coll_occurred(s.fwd_coll[i]);
+      r.lefs_stalled_rev += rv;
+      r.lefs_stalled_fwd += fw;
+      r.lefs_stalled_both += rv && fw;
+      r.lef_bar_collisions +=
+          coll_occurred(s.rev_coll[i], EV_LEF_BAR) + coll_occurred(s.fwd_coll[i], EV_LEF_BAR);
+      r.lef_lef_primary_collisions += coll_occurred(s.rev_coll[i], EV_LEF_LEF_PRIMARY) +
+                                      coll_occurred(s.fwd_coll[i], EV_LEF_LEF_PRIMARY);
+      r.lef_lef_secondary_collisions += coll_occurred(s.rev_coll[i], EV_LEF_LEF_SECONDARY) +
+                                        coll_occurred(s.fwd_coll[i], EV_LEF_LEF_SECONDARY);
+      loop_sum += static_cast<double>(s.fwd[i] - s.rev[i]);  // Lef::loop_size
+    }
+    r.loop_size_sum = static_cast<u64>(loop_sum);
+    log_[s.epoch] = r;
+  }
+
   CellState& state() { return s_; }
   Rng& rng() { return g_; }
   Barriers& barriers() { return bars_; }
@@ -625,6 +658,7 @@ class CellSim {
       CollisionCtx c = ctx();
       process_collisions(c, true);
       extrude();
+      dump_stats();
       release_lefs();
     }
     CellResult r;
@@ -879,6 +913,8 @@ class CellSim {
   Barriers bars_;
   CellTask task_;
   ContactSink sink_;
+  modle_b200_epoch_record* log_ = nullptr;
+  std::size_t log_cap_ = 0;
   CellState s_;
   Rng g_;
 };

@@ -183,8 +183,10 @@ def collision_steps(steps, start, end, rev, fwd, ep, rr, fr, rm, fm, bar_pos, ba
     return a
 
 
-def simulate_interval(params, interval, barriers, tasks, nthreads=1, want_occ=True):
-    """CPU counterpart of modle_b200.simulate_interval. Returns (band, occ1d, stats, missed)."""
+def simulate_interval(params, interval, barriers, tasks, nthreads=1, want_occ=True,
+                      log_capacity_per_cell=0):
+    """CPU counterpart of modle_b200.simulate_interval. Returns (band, occ1d, stats, missed)
+    and, with log_capacity_per_cell > 0, the internal-state log records[cell][epoch]."""
     from modle_b200.host import band_shape  # pure-host geometry helper (no GPU code)
 
     _, _, stats_dt = abi.np_dtypes()
@@ -195,6 +197,20 @@ def simulate_interval(params, interval, barriers, tasks, nthreads=1, want_occ=Tr
     missed = C.c_uint64(0)
     barriers = np.ascontiguousarray(barriers)
     tasks = np.ascontiguousarray(tasks)
+    if log_capacity_per_cell:
+        log = np.zeros((len(tasks), int(log_capacity_per_cell)), dtype=abi.epoch_record_dtype())
+        L = lib()
+        L.oracle_simulate_interval_logged.argtypes = [
+            C.POINTER(abi.SimParams), C.POINTER(abi.Interval), C.c_void_p, C.c_size_t, C.c_void_p,
+            C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_int,
+            C.c_void_p, C.c_size_t]
+        rc = L.oracle_simulate_interval_logged(
+            C.byref(params), C.byref(interval), barriers.ctypes.data, len(barriers),
+            tasks.ctypes.data, len(tasks), band.ctypes.data, occ.ctypes.data if want_occ else None,
+            stats.ctypes.data, C.byref(missed), int(nthreads), log.ctypes.data,
+            int(log_capacity_per_cell))
+        assert rc == 0
+        return band, occ, stats, int(missed.value), log
     rc = lib().oracle_simulate_interval(
         C.byref(params), C.byref(interval), barriers.ctypes.data, len(barriers),
         tasks.ctypes.data, len(tasks), band.ctypes.data, occ.ctypes.data if want_occ else None,
@@ -216,6 +232,14 @@ def band_to_pixels(band, nrows, ncols, bin_offset=0):
     if n:
         L.oracle_band_to_pixels(band.ctypes.data, nrows, ncols, bin_offset, out.ctypes.data, n)
     return out
+
+
+def lef_occupancy_profile(occ1d):
+    """write_lef_occupancy_to_bwig (src/libmodle/cpu/simulation.cpp:170-197), numpy restatement:
+    float(double(n) / double(max))."""
+    occ1d = np.asarray(occ1d, dtype=np.uint64)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return (occ1d.astype(np.float64) / np.float64(occ1d.max())).astype(np.float32)
 
 
 def snapshot_cell(params, interval, barriers, task):

@@ -284,3 +284,24 @@ def test_register_contacts_binned_path(gpu_ctx):
     assert gpu_ctx.kernel_launches() - launches0 == 8  # 4 kernels per binned call
     assert np.array_equal(band.cpu().numpy().view(np.uint32), 2 * expect)
     assert int(missed.item()) == 2 * int((~ok).sum())
+
+
+@pytest.mark.parametrize("name", ["defaults_small", "c4_high_collision", "fractional_pblock",
+                                  "skip_burnin", "mid_chr13_shape"])
+def test_internal_state_log_matches_oracle(gpu_ctx, name):
+    """SURVEY 8f row 4: the per-epoch quantities of Simulation::dump_stats
+    (simulation.cpp:995-1056), record by record."""
+    p, iv, bars, tasks = make_case(**CASES[name])
+    cap = 700
+    a = pyoracle.simulate_interval(p, iv, bars, tasks, nthreads=8, log_capacity_per_cell=cap)
+    b = gpu_ctx.simulate_interval(p, iv, bars, tasks, log_capacity_per_cell=cap)
+    assert results_equal(a[:4], b[:4]) == []
+    assert np.array_equal(a[4], b[4])
+    for c in range(len(tasks)):
+        ne = min(cap, int(b[2]["num_epochs"][c]))
+        rec = b[4][c]
+        assert np.array_equal(rec["epoch"][:ne], np.arange(ne))
+        assert not rec[ne:].view(np.uint8).any()  # epochs beyond the cell's last stay zero
+        assert (rec["lefs_stalled_both"] <= np.minimum(rec["lefs_stalled_rev"],
+                                                       rec["lefs_stalled_fwd"])).all()
+        assert (rec["barriers_occupied"][:ne] <= len(bars)).all()

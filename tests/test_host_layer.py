@@ -29,6 +29,7 @@ def test_struct_layouts_match_header(product_lib):
     assert C.sizeof(abi.Barrier) == 32
     assert C.sizeof(abi.CellTask) == 56
     assert C.sizeof(abi.CellStats) == 48
+    assert abi.epoch_record_dtype().itemsize == 56 and C.sizeof(abi.Pixel) == 24
     p = host.default_params()
     assert p.bin_size == 5000 and p.num_cells == 512 and p.debug_max_epochs == abi.U64_MAX
     assert p.contact_sampling_strategy == 7 and p.track_1d_lef_position == 1

@@ -149,3 +149,32 @@ def test_gev_noise_matches_scipy_quantiles():
     ref = -stats.genextreme.ppf([1 - q for q in qs], c=0.001, loc=0.0, scale=5000.0)
     got = np.quantile(x, qs)
     assert np.allclose(np.sort(np.abs(got)), np.sort(np.abs(ref)), rtol=0.03)
+
+
+def test_oracle_internal_state_log_invariants():
+    """dump_stats restatement (simulation.cpp:995-1056): one record per completed epoch, taken
+    after extrude; counts are consistent with each other and with the cell's stats."""
+    from common import make_case
+
+    p, iv, bars, tasks = make_case(size=4_000_000, ncells=2, nbar=60, target_contact_density=0.01)
+    plain = pyoracle.simulate_interval(p, iv, bars, tasks, nthreads=2)
+    band, occ, stats, missed, log = pyoracle.simulate_interval(p, iv, bars, tasks, nthreads=2,
+                                                               log_capacity_per_cell=2000)
+    assert np.array_equal(band, plain[0]) and np.array_equal(stats, plain[2])  # logging is passive
+    for c in range(2):
+        ne = int(stats["num_epochs"][c])
+        r = log[c][:ne]
+        assert np.array_equal(r["epoch"], np.arange(ne))
+        assert not log[c][ne:].view(np.uint8).any()
+        assert int(r["num_lefs"].astype(np.uint64).sum()) == int(stats["num_lef_updates"][c])
+        assert (r["lefs_stalled_both"] <= np.minimum(r["lefs_stalled_rev"],
+                                                     r["lefs_stalled_fwd"])).all()
+        # every stall is exactly one of: interval boundary, LEF-BAR, primary or secondary LEF-LEF
+        typed = r["lef_bar_collisions"] + r["lef_lef_primary_collisions"] + \
+            r["lef_lef_secondary_collisions"]
+        assert (typed <= r["lefs_stalled_rev"] + r["lefs_stalled_fwd"]).all()
+        assert (r["barriers_occupied"] <= len(bars)).all()
+        assert r["burnin"][0] == 1 and r["burnin"][-1] == 0
+        assert (np.diff(r["burnin"].astype(np.int64)) <= 0).all()  # burn-in never resumes
+        # epoch 0: the first LEF bound at epoch 0 has extruded once in each direction
+        assert 0 < r["loop_size_sum"][0] <= 2 * 17000

@@ -138,3 +138,22 @@ def test_cuda_pixels_of_a_simulated_band_on_device(gpu_ctx):
     rows = d_rows.cpu().numpy()
     assert np.array_equal(np.diff(rows), np.bincount((want["bin1_id"] - 1000).astype(np.int64),
                                                      minlength=ncols))
+
+
+# ------------------------------------------------------------------------ 1D occupancy profile
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [1, 31, 12889, 242194])
+def test_cuda_occupancy_profile_matches_oracle(gpu_ctx, n):
+    rng = np.random.default_rng(n)
+    occ = rng.integers(0, 2**40, n, dtype=np.uint64)
+    occ[rng.integers(0, n)] = 2**53 + 12345  # beyond the exactly representable doubles
+    a = gpu_ctx.lef_occupancy_profile(occ)
+    b = pyoracle.lef_occupancy_profile(occ)
+    assert a.dtype == np.float32 and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    z = gpu_ctx.lef_occupancy_profile(np.zeros(17, dtype=np.uint64))
+    assert np.isnan(z).all()  # 0 / 0, as in the reference
+
+
+def test_oracle_occupancy_profile():
+    p = pyoracle.lef_occupancy_profile(np.array([0, 5, 10, 2], dtype=np.uint64))
+    assert p.tolist() == [0.0, 0.5, 1.0, np.float32(0.2)]
