@@ -79,11 +79,31 @@ extern "C" {
 
 const char* emu_last_error() { return g_emu_error.c_str(); }
 
+int emu_simulate_interval_logged(const modle_b200_sim_params* params,
+                                 const modle_b200_interval* interval,
+                                 const modle_b200_barrier* barriers, size_t num_barriers,
+                                 const modle_b200_cell_task* tasks, size_t num_cells,
+                                 u32* band_out, u64* occ1d_out, modle_b200_cell_stats* stats_out,
+                                 u64* missed_updates_out, int virtual_threads, int staging,
+                                 modle_b200_epoch_record* log_out, size_t log_cap);
+
 int emu_simulate_interval(const modle_b200_sim_params* params, const modle_b200_interval* interval,
                           const modle_b200_barrier* barriers, size_t num_barriers,
                           const modle_b200_cell_task* tasks, size_t num_cells, u32* band_out,
                           u64* occ1d_out, modle_b200_cell_stats* stats_out,
                           u64* missed_updates_out, int virtual_threads, int staging) {
+  return emu_simulate_interval_logged(params, interval, barriers, num_barriers, tasks, num_cells,
+                                      band_out, occ1d_out, stats_out, missed_updates_out,
+                                      virtual_threads, staging, nullptr, 0);
+}
+
+int emu_simulate_interval_logged(const modle_b200_sim_params* params,
+                                 const modle_b200_interval* interval,
+                                 const modle_b200_barrier* barriers, size_t num_barriers,
+                                 const modle_b200_cell_task* tasks, size_t num_cells,
+                                 u32* band_out, u64* occ1d_out, modle_b200_cell_stats* stats_out,
+                                 u64* missed_updates_out, int virtual_threads, int staging,
+                                 modle_b200_epoch_record* log_out, size_t log_cap) {
   EmuCell cell;
   g_emu_error = cell.setup(*params, *interval, barriers, num_barriers, staging);
   if (!g_emu_error.empty()) return -1;
@@ -92,6 +112,8 @@ int emu_simulate_interval(const modle_b200_sim_params* params, const modle_b200_
           missed_updates_out ? missed_updates_out : &missed_local};
   for (size_t c = 0; c < num_cells; ++c) {
     modle_b200_cell_stats st{};
+    K.log = (log_out && log_cap) ? log_out + c * log_cap : nullptr;  // as k_simulate_cells does
+    K.log_cap = static_cast<u32>(log_cap);
     if (cell.kp.stop_on_epochs || tasks[c].num_target_contacts != 0) {
       Cta cta{&cell.shared->scratch, virtual_threads};
       CellSim sim{cell.kp, cell.D, cell.A, *cell.shared, K, cta, to_task(tasks[c])};

@@ -39,7 +39,8 @@ def _check(rc):
         raise RuntimeError("emu: " + lib().emu_last_error().decode())
 
 
-def simulate_interval(params, interval, barriers, tasks, virtual_threads=64, staging=0):
+def simulate_interval(params, interval, barriers, tasks, virtual_threads=64, staging=0,
+                      log_capacity_per_cell=0):
     _, _, stats_dt = abi.np_dtypes()
     nrows, ncols = host.band_shape(params, int(interval.end - interval.start))
     band = np.zeros(nrows * ncols + 1, dtype=np.uint32)
@@ -48,6 +49,19 @@ def simulate_interval(params, interval, barriers, tasks, virtual_threads=64, sta
     missed = C.c_uint64(0)
     barriers = np.ascontiguousarray(barriers)
     tasks = np.ascontiguousarray(tasks)
+    if log_capacity_per_cell:
+        log = np.zeros((len(tasks), int(log_capacity_per_cell)), dtype=abi.epoch_record_dtype())
+        L = lib()
+        L.emu_simulate_interval_logged.argtypes = [
+            C.POINTER(abi.SimParams), C.POINTER(abi.Interval), C.c_void_p, C.c_size_t, C.c_void_p,
+            C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_int,
+            C.c_int, C.c_void_p, C.c_size_t]
+        _check(L.emu_simulate_interval_logged(
+            C.byref(params), C.byref(interval), barriers.ctypes.data if len(barriers) else None,
+            len(barriers), tasks.ctypes.data, len(tasks), band.ctypes.data, occ.ctypes.data,
+            stats.ctypes.data, C.byref(missed), virtual_threads, staging, log.ctypes.data,
+            int(log_capacity_per_cell)))
+        return band, occ, stats, int(missed.value), log
     _check(lib().emu_simulate_interval(
         C.byref(params), C.byref(interval), barriers.ctypes.data if len(barriers) else None,
         len(barriers), tasks.ctypes.data, len(tasks), band.ctypes.data, occ.ctypes.data,

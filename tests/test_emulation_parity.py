@@ -163,3 +163,23 @@ def test_move_generation_stream_order(n, vt, seed):
     moves, used = emu_lib.sample_moves(state, n, 4000.0, 200.0, virtual_threads=vt)
     assert used == draws
     assert np.array_equal(moves, expect)
+
+
+@pytest.mark.parametrize("name", ["defaults_small", "lef_density_x4", "fractional_pblock",
+                                  "skip_burnin", "large_staging"])
+def test_internal_state_log_of_the_kernel_source_matches_oracle(name):
+    """log_epoch_state (sim_core.hpp) against the oracle's dump_stats restatement
+    (simulation.cpp:995-1056), record by record, for several virtual CTA widths."""
+    kw = dict(CASES[name])
+    kw.pop("_vt", None)
+    staging = kw.pop("_staging", 0)
+    p, iv, bars, tasks = make_case(**kw)
+    cap = 500
+    a = pyoracle.simulate_interval(p, iv, bars, tasks, nthreads=4, log_capacity_per_cell=cap)
+    for vt in (32, 96):
+        b = emu_lib.simulate_interval(p, iv, bars, tasks, virtual_threads=vt, staging=staging,
+                                      log_capacity_per_cell=cap)
+        assert results_equal(a[:4], b[:4]) == []
+        assert np.array_equal(a[4], b[4]), vt
+    ne = int(a[2]["num_epochs"][0])
+    assert a[4][0]["num_lefs"][:min(ne, cap)].any()
