@@ -19,30 +19,32 @@ NVCC_FLAGS = [
 ]
 
 
+def _deps():
+    return [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+
+
 def needs_build():
-    if not os.path.exists(LIB):
-        return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
-    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+    from . import buildutil
+
+    return not buildutil.is_current(LIB, [d for d in _deps() if os.path.exists(d)],
+                                    " ".join(NVCC_FLAGS))
 
 
 def build(force=False, verbose=False, variant=None, defines=()):
-    """Builds the product library, or with `variant` an experimental copy
-    libmodle_b200_<variant>.so compiled with extra -D `defines` (profiling sessions load it
-    through the MODLE_B200_LIB environment variable)."""
+    """Builds the product library (when its sources changed: content hash, see buildutil), or with
+    `variant` an experimental copy libmodle_b200_<variant>.so compiled with extra -D `defines`
+    (profiling sessions load it through the MODLE_B200_LIB environment variable)."""
+    from . import buildutil
+
     out = LIB if variant is None else os.path.join(HERE, f"libmodle_b200_{variant}.so")
-    if variant is None and not force and not needs_build():
-        return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-        ["-D" + d for d in defines] + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", out]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed building " + out)
-    return out
+
+    def cmd(tmp):
+        return [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+            ["-D" + d for d in defines] + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", tmp]
+
+    return buildutil.ensure_built(out, _deps(), cmd, extra=" ".join(NVCC_FLAGS + list(defines)),
+                                  force=force or variant is not None, verbose=verbose)
 
 
 if __name__ == "__main__":

@@ -5,7 +5,6 @@ this module; the product package modle_b200 never does.
 """
 import ctypes as C
 import os
-import subprocess
 
 import numpy as np
 
@@ -15,16 +14,22 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 
+CXXFLAGS = ["-O3", "-march=x86-64-v3", "-ffp-contract=off", "-fno-fast-math", "-std=c++17", "-fPIC",
+            "-Wall", "-Wextra", "-pthread", "-shared"]  # keep in step with oracle/Makefile
+
+
 def build(force=False):
+    """Builds liboracle.so when its sources changed (content hash; safe under concurrent callers,
+    see modle_b200/buildutil.py). Same compiler flags as oracle/Makefile."""
+    from modle_b200 import buildutil
+
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("oracle_capi.cpp", "oracle_sim.hpp", "oracle_rng.hpp")]
-    srcs.append(os.path.join(_HERE, "..", "include", "modle_b200.h"))
-    stale = (not os.path.exists(so)) or any(
-        os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
-    if force or stale:
-        subprocess.check_call(["make", "-C", _HERE, "-B", "liboracle.so"],
-                              stdout=subprocess.DEVNULL)
-    return so
+    deps = [os.path.join(_HERE, f) for f in ("oracle_capi.cpp", "oracle_sim.hpp", "oracle_rng.hpp")]
+    deps.append(os.path.join(_HERE, "..", "include", "modle_b200.h"))
+    cxx = os.environ.get("CXX", "g++")
+    return buildutil.ensure_built(
+        so, deps, lambda tmp: [cxx] + CXXFLAGS + ["-o", tmp, os.path.join(_HERE, "oracle_capi.cpp")],
+        extra=" ".join(CXXFLAGS), force=force)
 
 
 def lib():

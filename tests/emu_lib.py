@@ -1,7 +1,6 @@
 """TEST INFRASTRUCTURE ONLY -- ctypes wrapper of the CPU emulation of the kernel (tests/emu)."""
 import ctypes as C
 import os
-import subprocess
 
 import numpy as np
 
@@ -11,12 +10,31 @@ _HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu")
 _LIB = None
 
 
+CXXFLAGS = ["-O2", "-march=x86-64-v3", "-ffp-contract=off", "-fno-fast-math", "-std=c++17", "-fPIC",
+            "-Wall", "-Wextra", "-Wno-unused-parameter", "-pthread", "-shared"]  # as tests/emu/Makefile
+
+
+def build(force=False):
+    """Builds libemu.so when the kernel sources changed (content hash, modle_b200/buildutil.py)."""
+    from modle_b200 import buildutil
+
+    csrc = os.path.join(_HERE, "..", "..", "modle_b200", "csrc")
+    deps = [os.path.join(_HERE, "emu_capi.cpp")] + [
+        os.path.join(csrc, f) for f in ("sim_core.hpp", "sim_types.hpp", "cta.hpp", "launch_prep.hpp",
+                                        "host_rng.hpp", "host.cpp", "status.hpp")]
+    deps.append(os.path.join(_HERE, "..", "..", "include", "modle_b200.h"))
+    cxx = os.environ.get("CXX", "g++")
+    return buildutil.ensure_built(
+        os.path.join(_HERE, "libemu.so"), deps,
+        lambda tmp: [cxx] + CXXFLAGS + ["-o", tmp, os.path.join(_HERE, "emu_capi.cpp"),
+                                        os.path.join(csrc, "host.cpp")],
+        extra=" ".join(CXXFLAGS), force=force)
+
+
 def lib():
     global _LIB
     if _LIB is None:
-        subprocess.check_call(["make", "-C", _HERE, "libemu.so"], stdout=subprocess.DEVNULL,
-                              stderr=subprocess.DEVNULL)
-        L = C.CDLL(os.path.join(_HERE, "libemu.so"))
+        L = C.CDLL(build())
         u64p = C.POINTER(C.c_uint64)
         L.emu_last_error.restype = C.c_char_p
         L.emu_simulate_interval.argtypes = [
