@@ -374,4 +374,33 @@ u64 oracle_band_to_pixels(const u32* band, u64 nrows, u64 ncols, u64 bin_offset,
   return n_out;
 }
 
+// Collision word helpers, for the reference's encoding KATs (collision_encoding_test.cpp:27-176).
+// out = {decode_index, decode_event, collision_occurred(), collision_avoided(),
+//        collision_occurred(kind), collision_avoided(kind)}; collision_avoided() is
+// "!occurred && word != 0" (collision_encoding_impl.hpp:227-230).
+u32 oracle_collision_word(u64 idx, u32 event) { return coll_make(idx, event); }
+void oracle_collision_query(u32 word, u32 kind, u64* out) {
+  out[0] = coll_index(word);
+  out[1] = coll_event(word);
+  out[2] = coll_occurred(word);
+  out[3] = !coll_occurred(word) && word != 0;
+  out[4] = coll_occurred(word, kind);
+  out[5] = coll_avoided(word, kind);
+}
+
+// ContactMatrixDense<u32>::increment semantics (contact_matrix_dense_safe_impl.hpp:54-89) on a
+// caller-provided band: returns 1 when the pixel is outside the band (counted as missed).
+int oracle_band_increment(u32* band, u64 nrows, u64 ncols, u64 bin_size, u64 b1, u64 b2,
+                          u64* missed) {
+  ContactSink sink;
+  sink.geom.nrows = nrows;
+  sink.geom.ncols = ncols;
+  (void)bin_size;
+  sink.band = band;
+  const u64 before = *missed;
+  sink.missed = missed;
+  sink.increment(b1, b2);
+  return *missed != before;
+}
+
 }  // extern "C"

@@ -310,4 +310,15 @@ long long emu_sample_moves(const u64* state, size_t n, double speed, double sd, 
   return static_cast<long long>(cell.shared->rng_pos);
 }
 
+// The kernel's collision-word helpers (sim_types.hpp), for the reference's encoding KATs.
+u32 emu_collision_word(u64 idx, u32 event) { return coll_make(static_cast<u32>(idx), event); }
+void emu_collision_query(u32 word, u32 kind, u64* out) {
+  out[0] = coll_index(word);
+  out[1] = coll_event(word);
+  out[2] = coll_occurred(word);
+  out[3] = !coll_occurred(word) && word != 0;
+  out[4] = coll_is(word, kind);
+  out[5] = coll_avoided(word, kind);
+}
+
 }  // extern "C"

@@ -79,7 +79,8 @@ def parse_case(name, block, line):
     case["rng_seed"] = int(m.group(1)) if m else 10556020843759504871  # DEFAULT_PRNG
     # one or more LEF arrays (ranking tests have lefs1 / lefs2)
     lef_sets = []
-    for m in re.finditer(r"std::array<Lef,\s*\w+>\s+(\w+)\s*\{(.*?)\}\s*;", block, re.S):
+    for m in re.finditer(r"std::(?:array<Lef,\s*\w+>|vector<Lef>)\s+(\w+)\s*\{(.*?)\}\s*;", block,
+                         re.S):
         lefs = [[int(a), int(b), int(e)] for a, b, e in
                 re.findall(r"construct_lef\((\d+),\s*(\d+),\s*(\d+)\)", m.group(2))]
         lef_sets.append((m.group(1), lefs))
