@@ -439,11 +439,36 @@ struct Cta {
 
 #else  // ---------------------------------------------------------------- emulation
 
+// Order in which the emulation runs the virtual threads of a region: 0 = ascending, 1 =
+// descending, 2 = a different pseudo-random permutation for every region. A region whose result
+// depends on the order has a cross-thread dependency the device would need a barrier for, so the
+// tests replay every case under all three (a race detector that needs no GPU).
+inline int& emu_thread_order() {
+  static thread_local int mode = 0;
+  return mode;
+}
+
 struct Cta {
   CtaScratch* scr;
   int nthreads;
+  mutable u32 region_counter = 0;
   // The emulation runs a region as a loop over virtual threads, so "one value per thread"
   // primitives are split in two halves: put(tid, v) inside one region, get(tid) in a later one.
+  // k-th virtual thread to run in the current region (k == nthreads ends the region)
+  int order(int k) const {
+    if (k >= nthreads) return nthreads;
+    const int mode = emu_thread_order();
+    if (mode == 0) return k;
+    if (mode == 1) return nthreads - 1 - k;
+    if (k == 0) ++region_counter;
+    // affine permutation k -> (a * k + b) mod n with a coprime to n
+    static const u32 kMul[8] = {7, 11, 13, 17, 19, 23, 29, 31};
+    const u32 n = static_cast<u32>(nthreads);
+    u32 a = kMul[region_counter & 7];
+    while (std::__gcd(a, n) != 1) ++a;
+    const u32 b = (region_counter * 2654435761u) % n;
+    return static_cast<int>((u64(a) * static_cast<u32>(k) + b) % n);
+  }
   int nt() const { return nthreads; }
   int first() const { return 0; }
   int step() const { return 1; }
@@ -528,6 +553,11 @@ struct Cta {
 #endif
 
 // A region: every thread of the CTA executes the body once, then the CTA synchronises.
+#if MB_DEVICE_BUILD
 #define MB_REGION(cta, tid) for (int tid = (cta).first(); tid < (cta).nt(); tid += (cta).step())
+#else
+#define MB_REGION(cta, tid)                                                                  \
+  for (int mb_k_ = 0, tid = (cta).order(0); mb_k_ < (cta).nt(); ++mb_k_, tid = (cta).order(mb_k_))
+#endif
 
 }  // namespace modle_b200

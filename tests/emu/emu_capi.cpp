@@ -79,6 +79,9 @@ extern "C" {
 
 const char* emu_last_error() { return g_emu_error.c_str(); }
 
+// 0 ascending, 1 descending, 2 shuffled per region (cta.hpp: emu_thread_order)
+void emu_set_thread_order(int mode) { emu_thread_order() = mode; }
+
 int emu_simulate_interval_logged(const modle_b200_sim_params* params,
                                  const modle_b200_interval* interval,
                                  const modle_b200_barrier* barriers, size_t num_barriers,

@@ -52,6 +52,12 @@ def lib():
     return _LIB
 
 
+def set_thread_order(mode):
+    """0: virtual threads of a region run in ascending order, 1: descending, 2: shuffled
+    differently for every region (cta.hpp emu_thread_order)."""
+    lib().emu_set_thread_order(int(mode))
+
+
 def _check(rc):
     if rc != 0:
         raise RuntimeError("emu: " + lib().emu_last_error().decode())

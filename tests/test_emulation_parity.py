@@ -183,3 +183,45 @@ def test_internal_state_log_of_the_kernel_source_matches_oracle(name):
         assert np.array_equal(a[4], b[4]), vt
     ne = int(a[2]["num_epochs"][0])
     assert a[4][0]["num_lefs"][:min(ne, cap)].any()
+
+
+@pytest.fixture
+def thread_order():
+    yield emu_lib.set_thread_order
+    emu_lib.set_thread_order(0)
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_regions_do_not_depend_on_thread_order(name, mode, thread_order):
+    """A region (the code between two CTA barriers) must give the same result whatever order its
+    threads run in; otherwise the device needs a barrier the emulation's ascending loop hides.
+    Every case is replayed with the virtual threads of each region descending and shuffled."""
+    kw = dict(CASES[name])
+    vt = kw.pop("_vt", 64)
+    staging = kw.pop("_staging", 0)
+    p, iv, bars, tasks = make_case(**kw)
+    a = pyoracle.simulate_interval(p, iv, bars, tasks, nthreads=4, log_capacity_per_cell=300)
+    thread_order(mode)
+    b = emu_lib.simulate_interval(p, iv, bars, tasks, virtual_threads=vt, staging=staging,
+                                  log_capacity_per_cell=300)
+    assert b[2]["device_fault"].max() == 0
+    assert results_equal(a[:4], b[:4]) == []
+    assert np.array_equal(a[4], b[4])
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_reference_goldens_under_other_thread_orders(mode, thread_order):
+    import test_reference_goldens as trg
+
+    thread_order(mode)
+    for case in trg.STEP_CASES:
+        if case["released"]:
+            continue
+        for vthreads in (3, 8):
+            try:
+                trg.test_kernel_emulation_reproduces_reference_goldens(case, vthreads)
+            except pytest.skip.Exception:
+                pass
+    for case in trg.RANK_CASES:
+        trg.test_rank_lefs_goldens(case)
