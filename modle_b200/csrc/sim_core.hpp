@@ -593,9 +593,11 @@ struct CellSim {
   MB_FN void burnin_step() {
     for (;;) {
       const bool activating = S.num_active != P.n_lefs;
+      // every thread evaluates S.rng_pos here, the leader moves it in the region below: the
+      // barrier has to sit between the two (scripts/lint_shared_state.py checks this pattern)
+      if (activating) rng_ensure(S.rng_pos + 256);
       cta.sync();
       if (activating) {
-        rng_ensure(S.rng_pos + 256);
         MB_REGION(cta, tid) {
           if (cta.leader(tid)) {
             ++S.num_burnin_epochs;
@@ -1182,9 +1184,9 @@ struct CellSim {
       if (left < nev) nev = left;
     }
     if (nev == 0) return;
-    cta.sync();
     const bool need_binomial = P.tad_to_loop != 0.0 && isfinite(P.tad_to_loop);
-    if (need_binomial) rng_ensure(S.rng_pos + 256);
+    if (need_binomial) rng_ensure(S.rng_pos + 256);  // reads S.rng_pos: before the barrier
+    cta.sync();
     MB_REGION(cta, tid) {
       if (cta.leader(tid)) {
         u64 nloop;

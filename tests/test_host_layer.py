@@ -143,3 +143,38 @@ def test_barrier_records_to_stp(product_lib):
     assert b["stp_active"][0] == p.barrier_occupied_stp
     occ = host.lib().modle_b200_occupancy_from_stp(b["stp_active"][1], b["stp_inactive"][1])
     assert abs(occ - 0.8) < 1e-12
+
+
+def test_shared_state_lint_is_clean_and_still_bites(tmp_path):
+    """scripts/lint_shared_state.py: no finding on the kernel source; and it flags the pattern
+    that caused this round's determinism flake (S.rng_pos read by every thread right before the
+    region in which the leader advances it)."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location(
+        "lint_shared_state", os.path.join(ROOT, "scripts", "lint_shared_state.py"))
+    lint = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(lint)
+    assert lint.lint(os.path.join(ROOT, "modle_b200", "csrc", "sim_core.hpp")) == []
+    bad = tmp_path / "bad.hpp"
+    bad.write_text("""
+  MB_FN void next_barrier_states() {
+    rng_ensure(S.rng_pos + P.n_bar);
+    const u64 base = S.rng_pos;
+    MB_REGION(cta, tid) {
+      for (u32 i = tid; i < P.n_bar; i += cta.nt()) use(raw(base + i));
+      if (cta.leader(tid)) S.rng_pos = base + P.n_bar;
+    }
+    cta.sync();
+  }
+  MB_FN void after_region() {
+    MB_REGION(cta, tid) {
+      if (cta.leader(tid)) S.num_active = 3;
+    }
+    const u32 n = S.num_active;
+    cta.sync();
+  }
+""")
+    found = lint.lint(str(bad))
+    assert {(f[0], f[1]) for f in found} == {("next_barrier_states", "rng_pos"),
+                                             ("after_region", "num_active")}
