@@ -67,7 +67,7 @@ inline u32 staging_per_thread() {
   static const u32 l = [] {
     const char* e = std::getenv("MODLE_B200_GEN_PER_THREAD");
     const int v = e ? std::atoi(e) : 128;
-    return (v == 32 || v == 64 || v == 128) ? static_cast<u32>(v) : 128u;
+    return (v == 32 || v == 64 || v == 128 || v == 256) ? static_cast<u32>(v) : 128u;
   }();
   return l;
 }
