@@ -178,3 +178,38 @@ def test_shared_state_lint_is_clean_and_still_bites(tmp_path):
     found = lint.lint(str(bad))
     assert {(f[0], f[1]) for f in found} == {("next_barrier_states", "rng_pos"),
                                              ("after_region", "num_active")}
+
+
+def test_buildutil_concurrent_callers_build_once_and_atomically(tmp_path):
+    """modle_b200/buildutil.py: content-hash staleness (not mtimes), one build under concurrent
+    callers (torchrun starts one process per GPU), output renamed into place."""
+    import subprocess
+    import sys
+    import textwrap
+
+    src = tmp_path / "in.txt"
+    src.write_text("v1")
+    out = tmp_path / "out.bin"
+    log = tmp_path / "builds.log"
+    prog = textwrap.dedent(f"""
+        import sys, time
+        sys.path.insert(0, {ROOT!r})
+        from modle_b200 import buildutil
+        def cmd(tmp):
+            return [sys.executable, "-c",
+                    "import sys,time; time.sleep(0.5); open(sys.argv[2],'a').write('b\\\\n'); "
+                    "open(sys.argv[1],'w').write(open(sys.argv[3]).read())",
+                    tmp, {str(log)!r}, {str(src)!r}]
+        buildutil.ensure_built({str(out)!r}, [{str(src)!r}], cmd, extra="flags")
+    """)
+    procs = [subprocess.Popen([sys.executable, "-c", prog]) for _ in range(4)]
+    assert all(p.wait() == 0 for p in procs)
+    assert out.read_text() == "v1" and log.read_text().count("b") == 1
+    # unchanged content, newer mtime: still current; changed content: rebuilt once
+    os.utime(src, None)
+    subprocess.check_call([sys.executable, "-c", prog])
+    assert log.read_text().count("b") == 1
+    src.write_text("v2")
+    procs = [subprocess.Popen([sys.executable, "-c", prog]) for _ in range(3)]
+    assert all(p.wait() == 0 for p in procs)
+    assert out.read_text() == "v2" and log.read_text().count("b") == 2
