@@ -27,12 +27,14 @@ struct EmuCell {
   std::vector<u64> ring, gstate;
   std::unique_ptr<CellShared> shared;
   CellArrays A;
-  bool jump_ready[kJumpSlots] = {false, false};
+  
 
   std::string setup(const modle_b200_sim_params& p, const modle_b200_interval& iv,
                     const modle_b200_barrier* bars, size_t nb, int staging) {
     StagingConfig sc = staging == 1   ? staging_small()
                        : staging == 2 ? staging_large()
+                       : staging == 3 ? staging_mid()
+                       : staging == 4 ? staging_large_wide()
                                       : pick_staging(static_cast<u32>(iv.num_lefs),
                                                      static_cast<u32>(nb));
     const std::string err = prepare_interval(p, iv, bars, nb, sc, &kp, &hd);

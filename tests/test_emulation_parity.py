@@ -12,6 +12,9 @@ CASES = {
     "defaults_small": dict(size=3_000_000, ncells=4, target_contact_density=0.01),
     "large_staging": dict(size=3_000_000, ncells=3, target_contact_density=0.01, _staging=2,
                           _vt=96),
+    "mid_staging": dict(size=3_000_000, ncells=2, target_contact_density=0.01, _staging=3,
+                        _vt=96),
+    "wide_staging": dict(size=3_000_000, ncells=2, target_contact_density=0.01, _staging=4),
     "more_barriers": dict(size=8_000_000, ncells=3, nbar=150, target_contact_density=0.02,
                           _vt=128),
     "no_bypass": dict(size=5_000_000, ncells=3, nbar=90, target_contact_density=0.02,
