@@ -43,14 +43,30 @@ def _assign(pieces, world):
     return load
 
 
-def plan_shards(num_lefs, num_cells, world, tolerance=1.10, max_pieces=None):
+def plan_shards(num_lefs, num_cells, world, tolerance=1.10, max_pieces=None, slice_all=False):
     """Deals (interval, cell range) shards to `world` ranks.
 
     num_lefs[i] is the LEF count of interval i (0 = interval skipped, e.g. no barriers); the cost
     of a shard is num_lefs x cells. Starts from whole intervals and, while the heaviest rank
     carries more than `tolerance` x the mean load, halves the heaviest splittable piece of that
     rank. Deterministic: every rank computes the same plan.
+
+    slice_all: every interval is cut into `world` equal cell ranges instead, one per rank (the
+    first range of interval i goes to rank i % world, so the roots -- and with them the reduce
+    destinations and the device->host copies -- rotate over the ranks). Every rank then runs the
+    same mix of work, which removes both the imbalance between ranks and most of the tail of a
+    rank's last launches, at the price of one reduce per interval.
     """
+    if slice_all and world > 1:
+        out = []
+        for i, n in enumerate(num_lefs):
+            if n <= 0 or num_cells <= 0:
+                continue
+            for k in range(world):
+                lo, hi = num_cells * k // world, num_cells * (k + 1) // world
+                if hi > lo:
+                    out.append(Shard(i, lo, hi, (i + k) % world, float(n) * (hi - lo)))
+        return out
     pieces = [Shard(i, 0, num_cells, -1, float(n) * num_cells)
               for i, n in enumerate(num_lefs) if n > 0 and num_cells > 0]
     if not pieces:

@@ -14,12 +14,13 @@ from modle_b200 import distributed
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
+@pytest.mark.parametrize("slice_all", [False, True])
 @pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
 @pytest.mark.parametrize("num_lefs,cells", [([4979], 8192), ([1289, 900, 0, 3000, 40], 512),
                                             ([100] * 24, 7), ([5000, 10], 1)])
-def test_plan_covers_every_cell_once(world, num_lefs, cells):
-    shards = distributed.plan_shards(num_lefs, cells, world)
-    assert shards == distributed.plan_shards(num_lefs, cells, world)  # deterministic
+def test_plan_covers_every_cell_once(world, num_lefs, cells, slice_all):
+    shards = distributed.plan_shards(num_lefs, cells, world, slice_all=slice_all)
+    assert shards == distributed.plan_shards(num_lefs, cells, world, slice_all=slice_all)
     for i, n in enumerate(num_lefs):
         mine = sorted((s.cell_lo, s.cell_hi) for s in shards if s.interval == i)
         if n == 0:
@@ -28,6 +29,16 @@ def test_plan_covers_every_cell_once(world, num_lefs, cells):
         assert mine[0][0] == 0 and mine[-1][1] == cells
         assert all(a[1] == b[0] for a, b in zip(mine, mine[1:]))
     assert all(0 <= s.rank < world for s in shards)
+
+
+def test_sliced_plan_gives_every_rank_the_same_mix_and_rotates_the_roots():
+    sh = distributed.plan_shards([4979, 3000, 1289, 900], 512, 8, slice_all=True)
+    for r in range(8):
+        assert sorted((s.interval, s.cell_hi - s.cell_lo) for s in sh if s.rank == r) == \
+            [(i, 64) for i in range(4)]
+    roots = distributed.interval_roots(sorted(sh, key=lambda s: (s.interval, s.cell_lo)))
+    assert [roots[i][0] for i in range(4)] == [0, 1, 2, 3]
+    assert all(len(roots[i][1]) == 8 for i in range(4))
 
 
 def test_plan_balances_and_prefers_whole_intervals():
