@@ -12,6 +12,9 @@ LEF-updates/s (1 LEF-update = one active LEF carried through one epoch, burn-in 
          (H2D of tasks and barriers, D2H of band / 1D occupancy / stats inside the timed region)
   roofline, cpu_baseline, clocks, gpu_launches: see DESIGN.md "Measurement"
 
+--rng-mode throughput runs the same workload with counter-based draws ("Throughput
+mode"); the default and the headline is the deterministic mode.
+
 N > 1 (launched by torch.distributed.run, one rank per GPU): whole chromosomes are dealt to
 ranks heaviest-first (no data-path collective is needed for C2; a chromosome whose cells are
 split over ranks -- workload c3 -- is summed with one NCCL reduce). Total work is fixed, so
@@ -215,8 +218,9 @@ def run_ours(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     cfg, genome, desc = build_workload(args.workload, args.cells)
     p = cfg.params
-    sim = Simulation(cfg, genome, device=local_rank, rank=rank, world_size=world)
-    engine = distributed.DeviceEngine(local_rank, num_streams=args.streams)
+    rng_mode = 1 if args.rng_mode == "throughput" else 0
+    sim = Simulation(cfg, genome, device=local_rank, rank=rank, world_size=world, rng_mode=rng_mode)
+    engine = distributed.DeviceEngine(local_rank, num_streams=args.streams, rng_mode=rng_mode)
     ctx = engine.ctx
     barrier_dt, task_dt, stats_dt = abi.np_dtypes()
     shards = distributed.plan_shards(
@@ -371,6 +375,9 @@ def run_ours(args, rank, world, local_rank):
                        "l2_policy": "band matrices + RNG staging of a step exceed the 126 MB L2 "
                                     "for the genome-wide workload; bands are re-zeroed every step",
                        "streams": args.streams,
+                       "rng_mode": "deterministic (reference draw order, bit-exact)"
+                                   if rng_mode == 0 else
+                                   "throughput (counter-based draws, statistically equivalent)",
                        "parallelism": f"{world} rank(s), {len(shards)} (interval, cell-range) "
                                       f"shards dealt heaviest-first, {len(split)} interval(s) "
                                       "split over ranks and summed with one NCCL reduce each"},
@@ -414,6 +421,9 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4"])
     ap.add_argument("--cells", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--rng-mode", default="deterministic", choices=["deterministic", "throughput"],
+                    help="deterministic: the reference's draw order, bit-exact (the headline); "
+                         "throughput: counter-based draws, statistically equivalent")
     ap.add_argument("--streams", type=int, default=3,
                     help="concurrent launches per GPU (streams / host worker threads)")
     args = ap.parse_args()

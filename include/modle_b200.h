@@ -225,6 +225,22 @@ int modle_b200_genome_get_interval(const modle_b200_genome* genome, size_t i,
 int modle_b200_init(modle_b200_context** ctx, int device);
 void modle_b200_destroy(modle_b200_context* ctx);
 
+/* How the cells launched through this context take their random draws.
+ *   MODLE_B200_RNG_REFERENCE_ORDER (default) "deterministic mode": each cell consumes ONE
+ *     xoshiro256++ stream in exactly the order simulate_one_cell does
+ *     (src/libmodle/cpu/simulation.cpp:896-986 and callees), so trajectories and contact counts
+ *     are bit-identical to the reference algorithm for the same seed.
+ *   MODLE_B200_RNG_COUNTER "throughput mode": same distributions, but every (epoch, phase, item)
+ *     reads a private counter-based sequence keyed by the cell's task state, which removes the
+ *     draw staging, the offset scans and the speculation/repair the sequential order costs.
+ *     Results are a pure function of the task (independent of grid, CTA width, stream and GPU
+ *     count) and statistically equivalent to the reference's, NOT bit-identical to them;
+ *     modle_b200_cell_stats::num_rng_draws is reported as 0.
+ * The mode applies to the launches issued after the call. */
+enum { MODLE_B200_RNG_REFERENCE_ORDER = 0, MODLE_B200_RNG_COUNTER = 1 };
+int modle_b200_set_rng_mode(modle_b200_context* ctx, int mode);
+int modle_b200_get_rng_mode(const modle_b200_context* ctx);
+
 /* Simulates `num_cells` cells of one interval: the GPU replacement for popping num_cells Tasks
  * and running simulate_one_cell on each. HOST buffers in, HOST buffers out (copies included):
  *   band_out   nrows*ncols+1 uint32, ADDED to (caller zero-initialises; reference layout)

@@ -89,5 +89,6 @@ struct modle_b200_context {
   uint64_t px_calls = 0;
   size_t l2_bytes = 0;
   uint64_t launches = 0;
+  int rng_mode = MODLE_B200_RNG_REFERENCE_ORDER;  // modle_b200_set_rng_mode
 };
 

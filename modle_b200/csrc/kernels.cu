@@ -51,7 +51,9 @@ struct LaunchArgs {
 #ifndef MODLE_B200_LARGE_THREADS
 #define MODLE_B200_LARGE_THREADS 1024
 #endif
-template <int kThreads, int kMinBlocks>
+// kCtr selects the throughput mode (counter-based draws, sim_core.hpp) at compile time, so the
+// deterministic kernels carry none of its code.
+template <int kThreads, int kMinBlocks, bool kCtr = false>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
     k_simulate_cells(const __grid_constant__ LaunchArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -78,7 +80,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks)
       Cta cta{&S.scratch};
       Sinks K = a.K;
       if (K.log) K.log += size_t(cell) * K.log_cap;
-      CellSim sim{a.kp, a.D, A, S, K, cta, td};
+      CellSimT<kCtr> sim{a.kp, a.D, A, S, K, cta, td};
       sim.run();
     }
     __syncthreads();
@@ -372,6 +374,16 @@ int modle_b200_init(modle_b200_context** out, int device) {
     CUDA_TRY(cudaFuncSetAttribute(k_simulate_cells<512, 2>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(ctx->max_smem_optin - fa.sharedSizeBytes)));
+    // throughput-mode instantiations (same static shared memory: one u32)
+    CUDA_TRY(cudaFuncSetAttribute(k_simulate_cells<256, MODLE_B200_SMALL_MIN_BLOCKS, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(ctx->max_smem_optin - fa.sharedSizeBytes)));
+    CUDA_TRY(cudaFuncSetAttribute(k_simulate_cells<MODLE_B200_LARGE_THREADS, 1, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(ctx->max_smem_optin - fa.sharedSizeBytes)));
+    CUDA_TRY(cudaFuncSetAttribute(k_simulate_cells<512, 2, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(ctx->max_smem_optin - fa.sharedSizeBytes)));
     ctx->max_smem_optin -= fa.sharedSizeBytes;
   }
   *out = ctx;
@@ -387,6 +399,18 @@ void modle_b200_destroy(modle_b200_context* ctx) {
   if (ctx->binned_done) cudaEventDestroy(ctx->binned_done);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
+}
+
+int modle_b200_set_rng_mode(modle_b200_context* ctx, int mode) {
+  if (!ctx) return fail(MODLE_B200_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  if (mode != MODLE_B200_RNG_REFERENCE_ORDER && mode != MODLE_B200_RNG_COUNTER)
+    return fail(MODLE_B200_ERR_INVALID_ARGUMENT, "unknown RNG mode");
+  ctx->rng_mode = mode;
+  return MODLE_B200_OK;
+}
+
+int modle_b200_get_rng_mode(const modle_b200_context* ctx) {
+  return ctx ? ctx->rng_mode : MODLE_B200_RNG_REFERENCE_ORDER;
 }
 
 uint64_t modle_b200_kernel_launches(const modle_b200_context* ctx) {
@@ -489,18 +513,25 @@ int launch_simulate(modle_b200_context* ctx, const modle_b200_sim_params* params
                            sizeof(u32) * hd.bar_dir_rev.size(), cudaMemcpyHostToDevice, stream));
 
   // grid: persistent CTAs, as many as fit
+  const bool ctr = ctx->rng_mode == MODLE_B200_RNG_COUNTER;
   void (*kernel)(const LaunchArgs) =
-      sc.cta_threads == 256   ? k_simulate_cells<256, MODLE_B200_SMALL_MIN_BLOCKS>
-      : sc.cta_threads == 512 ? k_simulate_cells<512, 2>
-                              : k_simulate_cells<MODLE_B200_LARGE_THREADS, 1>;
+      sc.cta_threads == 256
+          ? (ctr ? k_simulate_cells<256, MODLE_B200_SMALL_MIN_BLOCKS, true>
+                 : k_simulate_cells<256, MODLE_B200_SMALL_MIN_BLOCKS>)
+      : sc.cta_threads == 512
+          ? (ctr ? k_simulate_cells<512, 2, true> : k_simulate_cells<512, 2>)
+          : (ctr ? k_simulate_cells<MODLE_B200_LARGE_THREADS, 1, true>
+                 : k_simulate_cells<MODLE_B200_LARGE_THREADS, 1>);
   int per_sm = 0;
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel,
                                                          static_cast<int>(sc.cta_threads), smem));
   if (per_sm < 1) return fail(MODLE_B200_ERR_UNSUPPORTED, "kernel does not fit on an SM");
   const u32 grid = static_cast<u32>(
       std::min<size_t>(num_cells, size_t(per_sm) * static_cast<size_t>(ctx->num_sms)));
-  CUDA_TRY(sl->d_rings.reserve(sizeof(u64) * 2 * size_t(sc.window) * grid));
-  CUDA_TRY(sl->d_states.reserve(sizeof(u64) * 4 * size_t(sc.gen_threads) * grid));
+  if (!ctr) {  // the throughput mode stages no draws
+    CUDA_TRY(sl->d_rings.reserve(sizeof(u64) * 2 * size_t(sc.window) * grid));
+    CUDA_TRY(sl->d_states.reserve(sizeof(u64) * 4 * size_t(sc.gen_threads) * grid));
+  }
   CUDA_TRY(sl->d_queue.reserve(sizeof(u32) * 4));
   CUDA_TRY(cudaMemsetAsync(sl->d_queue.p, 0, sizeof(u32) * 4, stream));
 

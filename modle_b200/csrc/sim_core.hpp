@@ -103,8 +103,45 @@ MB_FN double gev_from_canonical(double u, double mu, double sigma, double xi) {
   return mu + (sigma * (1.0 - pow(-log(u), xi))) / xi;
 }
 
+// ---- throughput mode: counter-based draws ---------------------------------------------------
+// The reference consumes ONE sequential stream per cell, which is what the default (deterministic)
+// mode reproduces draw for draw. The throughput mode gives up that order, not the distributions:
+// every (epoch, phase, item) owns a private sequence of 256 raw draws addressed by a 64-bit
+// counter, draw = mix64((counter ^ key1) * golden + key2) -- the SplitMix64 output function over
+// a per-cell keyed counter -- so no staging ring, no offset scans and no speculation/repair are
+// needed, and a cell's result still depends on nothing but its task (not on the CTA width, the
+// grid or the GPU count). Results are statistically equivalent to the reference's, not
+// bit-identical (tests/test_throughput_mode.py holds the gate).
+enum : u32 {
+  kDrInit = 0,
+  kDrBurnin,
+  kDrBind,
+  kDrSplit,
+  kDrLoop,  // + kind (0 loop, 1 TAD, 2 1D occupancy): kDrLoop, kDrTad, kDrOcc
+  kDrTad,
+  kDrOcc,
+  kDrMoves,
+  kDrBarriers,
+  kDrLefBar,
+  kDrPrimary,
+  kDrSecondary,
+  kDrRelease,
+};
+// counter layout: epoch (24 bits) | phase (4) | item (28) | draw number within the item (8)
+MB_FN u64 ctr_pack(u64 epoch, u32 phase, u32 item) {
+  return (epoch << 40) | (u64(phase & 15u) << 36) | (u64(item & 0x0FFFFFFFu) << 8);
+}
+constexpr u64 kCtrDrawsPerItem = 255;
+MB_FN u64 mix64(u64 z) {  // SplitMix64 output function
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
 // The per-cell simulator. All member functions are CTA-collective unless noted.
-struct CellSim {
+// kCtr = false: deterministic mode (the reference's draw order); true: throughput mode.
+template <bool kCtr>
+struct CellSimT {
   const KernelParams& P;
   const IntervalData& D;
   CellArrays A;
@@ -112,6 +149,7 @@ struct CellSim {
   Sinks K;
   Cta cta;
   CellTaskDev task;
+  u64 key1 = 0, key2 = 0;  // throughput mode: per-cell keys of the counter-based draws
 
   // ------------------------------------------------------------------------------ helpers
   // [lo, hi): thread tid's contiguous share of n items (n < 2^16, tid < 2^10: no overflow)
@@ -122,7 +160,19 @@ struct CellSim {
   MB_FN void fault(u32 code) const {
     if (S.fault == 0) S.fault = code;  // benign race: any code is reported
   }
-  MB_FN u64 raw(u64 off) const { return MB_LD_RING_U64(A.rng_ring + (off & (2 * u64(P.rng_window) - 1))); }
+  // deterministic mode: `off` is an offset into the cell's stream (staged in the ring);
+  // throughput mode: `off` is a counter (ctr_pack + draw number)
+  MB_FN u64 raw(u64 off) const {
+    if constexpr (kCtr) {
+      return mix64((off ^ key1) * 0x9E3779B97F4A7C15ull + key2);
+    } else {
+      return MB_LD_RING_U64(A.rng_ring + (off & (2 * u64(P.rng_window) - 1)));
+    }
+  }
+  MB_FN void ctr_keys() {
+    key1 = mix64(task.rng_state[0] ^ mix64(task.rng_state[1]));
+    key2 = mix64(task.rng_state[2] ^ mix64(task.rng_state[3]));
+  }
 
   // Phase timing: thread 0 charges the SM-clock cycles since the previous lap to phase `ph`.
   // (No-op in the CPU emulation.)
@@ -158,7 +208,7 @@ struct CellSim {
 
   // A serial reader of the raw stream used by the few inherently sequential samplers.
   struct Cursor {
-    const CellSim* sim;
+    const CellSimT* sim;
     u64 pos, limit;
     bool overrun;
     MB_FN u64 next() {
@@ -176,12 +226,20 @@ struct CellSim {
     }
   };
   MB_FN Cursor cursor(u64 pos, u64 limit) const { return Cursor{this, pos, limit, false}; }
+  // throughput mode: the private draw sequence of (epoch, phase, item)
+  MB_FN Cursor ctr_cursor(u64 epoch, u32 phase, u32 item) const {
+    const u64 c = ctr_pack(epoch, phase, item);
+    return Cursor{this, c, c + kCtrDrawsPerItem, false};
+  }
 
   // ------------------------------------------------------------------------------ RNG staging
   // Makes raw(o) valid for every o in [S.rng_pos, need_end). The stream is produced window by
   // window (W draws): generator thread g owns the l consecutive draws [g*l, (g+1)*l) of each
   // window and hops to the next window with a precomputed GF(2) matrix (T^W).
   MB_FN void rng_ensure(u64 need_end) {
+    if constexpr (!kCtr) rng_ensure_staged(need_end);  // throughput mode stages nothing
+  }
+  MB_FN void rng_ensure_staged(u64 need_end) {
     if (need_end > S.rng_pos + P.rng_window) {
       MB_REGION(cta, tid) {
         if (cta.leader(tid)) fault(kFaultRngWindow);
@@ -535,6 +593,26 @@ struct CellSim {
       }
     }
     cta.sync();
+    if constexpr (kCtr) {
+      MB_REGION(cta, tid) {
+        for (u32 i = tid; i < P.n_bar; i += cta.nt()) {
+          const double occ = D.bar_occupancy[i];
+          bool act = false;
+          if (occ != 0.0) act = bernoulli_raw(raw(ctr_pack(0, kDrInit, i)), occ);
+          A.bar_active[i] = act ? 1 : 0;
+        }
+        if (cta.leader(tid)) {
+          S.rng_pos = 0;
+          S.rng_generated = 0;
+          if (P.skip_burnin) {
+            S.num_active = P.n_lefs;
+            S.burnin_completed = 1;
+          }
+        }
+      }
+      cta.sync();
+      return;
+    }
     rng_bootstrap();
 
     // init_states: one Bernoulli(occupancy) per barrier whose occupancy is not 0
@@ -601,10 +679,11 @@ struct CellSim {
         MB_REGION(cta, tid) {
           if (cta.leader(tid)) {
             ++S.num_burnin_epochs;
-            Cursor c = cursor(S.rng_pos, S.rng_pos + 256);
+            Cursor c = kCtr ? ctr_cursor(S.num_burnin_epochs, kDrBurnin, 0)
+                            : cursor(S.rng_pos, S.rng_pos + 256);
             const u64 k = poisson_serial(c, P.lef_binding_rate_burnin);
             if (c.overrun) fault(kFaultSerialDraws);
-            S.rng_pos = c.pos;
+            if constexpr (!kCtr) S.rng_pos = c.pos;
             const u64 na = u64(S.num_active) + k;
             S.num_active = na < P.n_lefs ? static_cast<u32>(na) : P.n_lefs;
           }
@@ -688,6 +767,26 @@ struct CellSim {
     const u32 n = S.num_active;
     const u64 range = u64(P.end - 1) - u64(P.start);
     const u64 bucket = range ? uniform_int_bucket(range) : 1;
+    if constexpr (kCtr) {
+      // every unbound LEF draws its position from its own sequence: one pass, no repair
+      MB_REGION(cta, tid) {
+        for (u32 i = tid; i < n; i += cta.nt()) {
+          if (A.ep[i] != kUnbound) continue;
+          u64 r = 0;
+          if (range != 0) {
+            Cursor c = ctr_cursor(S.epoch, kDrBind, i);
+            do {
+              r = c.next() / bucket;
+            } while (r > range && !c.overrun);
+            if (c.overrun) fault(kFaultSerialDraws);
+          }
+          A.rev[i] = A.fwd[i] = static_cast<u32>(u64(P.start) + r);
+          A.ep[i] = static_cast<u32>(S.epoch);
+        }
+      }
+      cta.sync();
+      return;
+    }
     PerThread<u64> cnt(cta.nt());
     MB_REGION(cta, tid) {
       u32 lo, hi;
@@ -1116,6 +1215,30 @@ struct CellSim {
   // stride; the first event that consumes a different number of draws re-bases the rest.
   MB_FN void sampling_events(u32 n_events, int kind) {
     if (n_events == 0) return;
+    if constexpr (kCtr) {
+      // event e of this kind reads its own sequence and registers at once
+      MB_REGION(cta, tid) {
+        u32 registered = 0;
+        for (u32 e = tid; e < n_events; e += cta.nt()) {
+          u32 b1, b2;
+          const u64 o = ctr_pack(S.epoch, kDrLoop + static_cast<u32>(kind), e);
+          sampling_event(o, kind, o + kCtrDrawsPerItem, &b1, &b2);
+          if (b1 == kUnbound) continue;
+          if (kind == 2) {
+            if (K.occ1d) {
+              MB_ATOMIC_ADD_U64(K.occ1d + b1, u64(1));
+              MB_ATOMIC_ADD_U64(K.occ1d + b2, u64(1));
+            }
+          } else {
+            band_increment(b1, b2);
+            ++registered;
+          }
+        }
+        if (registered) MB_ATOMIC_ADD_U64(&S.tmp_u64[1], u64(registered));
+      }
+      cta.sync();
+      return;
+    }
     const u32 n_act = S.num_active;
     const u32 base_draws = n_act > 1 ? 1u : 0u;
     const u32 stride = base_draws + (P.noisify ? 2u : 0u) + (kind == 1 ? 2u : 0u);
@@ -1195,11 +1318,11 @@ struct CellSim {
         } else if (!need_binomial) {
           nloop = 0;
         } else {
-          Cursor c = cursor(S.rng_pos, S.rng_pos + 256);
+          Cursor c = kCtr ? ctr_cursor(S.epoch, kDrSplit, 0) : cursor(S.rng_pos, S.rng_pos + 256);
           nloop = static_cast<u64>(
               binomial_serial(c, static_cast<i64>(nev), 1.0 / (P.tad_to_loop + 1.0)));
           if (c.overrun) fault(kFaultSerialDraws);
-          S.rng_pos = c.pos;
+          if constexpr (!kCtr) S.rng_pos = c.pos;
         }
         S.tmp_u32[1] = static_cast<u32>(nloop);
         S.tmp_u64[1] = 0;
@@ -1241,6 +1364,30 @@ struct CellSim {
   // draws all rev moves and then all fwd moves). The fast ziggurat path uses exactly one draw;
   // the rare slow paths are evaluated speculatively and stitched into the stream by the leader.
   MB_FN void draw_normal_moves(u32 items, u32 n_rev, double rev_speed, double fwd_speed) {
+    if constexpr (kCtr) {
+      // one full ziggurat sampler per item on the item's own sequence (fast and slow paths alike)
+      sub_begin();
+      const double rsd = P.rev_std, fsd = P.fwd_std;
+      MB_REGION(cta, tid) {
+        bool over = false;
+        for (u32 i = tid; i < items; i += cta.nt()) {
+          Cursor c = ctr_cursor(S.epoch, kDrMoves, i);
+          const double z = unit_normal_serial(c);
+          if (c.overrun) fault(kFaultSerialDraws);
+          u32 mv;
+          if (i < n_rev) {
+            A.rm[i] = mv = move_from_z(z, rev_speed, rsd);
+          } else {
+            A.fm[i - n_rev] = mv = move_from_z(z, fwd_speed, fsd);
+          }
+          over |= mv > P.move_bound;
+        }
+        if (over) S.move_bound_hit = 1;
+      }
+      cta.sync();
+      sub_lap(kPhMvFinal);
+      return;
+    }
     const u32 slack = items / 8 + 64;
     const u32 span = items + slack;  // offsets examined
     const u64 base = S.rng_pos;
@@ -1698,10 +1845,10 @@ struct CellSim {
   MB_FN void next_barrier_states() {
     if (P.n_bar == 0) return;
     rng_ensure(S.rng_pos + P.n_bar);
-    const u64 base = S.rng_pos;
+    const u64 base = kCtr ? ctr_pack(S.epoch, kDrBarriers, 0) : S.rng_pos;
     MB_REGION(cta, tid) {
       for (u32 i = tid; i < P.n_bar; i += cta.nt()) {
-        const double u = canonical_raw(raw(base + i));
+        const double u = canonical_raw(raw(kCtr ? base + (u64(i) << 8) : base + i));
         const bool act = A.bar_active[i] != 0;
         if (!act && u > D.bar_stp_inactive[i]) {
           A.bar_active[i] = 1;
@@ -1711,10 +1858,12 @@ struct CellSim {
       }
     }
     cta.sync();  // every thread has read `base` before the leader moves the stream position
-    MB_REGION(cta, tid) {
-      if (cta.leader(tid)) S.rng_pos = base + P.n_bar;
+    if constexpr (!kCtr) {
+      MB_REGION(cta, tid) {
+        if (cta.leader(tid)) S.rng_pos = base + P.n_bar;
+      }
+      cta.sync();
     }
-    cta.sync();
   }
 
   MB_FN bool bar_blocks_rev(u32 b) const { return (D.bar_dir_rev[b >> 5] >> (b & 31)) & 1u; }
@@ -1814,6 +1963,24 @@ struct CellSim {
           if ((brev ? pmaj : pmin) == 1.0 && lef_bar_candidate_rev(b, j0, &unit, &nohint_r))
             MB_ATOMIC_MAX_U32(&A.rc[unit], coll_make(b, tmp_ev));
           if ((brev ? pmin : pmaj) == 1.0 && lef_bar_candidate_fwd(b, jend, &unit, &nohint_f))
+            MB_ATOMIC_MAX_U32(&A.fc[unit], coll_make(nb - 1 - b, tmp_ev));
+        }
+      }
+      cta.sync();
+    } else if constexpr (kCtr) {
+      // fractional pblock: trial (barrier b, direction) reads draw 2b / 2b+1 of this epoch
+      MB_REGION(cta, tid) {
+        for (u32 b = tid; b < nb; b += cta.nt()) {
+          if (!A.bar_active[b]) continue;
+          const bool brev = bar_blocks_rev(b);
+          const double pr = brev ? pmaj : pmin, pf = brev ? pmin : pmaj;
+          u32 unit;
+          u32 nohint_r = 0xFFFFFFFFu, nohint_f = 0xFFFFFFFFu;
+          if (pr != 0.0 && lef_bar_candidate_rev(b, j0, &unit, &nohint_r) &&
+              (pr == 1.0 || bernoulli_raw(raw(ctr_pack(S.epoch, kDrLefBar, 2 * b)), pr)))
+            MB_ATOMIC_MAX_U32(&A.rc[unit], coll_make(b, tmp_ev));
+          if (pf != 0.0 && lef_bar_candidate_fwd(b, jend, &unit, &nohint_f) &&
+              (pf == 1.0 || bernoulli_raw(raw(ctr_pack(S.epoch, kDrLefBar, 2 * b + 1)), pf)))
             MB_ATOMIC_MAX_U32(&A.fc[unit], coll_make(nb - 1 - b, tmp_ev));
         }
       }
@@ -1962,6 +2129,23 @@ struct CellSim {
     // collide) and none when 1 - bypass == 0 (Bernoulli(0) never draws and never succeeds)
     if (P.p_bypass != 0.0 && 1.0 - P.p_bypass == 0.0) return;
     const bool draws = P.p_bypass != 0.0;
+    if constexpr (kCtr) {
+      // the trial of the pair found at rev rank n5 + m reads draw m of this epoch: no counting pass
+      MB_REGION(cta, tid) {
+        u32 lo, hi;
+        chunk(tid, M, &lo, &hi);
+        u32 hint = 0xFFFFFFFFu;
+        for (u32 m = lo; m < hi; ++m) {
+          u32 r, f;
+          if (!primary_pair(n5 + m, n5, i2, &r, &f, &hint)) continue;
+          if (draws && !bernoulli_raw(raw(ctr_pack(S.epoch, kDrPrimary, m)), 1.0 - P.p_bypass))
+            continue;
+          primary_apply(r, f);
+        }
+      }
+      cta.sync();
+      return;
+    }
     PerThread<u64> cnt(cta.nt());
     u64 total = 0;
     if (draws) {
@@ -2138,6 +2322,21 @@ struct CellSim {
       ++c;
     }
   }
+  // Throughput mode: the same walk also runs every candidate's trial -- the candidate at scan
+  // position m of pass `dir` reads draw (dir, m) of this epoch -- and files the failures under the
+  // candidate number (the deterministic mode files them under the draw number instead).
+  MB_FN void sec_number_firsts_and_draw(const SecDir& d, int tid, u32 c, u32 dir, u32* firstc,
+                                        u32* fail) const {
+    u32 lo, hi;
+    chunk(tid, d.M, &lo, &hi);
+    for (u32 m = lo; m < hi; ++m) {
+      if (!((d.cand[m >> 5] >> (m & 31)) & 1u)) continue;
+      if ((d.head1[m >> 5] >> (m & 31)) & 1u) MB_ATOMIC_OR_U32(&firstc[c >> 5], 1u << (c & 31));
+      if (!bernoulli_raw(raw(ctr_pack(S.epoch, kDrSecondary, (dir << 24) | m)), 1.0 - P.p_bypass))
+        MB_ATOMIC_OR_U32(&fail[c >> 5], 1u << (c & 31));
+      ++c;
+    }
+  }
 
   // mode 0: outcomes from the reached / ok bitmaps; 1: every candidate stalls (bypass == 0);
   // 2: trials never succeed and draw nothing (bypass == 1): only run heads are reached.
@@ -2225,11 +2424,18 @@ struct CellSim {
     if (draws) {
       rng_ensure(S.rng_pos + npot);
       MB_REGION(cta, tid) {
-        sec_number_firsts(R, tid, static_cast<u32>(cnt[tid] & 0xFFFFFFFFu), bits_firstc);
-        sec_number_firsts(F, tid, npot_r + static_cast<u32>(cnt[tid] >> 32), bits_firstc);
-        for (u32 d = tid; d < npot; d += cta.nt()) {
-          if (!bernoulli_raw(raw(S.rng_pos + d), 1.0 - P.p_bypass))
-            MB_ATOMIC_OR_U32(&bits_fail[d >> 5], 1u << (d & 31));
+        if constexpr (kCtr) {
+          sec_number_firsts_and_draw(R, tid, static_cast<u32>(cnt[tid] & 0xFFFFFFFFu), 0u,
+                                     bits_firstc, bits_fail);
+          sec_number_firsts_and_draw(F, tid, npot_r + static_cast<u32>(cnt[tid] >> 32), 1u,
+                                     bits_firstc, bits_fail);
+        } else {
+          sec_number_firsts(R, tid, static_cast<u32>(cnt[tid] & 0xFFFFFFFFu), bits_firstc);
+          sec_number_firsts(F, tid, npot_r + static_cast<u32>(cnt[tid] >> 32), bits_firstc);
+          for (u32 d = tid; d < npot; d += cta.nt()) {
+            if (!bernoulli_raw(raw(S.rng_pos + d), 1.0 - P.p_bypass))
+              MB_ATOMIC_OR_U32(&bits_fail[d >> 5], 1u << (d & 31));
+          }
         }
       }
       cta.sync();
@@ -2258,7 +2464,9 @@ struct CellSim {
           u32 Rm = __ballot_sync(0xffffffffu, can);
           u32 bad = 0;
           for (int it = 0; it < 34; ++it) {
-            const u32 dd = d + static_cast<u32>(__popc(Rm & lt));
+            // deterministic mode: the d-th draw belongs to the d-th REACHED candidate;
+            // throughput mode: every candidate owns its trial
+            const u32 dd = kCtr ? 32 * w + lane : d + static_cast<u32>(__popc(Rm & lt));
             const u32 fbit = (bits_fail[dd >> 5] >> (dd & 31)) & 1u;
             bad = __ballot_sync(0xffffffffu, ((Rm >> lane) & 1u) && fbit);
             const u32 Rn = __ballot_sync(0xffffffffu, can && (bad & range) == 0);
@@ -2283,7 +2491,8 @@ struct CellSim {
           u32 Rm = 0, OK = 0;
           for (u32 i = 0; i < lim; ++i) {
             const u32 reach = ((Fw >> i) & 1u) | alive;
-            alive = reach & ~(bits_fail[d >> 5] >> (d & 31)) & 1u;
+            const u32 dd = kCtr ? 32 * w + i : d;
+            alive = reach & ~(bits_fail[dd >> 5] >> (dd & 31)) & 1u;
             Rm |= reach << i;
             OK |= alive << i;
             d += reach;
@@ -2302,7 +2511,7 @@ struct CellSim {
       sec_apply<true>(R, tid, static_cast<u32>(cnt[tid] & 0xFFFFFFFFu), mode, bits_reached, bits_ok);
       sec_apply<false>(F, tid, npot_r + static_cast<u32>(cnt[tid] >> 32), mode, bits_reached,
                        bits_ok);
-      if (draws && cta.leader(tid)) S.rng_pos += S.tmp_u32[4];
+      if (!kCtr && draws && cta.leader(tid)) S.rng_pos += S.tmp_u32[4];
     }
     cta.sync();
     sub_lap(kPhSecApply);
@@ -2422,7 +2631,7 @@ struct CellSim {
     const double base_p = S.burnin_completed ? P.p_release : P.p_release_burnin;
     const bool draws = base_p != 0.0;
     if (draws) rng_ensure(S.rng_pos + n);
-    const u64 base = S.rng_pos;
+    const u64 base = kCtr ? ctr_pack(S.epoch, kDrRelease, 0) : S.rng_pos;
     MB_REGION(cta, tid) {
       for (u32 i = tid; i < n; i += cta.nt()) {
         u32 rev = A.rev[i] - A.rm[i];
@@ -2435,7 +2644,7 @@ struct CellSim {
           if (coll_is(fcol, kEvLefBar) && !bar_blocks_rev(coll_index(fcol))) ++hard;
           const double affinity =
               hard == 0 ? 1.0 : (hard == 1 ? 1.0 / P.soft_mult : 1.0 / P.hard_mult);
-          if (bernoulli_raw(raw(base + i), affinity * base_p)) {
+          if (bernoulli_raw(raw(kCtr ? base + (u64(i) << 8) : base + i), affinity * base_p)) {
             rev = kUnbound;
             fwd = kUnbound;
             ep = kUnbound;
@@ -2447,7 +2656,7 @@ struct CellSim {
       }
     }
     cta.sync();  // every thread has read `base` before the leader moves the stream position
-    if (draws) {
+    if (!kCtr && draws) {
       MB_REGION(cta, tid) {
         if (cta.leader(tid)) S.rng_pos = base + n;
       }
@@ -2513,6 +2722,7 @@ struct CellSim {
     const u64 t_begin = static_cast<u64>(clock64());
     t_last = t_begin;
 #endif
+    if constexpr (kCtr) ctr_keys();
     init_cell();
     lap(kPhInit);
     for (;;) {
@@ -2558,5 +2768,8 @@ struct CellSim {
     cta.sync();
   }
 };
+
+using CellSim = CellSimT<false>;            // deterministic mode (the reference's draw order)
+using CellSimThroughput = CellSimT<true>;   // throughput mode (counter-based draws)
 
 }  // namespace modle_b200

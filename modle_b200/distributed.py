@@ -107,7 +107,7 @@ class DeviceEngine:
     """Runs shards on one GPU through the device-resident C-ABI call; buffers are torch tensors
     (torch is the allocator / stream / collective plumbing here, nothing more)."""
 
-    def __init__(self, device=0, num_streams=3):
+    def __init__(self, device=0, num_streams=3, rng_mode=0):
         import torch
 
         from .simulation import Context
@@ -115,7 +115,7 @@ class DeviceEngine:
         self.torch = torch
         self.device = torch.device("cuda", device)
         torch.cuda.set_device(self.device)
-        self.ctx = Context(device)
+        self.ctx = Context(device, rng_mode)
         self.streams = [torch.cuda.Stream(device=self.device) for _ in range(max(1, num_streams))]
         self._next = 0
 

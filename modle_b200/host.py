@@ -57,6 +57,8 @@ def lib():
         L.modle_b200_init.argtypes = [C.POINTER(C.c_void_p), C.c_int]
         L.modle_b200_destroy.argtypes = [C.c_void_p]
         L.modle_b200_destroy.restype = None
+        L.modle_b200_set_rng_mode.argtypes = [C.c_void_p, C.c_int]
+        L.modle_b200_get_rng_mode.argtypes = [C.c_void_p]
         L.modle_b200_synchronize.argtypes = [C.c_void_p]
         L.modle_b200_phase_cycles.argtypes = [C.c_void_p, u64p, C.c_size_t, C.c_int]
         L.modle_b200_kernel_launches.argtypes = [C.c_void_p]
@@ -112,6 +114,7 @@ EXPORTED_SYMBOLS = [
     "modle_b200_rng_seed", "modle_b200_rng_next", "modle_b200_rng_jump",
     "modle_b200_stp_active_from_occupancy", "modle_b200_occupancy_from_stp",
     "modle_b200_make_cell_tasks", "modle_b200_init", "modle_b200_destroy",
+    "modle_b200_set_rng_mode", "modle_b200_get_rng_mode",
     "modle_b200_simulate_interval", "modle_b200_simulate_interval_logged",
     "modle_b200_simulate_interval_device",
     "modle_b200_synchronize", "modle_b200_snapshot_cell", "modle_b200_register_contacts_device",

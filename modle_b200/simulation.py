@@ -78,13 +78,28 @@ class GenomicInterval:
         return abi.Interval(self.chrom_size, self.start, self.end, self.num_lefs)
 
 
+RNG_REFERENCE_ORDER = 0  # MODLE_B200_RNG_REFERENCE_ORDER
+RNG_COUNTER = 1          # MODLE_B200_RNG_COUNTER ("throughput mode")
+
+
 class Context:
     """RAII wrapper of modle_b200_context (one per GPU)."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, rng_mode=0):
         self._h = C.c_void_p()
         host.check(host.lib().modle_b200_init(C.byref(self._h), int(device)))
         self.device = int(device)
+        if rng_mode:
+            self.set_rng_mode(rng_mode)
+
+    def set_rng_mode(self, mode):
+        """RNG_REFERENCE_ORDER (0, default): deterministic mode, bit-identical to the reference
+        algorithm; RNG_COUNTER (1): throughput mode (see modle_b200_set_rng_mode)."""
+        host.check(host.lib().modle_b200_set_rng_mode(self._h, int(mode)))
+
+    @property
+    def rng_mode(self):
+        return int(host.lib().modle_b200_get_rng_mode(self._h))
 
     def close(self):
         if self._h:
@@ -244,6 +259,7 @@ class Simulation:
     device: int = 0
     rank: int = 0
     world_size: int = 1
+    rng_mode: int = RNG_REFERENCE_ORDER  # RNG_COUNTER selects the throughput mode
     intervals: list = field(default_factory=list)
     _ctxs: list = field(default_factory=list, repr=False)
     _engine: object = field(default=None, repr=False)
@@ -301,7 +317,7 @@ class Simulation:
             return self.intervals
         nw = max(1, min(num_workers, len(todo)))
         while len(self._ctxs) < nw:  # contexts (streams, device buffers) persist across calls
-            self._ctxs.append(Context(self.device))
+            self._ctxs.append(Context(self.device, self.rng_mode))
         if nw == 1:
             for idx in todo:
                 one(self._ctxs[0], idx)
@@ -342,7 +358,7 @@ class Simulation:
 
         p = self.config.params
         if self._engine is None:
-            self._engine = distributed.DeviceEngine(self.device)
+            self._engine = distributed.DeviceEngine(self.device, rng_mode=self.rng_mode)
         out = distributed.run_sharded(self._engine, p, self.intervals, self.rank, self.world_size,
                                       dist)
         for idx, o in out.items():

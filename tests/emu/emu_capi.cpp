@@ -74,6 +74,19 @@ CellTaskDev to_task(const modle_b200_cell_task& t) {
 }
 
 thread_local std::string g_emu_error;
+thread_local int g_emu_rng_mode = MODLE_B200_RNG_REFERENCE_ORDER;
+
+// runs one cell in the selected mode (deterministic or throughput, see modle_b200_set_rng_mode)
+void run_cell(EmuCell& cell, const Sinks& K, int virtual_threads, const modle_b200_cell_task& t) {
+  Cta cta{&cell.shared->scratch, virtual_threads};
+  if (g_emu_rng_mode == MODLE_B200_RNG_COUNTER) {
+    CellSimThroughput sim{cell.kp, cell.D, cell.A, *cell.shared, K, cta, to_task(t)};
+    sim.run();
+  } else {
+    CellSim sim{cell.kp, cell.D, cell.A, *cell.shared, K, cta, to_task(t)};
+    sim.run();
+  }
+}
 
 }  // namespace
 
@@ -83,6 +96,8 @@ const char* emu_last_error() { return g_emu_error.c_str(); }
 
 // 0 ascending, 1 descending, 2 shuffled per region (cta.hpp: emu_thread_order)
 void emu_set_thread_order(int mode) { emu_thread_order() = mode; }
+// MODLE_B200_RNG_* of the calling thread's later emu_simulate_* / emu_snapshot_cell calls
+void emu_set_rng_mode(int mode) { g_emu_rng_mode = mode; }
 
 int emu_simulate_interval_logged(const modle_b200_sim_params* params,
                                  const modle_b200_interval* interval,
@@ -120,9 +135,7 @@ int emu_simulate_interval_logged(const modle_b200_sim_params* params,
     K.log = (log_out && log_cap) ? log_out + c * log_cap : nullptr;  // as k_simulate_cells does
     K.log_cap = static_cast<u32>(log_cap);
     if (cell.kp.stop_on_epochs || tasks[c].num_target_contacts != 0) {
-      Cta cta{&cell.shared->scratch, virtual_threads};
-      CellSim sim{cell.kp, cell.D, cell.A, *cell.shared, K, cta, to_task(tasks[c])};
-      sim.run();
+      run_cell(cell, K, virtual_threads, tasks[c]);
       st.num_contacts = cell.shared->num_contacts;
       st.num_epochs = cell.shared->epoch;
       st.num_burnin_epochs = cell.shared->num_burnin_epochs;
@@ -146,9 +159,7 @@ int emu_snapshot_cell(const modle_b200_sim_params* params, const modle_b200_inte
   std::vector<u64> occ(cell.kp.ncols, 0);
   u64 missed = 0;
   Sinks K{band.data(), occ.data(), &missed};
-  Cta cta{&cell.shared->scratch, virtual_threads};
-  CellSim sim{cell.kp, cell.D, cell.A, *cell.shared, K, cta, to_task(*task)};
-  sim.run();
+  run_cell(cell, K, virtual_threads, *task);
   const CellShared& S = *cell.shared;
   if (stats_out) {
     stats_out->num_contacts = S.num_contacts;
@@ -302,18 +313,44 @@ long long emu_sample_moves(const u64* state, size_t n, double speed, double sd, 
   modle_b200_cell_task t{};
   for (int i = 0; i < 4; ++i) t.rng_state[i] = state[i];
   cell.kp.rev_std = sd;
-  CellSim sim{cell.kp, cell.D, cell.A, *cell.shared, K, cta, to_task(t)};
-  sim.init_cell();
-  cell.shared->num_active = static_cast<u32>(n);
-  for (size_t i = 0; i < n; ++i) {
-    cell.A.rev[i] = cell.A.fwd[i] = 500000;
-    cell.A.ep[i] = 0;
+  auto go = [&](auto& sim) {
+    sim.init_cell();
+    cell.shared->num_active = static_cast<u32>(n);
+    for (size_t i = 0; i < n; ++i) {
+      cell.A.rev[i] = cell.A.fwd[i] = 500000;
+      cell.A.ep[i] = 0;
+    }
+    sim.draw_normal_moves(static_cast<u32>(n), static_cast<u32>(n), speed, speed);
+  };
+  if (g_emu_rng_mode == MODLE_B200_RNG_COUNTER) {
+    CellSimThroughput sim{cell.kp, cell.D, cell.A, *cell.shared, K, cta, to_task(t)};
+    sim.ctr_keys();
+    go(sim);
+  } else {
+    CellSim sim{cell.kp, cell.D, cell.A, *cell.shared, K, cta, to_task(t)};
+    go(sim);
   }
-  sim.draw_normal_moves(static_cast<u32>(n), static_cast<u32>(n), speed, speed);
   for (size_t i = 0; i < n; ++i) moves_out[i] = cell.A.rm[i];
   if (cell.shared->fault) return -100 - static_cast<long long>(cell.shared->fault);
   return static_cast<long long>(cell.shared->rng_pos);
 }
+
+// Throughput mode: the raw draw `k` of (epoch, phase, item) for the cell whose task carries PRNG
+// state `state` (sim_core.hpp ctr_pack / raw), and the mixer on its own.
+u64 emu_ctr_draw(const u64* state, u64 epoch, u32 phase, u32 item, u32 k) {
+  KernelParams kp{};
+  IntervalData D{};
+  CellArrays A{};
+  auto S = std::make_unique<CellShared>();
+  Sinks K{};
+  Cta cta{&S->scratch, 1};
+  CellTaskDev t{};
+  for (int i = 0; i < 4; ++i) t.rng_state[i] = state[i];
+  CellSimThroughput sim{kp, D, A, *S, K, cta, t};
+  sim.ctr_keys();
+  return sim.raw(ctr_pack(epoch, phase, item) + k);
+}
+u64 emu_mix64(u64 x) { return mix64(x); }
 
 // The kernel's collision-word helpers (sim_types.hpp), for the reference's encoding KATs.
 u32 emu_collision_word(u64 idx, u32 event) { return coll_make(static_cast<u32>(idx), event); }

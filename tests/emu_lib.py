@@ -58,6 +58,12 @@ def set_thread_order(mode):
     lib().emu_set_thread_order(int(mode))
 
 
+def set_rng_mode(mode):
+    """0: deterministic mode (reference draw order), 1: throughput mode (counter-based draws);
+    see modle_b200_set_rng_mode. Applies to the calling thread's later calls."""
+    lib().emu_set_rng_mode(int(mode))
+
+
 def _check(rc):
     if rc != 0:
         raise RuntimeError("emu: " + lib().emu_last_error().decode())
