@@ -448,6 +448,19 @@ inline int& emu_thread_order() {
   return mode;
 }
 
+// CTA barriers the device build would execute (explicit sync() calls plus the three inside every
+// block-wide collective): the emulation counts them so that the barrier cost of an epoch can be
+// compared between variants of the code without a GPU.
+inline u64& emu_barrier_count() {
+  static thread_local u64 n = 0;
+  return n;
+}
+
+inline u64* emu_phase_barriers() {  // per phase of the epoch loop (sim_types.hpp kPh*)
+  static thread_local u64 n[64] = {};
+  return n;
+}
+
 struct Cta {
   CtaScratch* scr;
   int nthreads;
@@ -473,10 +486,11 @@ struct Cta {
   int first() const { return 0; }
   int step() const { return 1; }
   bool leader(int tid) const { return tid == 0; }
-  void sync() const {}
+  void sync() const { ++emu_barrier_count(); }
   u32 div_nt(u32 x) const { return x / static_cast<u32>(nthreads); }
 
   u64 exscan_sum(PerThread<u64>& v) const {
+    emu_barrier_count() += 3;
     u64 acc = 0;
     for (int t = 0; t < nthreads; ++t) {
       const u64 x = v[t];
@@ -486,16 +500,19 @@ struct Cta {
     return acc;
   }
   u64 reduce_max(const PerThread<u64>& v) const {
+    emu_barrier_count() += 3;
     u64 m = 0;
     for (int t = 0; t < nthreads; ++t) m = std::max(m, v[t]);
     return m;
   }
   u64 reduce_min(const PerThread<u64>& v) const {
+    emu_barrier_count() += 3;
     u64 m = ~u64(0);
     for (int t = 0; t < nthreads; ++t) m = std::min(m, v[t]);
     return m;
   }
   u64 reduce_sum(const PerThread<u64>& v) const {
+    emu_barrier_count() += 3;
     u64 acc = 0;
     for (int t = 0; t < nthreads; ++t) acc += v[t];
     return acc;
@@ -503,6 +520,7 @@ struct Cta {
   // same association order as the device: xor-butterfly inside each group of 32, then groups
   // left to right
   double reduce_sum_f64(const PerThread<double>& v) const {
+    emu_barrier_count() += 3;
     double total = 0.0;
     for (int w = 0; w * 32 < nthreads; ++w) {
       double lane[32];
@@ -517,6 +535,7 @@ struct Cta {
     return total;
   }
   void exscan_minplus(PerThread<MinPlus>& v) const {
+    emu_barrier_count() += 3;
     MinPlus acc = minplus_identity();
     for (int t = 0; t < nthreads; ++t) {
       const MinPlus x = v[t];
@@ -527,12 +546,15 @@ struct Cta {
   void exscan_minplus2(PerThread<MinPlus>& a, PerThread<MinPlus>& b) const {
     exscan_minplus(a);
     exscan_minplus(b);
+    emu_barrier_count() -= 3;  // one collective on the device
   }
   void exscan_secop2(PerThread<SecOp>& a, PerThread<SecOp>& b) const {
     exscan_secop(a);
     exscan_secop(b);
+    emu_barrier_count() -= 3;  // one collective on the device
   }
   void exscan_secop(PerThread<SecOp>& v) const {
+    emu_barrier_count() += 3;
     SecOp acc = secop_identity();
     for (int t = 0; t < nthreads; ++t) {
       const SecOp x = v[t];

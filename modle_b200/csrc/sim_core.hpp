@@ -202,7 +202,10 @@ struct CellSimT {
       t_last = now;
     }
 #else
-    (void)ph;
+    // the emulation charges CTA barriers instead of cycles (scripts/barriers_per_epoch.py)
+    const u64 now = emu_barrier_count();
+    emu_phase_barriers()[ph] += now - t_last;
+    t_last = now;
 #endif
   }
 
@@ -2723,6 +2726,9 @@ struct CellSimT {
     t_last = t_begin;
 #endif
     if constexpr (kCtr) ctr_keys();
+#if !MB_DEVICE_BUILD
+    t_last = emu_barrier_count();
+#endif
     init_cell();
     lap(kPhInit);
     for (;;) {

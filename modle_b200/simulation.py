@@ -11,6 +11,7 @@ C ABI (include/modle_b200.h). Names follow the reference (Config fields, Genomic
 run_simulate); there is no CPU fallback.
 """
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -85,10 +86,12 @@ RNG_COUNTER = 1          # MODLE_B200_RNG_COUNTER ("throughput mode")
 class Context:
     """RAII wrapper of modle_b200_context (one per GPU)."""
 
-    def __init__(self, device=0, rng_mode=0):
+    def __init__(self, device=0, rng_mode=None):
         self._h = C.c_void_p()
         host.check(host.lib().modle_b200_init(C.byref(self._h), int(device)))
         self.device = int(device)
+        if rng_mode is None:  # measurement knob for the scripts/ (DESIGN.md 6)
+            rng_mode = int(os.environ.get("MODLE_B200_RNG_MODE", "0"))
         if rng_mode:
             self.set_rng_mode(rng_mode)
 

@@ -26,6 +26,6 @@ def product_lib():
 def gpu_ctx(product_lib):
     from modle_b200.simulation import Context
 
-    ctx = Context(0)
+    ctx = Context(0, rng_mode=0)
     yield ctx
     ctx.close()

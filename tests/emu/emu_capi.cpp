@@ -96,6 +96,18 @@ const char* emu_last_error() { return g_emu_error.c_str(); }
 
 // 0 ascending, 1 descending, 2 shuffled per region (cta.hpp: emu_thread_order)
 void emu_set_thread_order(int mode) { emu_thread_order() = mode; }
+// CTA barriers the device build would have executed in this thread's calls so far (cta.hpp)
+u64 emu_barrier_count_get(int reset) {
+  const u64 n = emu_barrier_count();
+  if (reset) emu_barrier_count() = 0;
+  return n;
+}
+void emu_phase_barriers_get(u64* out, int n, int reset) {
+  for (int i = 0; i < n && i < 64; ++i) {
+    out[i] = emu_phase_barriers()[i];
+    if (reset) emu_phase_barriers()[i] = 0;
+  }
+}
 // MODLE_B200_RNG_* of the calling thread's later emu_simulate_* / emu_snapshot_cell calls
 void emu_set_rng_mode(int mode) { g_emu_rng_mode = mode; }
 

@@ -64,6 +64,21 @@ def set_rng_mode(mode):
     lib().emu_set_rng_mode(int(mode))
 
 
+def barrier_count(reset=True):
+    """CTA barriers the device build would have executed in this thread's emulation calls."""
+    L = lib()
+    L.emu_barrier_count_get.restype = C.c_uint64
+    return int(L.emu_barrier_count_get(1 if reset else 0))
+
+
+def phase_barriers(reset=True):
+    """{phase name: CTA barriers} of this thread's emulation calls (the emulation's counterpart
+    of modle_b200_phase_cycles)."""
+    out = (C.c_uint64 * len(host.PHASE_NAMES))()
+    lib().emu_phase_barriers_get(out, len(host.PHASE_NAMES), 1 if reset else 0)
+    return dict(zip(host.PHASE_NAMES, [int(x) for x in out]))
+
+
 def _check(rc):
     if rc != 0:
         raise RuntimeError("emu: " + lib().emu_last_error().decode())
