@@ -40,3 +40,25 @@ def stratum_adjusted_correlation(b1, b2, nrows, ncols, max_d=None):
         num += w * rho
         den += w
     return num / den if den else float("nan")
+
+
+def stripe_pearson(b1, b2, nrows, ncols, direction="vertical"):
+    """Per-bin Pearson correlation of matching stripes of two band matrices, the `modle_tools
+    eval --metric pearson` definition (src/modle_tools/eval.cpp:460-470 fills one buffer of nrows
+    pixels per bin with unsafe_get_column / unsafe_get_row and correlates the two buffers):
+    vertical stripe of bin i = pixels (i - d, i), horizontal = pixels (i, i + d), d < nrows.
+    Stripes without variance in either matrix give NaN (ignored by the callers' nanmedian)."""
+    A = np.asarray(b1[:nrows * ncols], dtype=np.float64).reshape(ncols, nrows)
+    B = np.asarray(b2[:nrows * ncols], dtype=np.float64).reshape(ncols, nrows)
+    if direction == "horizontal":  # pixel (i, i + d) is stored in column i + d at row d
+        def rows(M):
+            H = np.zeros_like(M)
+            for d in range(nrows):
+                H[:ncols - d, d] = M[d:, d]
+            return H
+        A, B = rows(A), rows(B)
+    a = A - A.mean(axis=1, keepdims=True)
+    b = B - B.mean(axis=1, keepdims=True)
+    den = np.sqrt((a * a).sum(axis=1) * (b * b).sum(axis=1))
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return (a * b).sum(axis=1) / den

@@ -10,6 +10,8 @@ within 12.7 %, SCC 0.467 - 0.471, KS p >= 0.06):
   * per-diagonal mean: within 5 % for diagonals holding >= 1e4 contacts
   * per-diagonal variance: within 20 % for the same diagonals
   * SCC(gpu, oracle) not more than 0.01 below SCC(oracle, oracle')
+  * median per-stripe Pearson (the `modle_tools eval` definition, vertical and horizontal
+    stripes; 0.965 +- 0.0003 over oracle seed pairs) not more than 0.005 below the oracle pair's
   * burn-in epochs: two-sample KS test p > 0.001
 """
 import numpy as np
@@ -17,7 +19,7 @@ import pytest
 
 from common import make_case
 from oracle import pyoracle
-from stats_eval import per_diagonal_mean_var, stratum_adjusted_correlation
+from stats_eval import per_diagonal_mean_var, stratum_adjusted_correlation, stripe_pearson
 
 pytestmark = pytest.mark.gpu
 
@@ -51,6 +53,10 @@ def test_independent_seeds_are_statistically_equivalent(gpu_ctx):
     scc_oo = stratum_adjusted_correlation(ora2[0], ora3[0], nrows, ncols, max_d=200)
     assert scc_go > scc_oo - 0.01, (scc_go, scc_oo)
     assert scc_go > 0.4  # barriers leave a shared structure on top of the sampling noise
+    for direction in ("vertical", "horizontal"):  # per-stripe Pearson of `modle_tools eval`
+        r_go = np.nanmedian(stripe_pearson(gpu[0], ora2[0], nrows, ncols, direction))
+        r_oo = np.nanmedian(stripe_pearson(ora2[0], ora3[0], nrows, ncols, direction))
+        assert r_go > r_oo - 0.005, (direction, r_go, r_oo)
 
     ks = ks_2samp(gpu[2]["num_burnin_epochs"], ora2[2]["num_burnin_epochs"])
     assert ks.pvalue > 0.001, ks

@@ -15,7 +15,7 @@ import emu_lib
 from common import make_case, results_equal
 from modle_b200 import host
 from oracle import pyoracle
-from stats_eval import per_diagonal_mean_var, stratum_adjusted_correlation
+from stats_eval import per_diagonal_mean_var, stratum_adjusted_correlation, stripe_pearson
 
 M64 = (1 << 64) - 1
 GOLDEN = 0x9E3779B97F4A7C15
@@ -199,6 +199,11 @@ def test_statistically_equivalent_to_the_oracle(throughput):
     scc_oo = stratum_adjusted_correlation(ora2[0], ora3[0], nrows, ncols, max_d=200)
     assert scc_to > scc_oo - 0.01, (scc_to, scc_oo)
     assert scc_to > 0.4
+    # per-stripe Pearson as `modle_tools eval` computes it: medians within 0.005 of the floor
+    for direction in ("vertical", "horizontal"):
+        r_to = np.nanmedian(stripe_pearson(thr[0], ora2[0], nrows, ncols, direction))
+        r_oo = np.nanmedian(stripe_pearson(ora2[0], ora3[0], nrows, ncols, direction))
+        assert r_to > r_oo - 0.005, (direction, r_to, r_oo)
 
     assert ks_2samp(thr[2]["num_burnin_epochs"], ora2[2]["num_burnin_epochs"]).pvalue > 0.001
     assert ks_2samp(thr[2]["num_epochs"], ora2[2]["num_epochs"]).pvalue > 0.001
@@ -207,3 +212,34 @@ def test_statistically_equivalent_to_the_oracle(throughput):
     r = np.corrcoef(thr[1].astype(np.float64), ora2[1].astype(np.float64))[0, 1]
     r_oo = np.corrcoef(ora3[1].astype(np.float64), ora2[1].astype(np.float64))[0, 1]
     assert r > r_oo - 0.02, (r, r_oo)
+
+
+def test_stripe_pearson_matches_a_pixel_by_pixel_loop():
+    rng = np.random.default_rng(3)
+    nrows, ncols = 5, 23
+    b1 = rng.integers(0, 50, nrows * ncols + 1).astype(np.uint32)
+    b2 = rng.integers(0, 50, nrows * ncols + 1).astype(np.uint32)
+    for b in (b1, b2):  # pixels above the first row of the matrix do not exist
+        for j in range(ncols):
+            for d in range(nrows):
+                if d > j:
+                    b[j * nrows + d] = 0
+
+    def get(b, i, j):  # ContactMatrixDense::unsafe_get (contact_matrix_dense_impl.hpp)
+        if i > j:
+            i, j = j, i
+        return float(b[j * nrows + (j - i)]) if j - i < nrows and j < ncols else 0.0
+
+    for direction in ("vertical", "horizontal"):
+        got = stripe_pearson(b1, b2, nrows, ncols, direction)
+        for i in range(ncols):
+            if direction == "vertical":
+                x = [get(b1, i - d, i) if i >= d else 0.0 for d in range(nrows)]
+                y = [get(b2, i - d, i) if i >= d else 0.0 for d in range(nrows)]
+            else:
+                x = [get(b1, i, i + d) for d in range(nrows)]
+                y = [get(b2, i, i + d) for d in range(nrows)]
+            if np.std(x) == 0 or np.std(y) == 0:
+                assert np.isnan(got[i])
+            else:
+                assert abs(got[i] - np.corrcoef(x, y)[0, 1]) < 1e-12

@@ -11,7 +11,7 @@ import pytest
 import emu_lib
 from common import make_case, results_equal
 from oracle import pyoracle
-from stats_eval import per_diagonal_mean_var, stratum_adjusted_correlation
+from stats_eval import per_diagonal_mean_var, stratum_adjusted_correlation, stripe_pearson
 from test_gpu_parity import CASES
 
 pytestmark = pytest.mark.gpu
@@ -92,6 +92,10 @@ def test_statistically_equivalent_to_the_oracle(thr_ctx):
     scc_oo = stratum_adjusted_correlation(ora2[0], ora3[0], nrows, ncols, max_d=200)
     assert scc_go > scc_oo - 0.01, (scc_go, scc_oo)
     assert scc_go > 0.4
+    for direction in ("vertical", "horizontal"):  # per-stripe Pearson of `modle_tools eval`
+        r_go = np.nanmedian(stripe_pearson(gpu[0], ora2[0], nrows, ncols, direction))
+        r_oo = np.nanmedian(stripe_pearson(ora2[0], ora3[0], nrows, ncols, direction))
+        assert r_go > r_oo - 0.005, (direction, r_go, r_oo)
     assert ks_2samp(gpu[2]["num_burnin_epochs"], ora2[2]["num_burnin_epochs"]).pvalue > 0.001
 
 
