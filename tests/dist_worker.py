@@ -30,6 +30,7 @@ class EmuEngine:
         import emu_lib
 
         t = self.torch
+        emu_lib.set_rng_mode(int(os.environ.get("MODLE_B200_RNG_MODE", "0")))
         b, o, st, ms = emu_lib.simulate_interval(params, abi_interval, barriers, tasks)
         band += t.from_numpy(b.view(np.int32))
         occ[:len(o)] += t.from_numpy(o.view(np.int64))

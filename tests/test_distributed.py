@@ -61,6 +61,35 @@ def _free_port():
         return s.getsockname()[1]
 
 
+def test_run_sharded_world2_gloo_throughput_mode_is_split_invariant(tmp_path):
+    """Throughput mode: a cell's result depends on its task only, so the sharded world-2 run
+    (chrA's cells split 2 + 4 over the ranks, summed with one reduce) equals the unsharded one."""
+    import emu_lib
+    from dist_worker import make_genome
+    from modle_b200 import host
+
+    port = _free_port()
+    env = dict(os.environ, MODLE_B200_RNG_MODE="1")
+    procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "dist_worker.py"), str(r), "2",
+                               str(port), str(tmp_path), "1"], env=env) for r in range(2)]
+    for pr in procs:
+        assert pr.wait(timeout=600) == 0
+    res = [np.load(tmp_path / f"rank{r}.npz") for r in range(2)]
+    p, genome = make_genome()
+    emu_lib.set_rng_mode(1)
+    try:
+        for idx, (name, iv, bars) in enumerate(genome):
+            if len(bars) == 0:
+                continue
+            tasks = host.make_cell_tasks(p, name, iv)
+            band, occ, stats, missed = emu_lib.simulate_interval(p, iv, bars, tasks)
+            root = int([r for r in res if f"band{idx}" in r][0][f"root{idx}"][0])
+            assert np.array_equal(res[root][f"band{idx}"], band), name
+            assert np.array_equal(res[root][f"occ{idx}"][:len(occ)], occ), name
+    finally:
+        emu_lib.set_rng_mode(0)
+
+
 @pytest.mark.parametrize("force_split", [False, True])
 def test_run_sharded_world2_gloo_matches_oracle(tmp_path, force_split):
     from dist_worker import make_genome
