@@ -8,7 +8,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmodle_b200.so")
 SOURCES = ["host.cpp", "genome.cpp", "kernels.cu", "pixels.cu"]
 HEADERS = ["cta.hpp", "sim_types.hpp", "sim_core.hpp", "launch_prep.hpp", "host_rng.hpp",
-           "status.hpp", "context.hpp", os.path.join("..", "..", "include", "modle_b200.h")]
+           "status.hpp", "context.hpp", "ziggurat_tables.inc", os.path.join("..", "..", "include", "modle_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -16,40 +16,23 @@
 namespace modle_b200 {
 
 // Ziggurat tables of Boost.Random's unit normal (128 layers) and unit exponential (256 layers)
-// distributions, rebuilt from the standard construction (boost/random/normal_distribution.hpp
-// and exponential_distribution.hpp hold them as literals; those headers are not available here,
-// see DESIGN.md "third-party arithmetic").
+// distributions. boost/random/normal_distribution.hpp and exponential_distribution.hpp hold them
+// as 20-digit literals of the exact solution of the ziggurat equations; those headers are not
+// available here, so scripts/make_ziggurat_tables.py recomputes the solution with 60 digits and
+// writes the same 20-digit literals (the leading entries are pinned by tests/test_oracle_kats.py).
+namespace zigdata {
+#include "ziggurat_tables.inc"
+}  // namespace zigdata
 struct ZigguratTables {
   double nx[129], ny[129], ex[257], ey[257];
   ZigguratTables() {
-    {
-      const long double r = 3.442619855899L, v = 9.91256303526217e-3L;
-      long double x[129];
-      x[0] = v / std::exp(-0.5L * r * r);
-      x[1] = r;
-      for (int i = 2; i < 128; ++i)
-        x[i] = std::sqrt(-2.0L * std::log(v / x[i - 1] + std::exp(-0.5L * x[i - 1] * x[i - 1])));
-      x[128] = 0.0L;
-      for (int i = 0; i <= 128; ++i) {
-        nx[i] = static_cast<double>(x[i]);
-        ny[i] = static_cast<double>(std::exp(-0.5L * x[i] * x[i]));
-      }
-      ny[0] = 0.0;
-      ny[128] = 1.0;
+    for (int i = 0; i <= 128; ++i) {
+      nx[i] = zigdata::kZigNormalX[i];
+      ny[i] = zigdata::kZigNormalY[i];
     }
-    {
-      const long double r = 7.69711747013104972L, v = 3.949659822581572e-3L;
-      long double x[257];
-      x[0] = v / std::exp(-r);
-      x[1] = r;
-      for (int i = 2; i < 256; ++i) x[i] = -std::log(v / x[i - 1] + std::exp(-x[i - 1]));
-      x[256] = 0.0L;
-      for (int i = 0; i <= 256; ++i) {
-        ex[i] = static_cast<double>(x[i]);
-        ey[i] = static_cast<double>(std::exp(-x[i]));
-      }
-      ey[0] = 0.0;
-      ey[256] = 1.0;
+    for (int i = 0; i <= 256; ++i) {
+      ex[i] = zigdata::kZigExpX[i];
+      ey[i] = zigdata::kZigExpY[i];
     }
   }
 };

@@ -14,9 +14,14 @@
 //   - XXH3-64 with seed: pinned against the python `xxhash` package in tests/.
 //   - bernoulli / uniform_int / generate_canonical / uniform_01 / normal (ziggurat) /
 //     exponential (ziggurat) / poisson (inversion + PTRD) / binomial (inversion + BTRD):
-//     Boost.Random algorithms, restated from memory of boost/random/*.hpp. The ziggurat tables
-//     are regenerated from the standard construction (may differ from Boost's literals in the
-//     last ulp). No in-tree test of the reference pins these; see DESIGN.md.
+//     Boost.Random algorithms, restated from memory of boost/random/*.hpp. No in-tree test of
+//     the reference pins these; see DESIGN.md.
+//   - ziggurat tables: Boost holds them as 20-digit literals of the EXACT solution of the
+//     ziggurat equations (not Marsaglia & Tsang's rounded r = 3.442619855899);
+//     scripts/make_ziggurat_tables.py recomputes that solution with 60 digits and writes the same
+//     20-digit literals into ziggurat_tables.inc; the leading entries (3.7130862467403632609,
+//     3.4426198558966521214, ... / 8.6971174701310497140, 7.6971174701310497140, ...) are pinned
+//     in tests/test_oracle_kats.py.
 #pragma once
 #include <cmath>
 #include <cstddef>
@@ -150,40 +155,22 @@ inline std::pair<double, int> int_float_pair8(Rng& g) noexcept {
 }
 
 // --------------------------------------------------------------------------------------------
-// Ziggurat tables (regenerated; see header note).
+// Ziggurat tables (generated file; see header note).
 // --------------------------------------------------------------------------------------------
+namespace zigdata {
+#include "ziggurat_tables.inc"
+}  // namespace zigdata
 struct ZigTables {
   double nx[129], ny[129];  // normal, 128 layers
   double ex[257], ey[257];  // exponential, 256 layers
   ZigTables() {
-    {
-      const long double R = 3.442619855899L, V = 9.91256303526217e-3L;
-      long double x[129];
-      x[0] = V / std::exp(-0.5L * R * R);
-      x[1] = R;
-      for (int i = 2; i < 128; ++i)
-        x[i] = std::sqrt(-2.0L * std::log(V / x[i - 1] + std::exp(-0.5L * x[i - 1] * x[i - 1])));
-      x[128] = 0.0L;
-      for (int i = 0; i <= 128; ++i) {
-        nx[i] = static_cast<double>(x[i]);
-        ny[i] = static_cast<double>(std::exp(-0.5L * x[i] * x[i]));
-      }
-      ny[0] = 0.0;
-      ny[128] = 1.0;
+    for (int i = 0; i <= 128; ++i) {
+      nx[i] = zigdata::kZigNormalX[i];
+      ny[i] = zigdata::kZigNormalY[i];
     }
-    {
-      const long double R = 7.69711747013104972L, V = 3.949659822581572e-3L;
-      long double x[257];
-      x[0] = V / std::exp(-R);
-      x[1] = R;
-      for (int i = 2; i < 256; ++i) x[i] = -std::log(V / x[i - 1] + std::exp(-x[i - 1]));
-      x[256] = 0.0L;
-      for (int i = 0; i <= 256; ++i) {
-        ex[i] = static_cast<double>(x[i]);
-        ey[i] = static_cast<double>(std::exp(-x[i]));
-      }
-      ey[0] = 0.0;
-      ey[256] = 1.0;
+    for (int i = 0; i <= 256; ++i) {
+      ex[i] = zigdata::kZigExpX[i];
+      ey[i] = zigdata::kZigExpY[i];
     }
   }
 };

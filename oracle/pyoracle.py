@@ -24,7 +24,7 @@ def build(force=False):
     from modle_b200 import buildutil
 
     so = os.path.join(_HERE, "liboracle.so")
-    deps = [os.path.join(_HERE, f) for f in ("oracle_capi.cpp", "oracle_sim.hpp", "oracle_rng.hpp")]
+    deps = [os.path.join(_HERE, f) for f in ("oracle_capi.cpp", "oracle_sim.hpp", "oracle_rng.hpp", "ziggurat_tables.inc")]
     deps.append(os.path.join(_HERE, "..", "include", "modle_b200.h"))
     cxx = os.environ.get("CXX", "g++")
     return buildutil.ensure_built(

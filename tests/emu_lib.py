@@ -21,7 +21,7 @@ def build(force=False):
     csrc = os.path.join(_HERE, "..", "..", "modle_b200", "csrc")
     deps = [os.path.join(_HERE, "emu_capi.cpp")] + [
         os.path.join(csrc, f) for f in ("sim_core.hpp", "sim_types.hpp", "cta.hpp", "launch_prep.hpp",
-                                        "host_rng.hpp", "host.cpp", "status.hpp")]
+                                        "host_rng.hpp", "host.cpp", "status.hpp", "ziggurat_tables.inc")]
     deps.append(os.path.join(_HERE, "..", "..", "include", "modle_b200.h"))
     cxx = os.environ.get("CXX", "g++")
     return buildutil.ensure_built(

@@ -91,11 +91,31 @@ def test_interval_hash_probes():
 
 def test_ziggurat_tables_shape():
     nx, ny, ex, ey = pyoracle.zig_tables()
-    assert abs(nx[0] - 3.7130862467425505) < 1e-12 and abs(nx[1] - 3.442619855899) < 1e-12
+    # leading / trailing literals of boost/random/normal_distribution.hpp (normal_table<>) and
+    # exponential_distribution.hpp (exponential_table<>), Boost 1.88: bit-exact after parsing
+    assert list(nx[:8]) == [3.7130862467403632609, 3.4426198558966521214, 3.2230849845786185446,
+                            3.0832288582142137009, 2.9786962526450169606, 2.8943440070186706210,
+                            2.8231253505459664379, 2.7611693723841538514]
+    assert list(ny[:4]) == [0, 0.0026696290839025035092, 0.0055489952208164705392,
+                            0.0086244844129304709682]
+    assert list(ex[:4]) == [8.6971174701310497140, 7.6971174701310497140, 6.9410336293772123602,
+                            6.4783784938325698538]
     assert nx[128] == 0.0 and ny[0] == 0.0 and ny[128] == 1.0
+    assert ex[256] == 0.0 and ey[0] == 0.0 and ey[256] == 1.0
     assert np.all(np.diff(nx) < 0) and np.all(np.diff(ny) > 0)
-    assert abs(ex[0] - 8.69711747013105) < 1e-12 and abs(ex[1] - 7.69711747013105) < 1e-12
     assert np.all(np.diff(ex) < 0) and np.all(np.diff(ey) > 0)
+    # the tables solve the ziggurat equations: equal-area layers, the last one closing at f = 1
+    v = nx[1] * ny[1] + np.sqrt(np.pi / 2) * __import__("math").erfc(nx[1] / np.sqrt(2))
+    area = nx[1:128] * (ny[2:129] - ny[1:128])
+    assert np.allclose(area, v, rtol=1e-13) and abs(nx[0] * ny[1] - v) < 1e-15
+    ve = (ex[1] + 1) * ey[1]
+    assert np.allclose(ex[1:256] * (ey[2:257] - ey[1:256]), ve, rtol=1e-13)
+    # the kernel's copy (modle_b200/csrc) is the same generated file
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    a = open(os.path.join(here, "..", "oracle", "ziggurat_tables.inc")).read()
+    b = open(os.path.join(here, "..", "modle_b200", "csrc", "ziggurat_tables.inc")).read()
+    assert a == b
 
 
 @pytest.mark.parametrize("kind,args,mean,var", [
