@@ -23,6 +23,20 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#ifdef MODLE_B200_EMU_MT
+#include <pthread.h>
+#endif
+#endif
+
+// Two host-side emulations of the CTA (both TEST INFRASTRUCTURE, tests/emu):
+//   serial (MODLE_B200_EMU):            a region is a loop over virtual thread ids in one OS thread
+//   SPMD   (MODLE_B200_EMU + _EMU_MT):  every virtual thread is an OS thread running the whole
+//       per-cell program, CTA barriers are pthread barriers -- built with -fsanitize=thread this is
+//       a race detector for the kernel source (missing / misplaced barriers) that needs no GPU.
+#if MB_DEVICE_BUILD || defined(MODLE_B200_EMU_MT)
+#define MB_SPMD 1
+#else
+#define MB_SPMD 0
 #endif
 
 namespace modle_b200 {
@@ -110,7 +124,7 @@ MB_FN SecOp secop_then(const SecOp& f, const SecOp& g) {
 // by the virtual thread id in the emulation.
 template <class T>
 struct PerThread {
-#if MB_DEVICE_BUILD
+#if MB_SPMD
   T val;
   MB_FN explicit PerThread(int) : val() {}
   MB_FN T& operator[](int) { return val; }
@@ -437,16 +451,7 @@ struct Cta {
 #define MB_POPC(x) __popc(x)
 #define MB_FFS(x) __ffs(static_cast<int>(x))
 
-#else  // ---------------------------------------------------------------- emulation
-
-// Order in which the emulation runs the virtual threads of a region: 0 = ascending, 1 =
-// descending, 2 = a different pseudo-random permutation for every region. A region whose result
-// depends on the order has a cross-thread dependency the device would need a barrier for, so the
-// tests replay every case under all three (a race detector that needs no GPU).
-inline int& emu_thread_order() {
-  static thread_local int mode = 0;
-  return mode;
-}
+#else  // ---------------------------------------------------------------- emulations
 
 // CTA barriers the device build would execute (explicit sync() calls plus the three inside every
 // block-wide collective): the emulation counts them so that the barrier cost of an epoch can be
@@ -460,6 +465,148 @@ inline u64* emu_phase_barriers() {  // per phase of the epoch loop (sim_types.hp
   static thread_local u64 n[64] = {};
   return n;
 }
+
+// Order in which the emulation runs the virtual threads of a region: 0 = ascending, 1 =
+// descending, 2 = a different pseudo-random permutation for every region. A region whose result
+// depends on the order has a cross-thread dependency the device would need a barrier for, so the
+// tests replay every case under all three (a race detector that needs no GPU).
+inline int& emu_thread_order() {
+  static thread_local int mode = 0;
+  return mode;
+}
+
+#ifdef MODLE_B200_EMU_MT  // ----------------------------------------------- SPMD emulation
+
+// Collectives go through per-thread slots of the shared scratch (at most kMaxWarps = 32 virtual
+// threads), bracketed by barriers like their device counterparts.
+struct Cta {
+  CtaScratch* scr;
+  int nthreads;
+  int my;                   // this OS thread's virtual thread id
+  pthread_barrier_t* bar;
+  int nt() const { return nthreads; }
+  int first() const { return my; }
+  int step() const { return nthreads; }
+  bool leader(int tid) const { return tid == 0; }
+  void sync() const {
+    ++emu_barrier_count();
+    pthread_barrier_wait(bar);
+  }
+  u32 div_nt(u32 x) const { return x / static_cast<u32>(nthreads); }
+
+  u64 exscan_sum(PerThread<u64>& v) const {
+    scr->warp_u64[my] = v.val;
+    sync();
+    u64 acc = 0, mine = 0;
+    for (int t = 0; t < nthreads; ++t) {
+      if (t == my) mine = acc;
+      acc += scr->warp_u64[t];
+    }
+    sync();
+    emu_barrier_count() += 1;  // the device version has three barriers
+    v.val = mine;
+    return acc;
+  }
+  u64 reduce_max(const PerThread<u64>& v) const {
+    scr->warp_u64[my] = v.val;
+    sync();
+    u64 m = 0;
+    for (int t = 0; t < nthreads; ++t) m = std::max(m, scr->warp_u64[t]);
+    sync();
+    emu_barrier_count() += 1;
+    return m;
+  }
+  u64 reduce_min(const PerThread<u64>& v) const {
+    PerThread<u64> w(0);
+    w.val = ~v.val;
+    return ~reduce_max(w);
+  }
+  u64 reduce_sum(const PerThread<u64>& v) const {
+    PerThread<u64> w(0);
+    w.val = v.val;
+    return exscan_sum(w);
+  }
+  // same association order as the device (see the serial emulation below)
+  double reduce_sum_f64(const PerThread<double>& v) const {
+    scr->warp_f64[my] = v.val;
+    sync();
+    double lane[32];
+    for (int l = 0; l < 32; ++l) lane[l] = l < nthreads ? scr->warp_f64[l] : 0.0;
+    for (int d = 1; d < 32; d <<= 1) {
+      double nxt[32];
+      for (int l = 0; l < 32; ++l) nxt[l] = lane[l] + lane[l ^ d];
+      for (int l = 0; l < 32; ++l) lane[l] = nxt[l];
+    }
+    sync();
+    emu_barrier_count() += 1;
+    return 0.0 + lane[0];
+  }
+  void exscan_minplus(PerThread<MinPlus>& v) const {
+    scr->warp_u64[my] = static_cast<u64>(v.val.a);
+    scr->warp_u64b[my] = static_cast<u64>(v.val.b);
+    sync();
+    MinPlus acc = minplus_identity(), mine = acc;
+    for (int t = 0; t < nthreads; ++t) {
+      if (t == my) mine = acc;
+      acc = minplus_then(acc, MinPlus{static_cast<i64>(scr->warp_u64[t]),
+                                      static_cast<i64>(scr->warp_u64b[t])});
+    }
+    sync();
+    emu_barrier_count() += 1;
+    v.val = mine;
+  }
+  void exscan_minplus2(PerThread<MinPlus>& a, PerThread<MinPlus>& b) const {
+    exscan_minplus(a);
+    exscan_minplus(b);
+    emu_barrier_count() -= 3;  // one collective on the device
+  }
+  void exscan_secop(PerThread<SecOp>& v) const {
+    scr->warp_u64[my] = static_cast<u64>(v.val.T);
+    scr->warp_u64b[my] = static_cast<u64>(v.val.a);
+    scr->warp_u64c[my] = static_cast<u64>(v.val.b);
+    sync();
+    SecOp acc = secop_identity(), mine = acc;
+    for (int t = 0; t < nthreads; ++t) {
+      if (t == my) mine = acc;
+      acc = secop_then(acc, SecOp{static_cast<i64>(scr->warp_u64[t]),
+                                  static_cast<i64>(scr->warp_u64b[t]),
+                                  static_cast<i64>(scr->warp_u64c[t])});
+    }
+    sync();
+    emu_barrier_count() += 1;
+    v.val = mine;
+  }
+  void exscan_secop2(PerThread<SecOp>& a, PerThread<SecOp>& b) const {
+    exscan_secop(a);
+    exscan_secop(b);
+    emu_barrier_count() -= 3;
+  }
+};
+
+// relaxed atomics: ThreadSanitizer treats them as synchronisation-free but race-free accesses
+inline u32 emu_atomic_max_u32(u32* p, u32 v) {
+  u32 cur = __atomic_load_n(p, __ATOMIC_RELAXED);
+  while (cur < v && !__atomic_compare_exchange_n(p, &cur, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {
+  }
+  return cur;
+}
+inline u32 emu_atomic_min_u32(u32* p, u32 v) {
+  u32 cur = __atomic_load_n(p, __ATOMIC_RELAXED);
+  while (cur > v && !__atomic_compare_exchange_n(p, &cur, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {
+  }
+  return cur;
+}
+#define MB_ATOMIC_MAX_U32(ptr, val) emu_atomic_max_u32((ptr), (val))
+#define MB_ATOMIC_MIN_U32_(ptr, val) emu_atomic_min_u32((ptr), (val))
+#define MB_ATOMIC_OR_U32(ptr, val) __atomic_fetch_or((ptr), (val), __ATOMIC_RELAXED)
+#define MB_ATOMIC_ADD_U32(ptr, val) __atomic_fetch_add((ptr), (val), __ATOMIC_RELAXED)
+#define MB_ATOMIC_ADD_U64(ptr, val) __atomic_fetch_add((ptr), (val), __ATOMIC_RELAXED)
+#define MB_U64_TO_F64(x) static_cast<double>(x)
+#define MB_POPC(x) __builtin_popcount(x)
+#define MB_FFS(x) __builtin_ffs(static_cast<int>(x))
+
+#else  // ------------------------------------------------------------------ serial emulation
+
 
 struct Cta {
   CtaScratch* scr;
@@ -572,10 +719,25 @@ struct Cta {
 #define MB_POPC(x) __builtin_popcount(x)
 #define MB_FFS(x) __builtin_ffs(static_cast<int>(x))
 
+#endif  // serial / SPMD emulation
+#endif
+
+// Stores and loads of words that several threads may touch in the same region BY DESIGN (flags
+// every writer sets to the same value; words whose other bits a neighbour updates). Plain
+// accesses on the device; relaxed atomics in the SPMD emulation, so that the race detector
+// reports only what is not meant to happen.
+#ifdef MODLE_B200_EMU_MT
+#define MB_SHARED_STORE_U32(ptr, val) __atomic_store_n((ptr), (val), __ATOMIC_RELAXED)
+#define MB_SHARED_LOAD_U32(ptr) __atomic_load_n((ptr), __ATOMIC_RELAXED)
+#define MB_SHARED_OR_U32(ptr, val) __atomic_fetch_or((ptr), (val), __ATOMIC_RELAXED)
+#else
+#define MB_SHARED_STORE_U32(ptr, val) (*(ptr) = (val))
+#define MB_SHARED_LOAD_U32(ptr) (*(ptr))
+#define MB_SHARED_OR_U32(ptr, val) (*(ptr) |= (val))
 #endif
 
 // A region: every thread of the CTA executes the body once, then the CTA synchronises.
-#if MB_DEVICE_BUILD
+#if MB_SPMD
 #define MB_REGION(cta, tid) for (int tid = (cta).first(); tid < (cta).nt(); tid += (cta).step())
 #else
 #define MB_REGION(cta, tid)                                                                  \

@@ -28,7 +28,11 @@ constexpr size_t kJumpTableWords = size_t(32) * 256 * 4;
 #define MB_ATOMIC_MIN_U32(ptr, val) atomicMin((ptr), (val))
 #else
 #define MB_LD_RING_U64(p) (*(p))
+#ifdef MODLE_B200_EMU_MT
+#define MB_ATOMIC_MIN_U32(ptr, val) emu_atomic_min_u32((ptr), (val))
+#else
 #define MB_ATOMIC_MIN_U32(ptr, val) (*(ptr) = std::min<u32>(*(ptr), (val)))
+#endif
 #endif
 
 constexpr double kTwo64 = 18446744073709551616.0;
@@ -929,8 +933,13 @@ struct CellSimT {
     }
     __syncthreads();
 #else
-    std::sort(A.rr, A.rr + n, [&](u16 a, u16 b) { return rank_less<true>(a, b, prev_r); });
-    std::sort(A.fr, A.fr + n, [&](u16 a, u16 b) { return rank_less<false>(a, b, prev_f); });
+    MB_REGION(cta, tid) {
+      if (cta.leader(tid)) {
+        std::sort(A.rr, A.rr + n, [&](u16 a, u16 b) { return rank_less<true>(a, b, prev_r); });
+        std::sort(A.fr, A.fr + n, [&](u16 a, u16 b) { return rank_less<false>(a, b, prev_f); });
+      }
+    }
+    cta.sync();
 #endif
   }
 
@@ -1009,7 +1018,7 @@ struct CellSimT {
               swapped = true;
             }
           }
-          if (swapped) S.tmp_u32[5 + (pass & 1)] = 1;
+          if (swapped) MB_SHARED_STORE_U32(&S.tmp_u32[5 + (pass & 1)], 1u);
           // the other flag was last read before this pass's first barrier: safe to reset now
           if (parity == 1 && cta.leader(tid)) S.tmp_u32[5 + ((pass + 1) & 1)] = 0;
         }
@@ -1481,12 +1490,13 @@ struct CellSimT {
           for (u32 i = j; i-- > 0;) {
             const u32 oi = ex[4 * i];
             if (off - oi >= 256u) break;  // a slow path never takes that many draws (cursor limit)
-            if (oi + (ex[4 * i + 1] & 0xFFFFu) > off) {
+            // (the owner of record i may be setting its head flag, bit 31, right now)
+            if (oi + (MB_SHARED_LOAD_U32(&ex[4 * i + 1]) & 0xFFFFu) > off) {
               head = false;
               break;
             }
           }
-          if (head) ex[4 * j + 1] |= 0x80000000u;
+          if (head) MB_SHARED_OR_U32(&ex[4 * j + 1], 0x80000000u);
         }
         if (cta.leader(tid)) {
           S.tmp_u32[2] = 0;
@@ -1496,13 +1506,15 @@ struct CellSimT {
       cta.sync();
       MB_REGION(cta, tid) {
         const u32 j = static_cast<u32>(tid);
-        if (j < n_exc && (ex[4 * j + 1] & 0x80000000u)) {
-          u32 covered = ex[4 * j] + (ex[4 * j + 1] & 0xFFFFu);
-          ex[4 * j + 1] |= 0x40000000u;  // kept
-          for (u32 k = j + 1; k < n_exc && !(ex[4 * k + 1] & 0x80000000u); ++k) {
+        // (a cluster's walk ends at the next head, whose owner is setting bit 30 of that word)
+        if (j < n_exc && (MB_SHARED_LOAD_U32(&ex[4 * j + 1]) & 0x80000000u)) {
+          u32 covered = ex[4 * j] + (MB_SHARED_LOAD_U32(&ex[4 * j + 1]) & 0xFFFFu);
+          MB_SHARED_OR_U32(&ex[4 * j + 1], 0x40000000u);  // kept
+          for (u32 k = j + 1; k < n_exc && !(MB_SHARED_LOAD_U32(&ex[4 * k + 1]) & 0x80000000u);
+               ++k) {
             if (ex[4 * k] >= covered) {
-              ex[4 * k + 1] |= 0x40000000u;
-              covered = ex[4 * k] + (ex[4 * k + 1] & 0xFFFFu);
+              MB_SHARED_OR_U32(&ex[4 * k + 1], 0x40000000u);
+              covered = ex[4 * k] + (MB_SHARED_LOAD_U32(&ex[4 * k + 1]) & 0xFFFFu);
             }
           }
         }
@@ -2288,8 +2300,10 @@ struct CellSimT {
     chunk(tid, d.M, &lo, &hi);
     bool alive = prefix.b == kSecConst;
     i64 v = prefix.a;
-    bool prev_head =
-        lo > 0 && lo < hi && coll_occurred(coll[sec_idx<kRevPass>(d.first, lo - 1)]);
+    // (the owner of scan position lo - 1 may be parking a move in the index bits of that word;
+    // the event bits read here do not change in this region)
+    bool prev_head = lo > 0 && lo < hi &&
+                     coll_occurred(MB_SHARED_LOAD_U32(&coll[sec_idx<kRevPass>(d.first, lo - 1)]));
     u32 c = 0;
     for (u32 m = lo; m < hi; ++m) {
       const u32 idx = sec_idx<kRevPass>(d.first, m);
@@ -2302,7 +2316,7 @@ struct CellSimT {
       if (alive && sec_q<kRevPass>(idx) <= v) {
         const i64 p = sec_pos<kRevPass>(idx);
         const i64 mv = p - v;  // distance to the blocker's site
-        coll[idx] = static_cast<u32>(mv > 0 ? mv - 1 : 0);  // event bits stay 0
+        MB_SHARED_STORE_U32(&coll[idx], static_cast<u32>(mv > 0 ? mv - 1 : 0));  // event bits stay 0
         MB_ATOMIC_OR_U32(&d.cand[m >> 5], 1u << (m & 31));
         if (prev_head) MB_ATOMIC_OR_U32(&d.head1[m >> 5], 1u << (m & 31));
         v = p < v + 1 ? p : v + 1;
@@ -2486,7 +2500,8 @@ struct CellSimT {
         if (lane == 0) S.tmp_u32[4] = d;
       }
 #else
-      {
+      MB_REGION(cta, tid) {
+        if (!cta.leader(tid)) continue;
         u32 d = 0, alive = 0;
         for (u32 w = 0; w < ncw; ++w) {
           const u32 Fw = bits_firstc[w];

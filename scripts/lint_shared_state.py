@@ -26,7 +26,10 @@ FUNC = re.compile(r"^\s*(?:template\s*<[^>]*>\s*)?MB_FN(?:_NOINLINE)?\s+[^;(]*?\
 
 
 def strip_comments(line):
-    return re.sub(r"//.*", "", line)
+    line = re.sub(r"//.*", "", line)
+    # accesses through MB_SHARED_* are shared by design (cta.hpp) and checked by the SPMD
+    # emulation under ThreadSanitizer (tests/test_emulation_races.py), not by this scan
+    return re.sub(r"MB_SHARED_\w+\s*\(\s*&\s*S\.[a-z_0-9]+", "MB_SHARED(", line)
 
 
 def lint(path):
