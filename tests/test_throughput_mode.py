@@ -171,11 +171,26 @@ def _emu_parallel(p, iv, bars, tasks, nthreads=8):
     return band, occ, np.concatenate([x[2] for x in parts]), sum(x[3] for x in parts)
 
 
-def test_statistically_equivalent_to_the_oracle(throughput):
+REGIMES = {
+    "defaults": dict(),
+    # BASELINE C4: LEF density x4, dense barriers, bypass ~ 0 (rank + collision handling stressed)
+    "high_collision": dict(number_of_lefs_per_mbp=80.0, nbar=1300,
+                           probability_of_extrusion_unit_bypass=0.01),
+    # every Bernoulli of the collision pipeline fractional; TAD-heavy sampling
+    "fractional_everything": dict(lef_bar_major_collision_pblock=0.7,
+                                  lef_bar_minor_collision_pblock=0.2,
+                                  probability_of_extrusion_unit_bypass=0.3,
+                                  tad_to_loop_contact_ratio=12.0),
+}
+
+
+@pytest.mark.parametrize("regime", sorted(REGIMES))
+def test_statistically_equivalent_to_the_oracle(throughput, regime):
     """Gate (ii) of SURVEY 8c with the tolerances of tests/test_statistical_parity.py."""
     from scipy.stats import ks_2samp
 
     kw = dict(size=20_000_000, ncells=128, nbar=350, target_contact_density=1.0, name="chrS")
+    kw.update(REGIMES[regime])
     runs = {}
     for seed in (1, 2, 3):
         p, iv, bars, tasks = make_case(seed=7, **kw)
@@ -186,7 +201,7 @@ def test_statistically_equivalent_to_the_oracle(throughput):
     ora2 = pyoracle.simulate_interval(*runs[2], nthreads=8)
     ora3 = pyoracle.simulate_interval(*runs[3], nthreads=8)
     assert thr[2]["device_fault"].max() == 0
-    assert int(thr[0].sum()) == int(ora2[0].sum())
+    assert int(thr[0].sum()) + thr[3] == int(ora2[0].sum()) + ora2[3]  # (+ out-of-band updates)
 
     m_t, v_t, tot_t = per_diagonal_mean_var(thr[0], nrows, ncols)
     m_o, v_o, tot_o = per_diagonal_mean_var(ora2[0], nrows, ncols)
@@ -198,7 +213,8 @@ def test_statistically_equivalent_to_the_oracle(throughput):
     scc_to = stratum_adjusted_correlation(thr[0], ora2[0], nrows, ncols, max_d=200)
     scc_oo = stratum_adjusted_correlation(ora2[0], ora3[0], nrows, ncols, max_d=200)
     assert scc_to > scc_oo - 0.01, (scc_to, scc_oo)
-    assert scc_to > 0.4
+    if regime == "defaults":  # (the other regimes leave less structure above the sampling noise)
+        assert scc_to > 0.4
     # per-stripe Pearson as `modle_tools eval` computes it: medians within 0.005 of the floor
     for direction in ("vertical", "horizontal"):
         r_to = np.nanmedian(stripe_pearson(thr[0], ora2[0], nrows, ncols, direction))
