@@ -234,8 +234,14 @@ int modle_b200_make_cell_tasks(const modle_b200_sim_params* p, const char* chrom
   u64 nrows = 0, ncols = 0;
   modle_b200_band_shape(p, interval->end - interval->start, &nrows, &ncols);
   const bool epochs_mode = p->stopping_criterion == MODLE_B200_STOP_SIMULATION_EPOCHS;
+  // GenomicInterval::npixels() is ContactMatrixLazy's ncols * nrows (genome_impl.hpp:21,96), whose
+  // nrows is ceil(diagonal_width / bin_size) (genome.cpp:39-41) -- NOT clamped to ncols the way
+  // ContactMatrixDense clamps its own (contact_matrix_dense_impl.hpp:39-44): an interval shorter
+  // than the diagonal width still gets its contact target from the unclamped product.
+  const u64 nrows_lazy = (p->diagonal_width + p->bin_size - 1) / p->bin_size;
+  (void)nrows;
   const u64 total = epochs_mode ? 0
-                                : static_cast<u64>(std::round(static_cast<double>(nrows * ncols) *
+                                : static_cast<u64>(std::round(static_cast<double>(nrows_lazy * ncols) *
                                                               p->target_contact_density));
   const u64 per_cell = (total + p->num_cells - 1) / p->num_cells;
   u64 assigned = 0;

@@ -64,6 +64,7 @@ class GenomicInterval:
     num_lefs: int = 0
     nrows: int = 0
     ncols: int = 0
+    nrows_lazy: int = 0  # ceil(diagonal_width / bin_size), not clamped to ncols (see npixels)
     contacts: np.ndarray = None          # band, reference layout (nrows*ncols+1 uint32)
     lef_1d_occupancy: np.ndarray = None  # ncols uint64
     missed_updates: int = 0
@@ -73,7 +74,10 @@ class GenomicInterval:
         return self.end - self.start
 
     def npixels(self):
-        return self.nrows * self.ncols
+        """GenomicInterval::npixels (genome_impl.hpp:21,96): ContactMatrixLazy's ncols x nrows,
+        whose nrows is NOT clamped to ncols (the contact target of an interval shorter than the
+        diagonal width is computed from this product)."""
+        return self.ncols * self.nrows_lazy
 
     def abi_interval(self):
         return abi.Interval(self.chrom_size, self.start, self.end, self.num_lefs)
@@ -275,6 +279,7 @@ class Simulation:
                 [r for r in records if start <= r[0] < end], p)
             iv.num_lefs = host.compute_num_lefs(p, end - start)
             iv.nrows, iv.ncols = host.band_shape(p, end - start)
+            iv.nrows_lazy = (int(p.diagonal_width) + int(p.bin_size) - 1) // int(p.bin_size)
             self.intervals.append(iv)
 
     def partition(self):

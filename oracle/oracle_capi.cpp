@@ -143,8 +143,12 @@ int oracle_make_cell_tasks(const modle_b200_sim_params* p, const char* name, std
   Rng g = Rng::from_seed(h);
   const Band band = Band::make(iv->end - iv->start, p->diagonal_width, p->bin_size);
   const bool epochs_mode = p->stopping_criterion == MODLE_B200_STOP_SIMULATION_EPOCHS;
+  // interval.npixels() (scheduler_simulate.cpp:129) = ContactMatrixLazy::npixels()
+  // (genome_impl.hpp:21,96): ncols * ceil(diagonal_width / bin_size), without the
+  // min(nrows, ncols) clamp of ContactMatrixDense
+  const u64 npixels_lazy = band.ncols * ((p->diagonal_width + p->bin_size - 1) / p->bin_size);
   const u64 tot = epochs_mode ? 0
-                              : static_cast<u64>(std::round(static_cast<double>(band.npixels()) *
+                              : static_cast<u64>(std::round(static_cast<double>(npixels_lazy) *
                                                             p->target_contact_density));
   const u64 per_cell = (tot + p->num_cells - 1) / p->num_cells;
   u64 rolling = 0;

@@ -133,6 +133,15 @@ def test_task_fanout_matches_oracle(product_lib):
     t = host.make_cell_tasks(p, "chr20", iv)
     assert t["num_target_contacts"].sum() == round(600 * 12889 * 0.00001)
     assert (t["num_target_contacts"] == 0).sum() > 0
+    # an interval shorter than the diagonal width: the target comes from GenomicInterval::npixels =
+    # ncols * ceil(diagonal_width / bin_size) (genome_impl.hpp:21,96; scheduler_simulate.cpp:129),
+    # not from the (clamped) shape of the dense matrix
+    p.num_cells = 5
+    p.target_contact_density = 0.5
+    short = abi.Interval(64444167, 1_000_000, 1_120_000, 2)
+    assert host.band_shape(p, 120_000) == (24, 24)
+    for t in (host.make_cell_tasks(p, "chr20", short), pyoracle.make_cell_tasks(p, "chr20", short)):
+        assert t["num_target_contacts"].sum() == round(600 * 24 * 0.5)
 
 
 def test_barrier_records_to_stp(product_lib):
