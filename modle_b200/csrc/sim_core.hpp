@@ -1227,30 +1227,6 @@ struct CellSimT {
   // stride; the first event that consumes a different number of draws re-bases the rest.
   MB_FN void sampling_events(u32 n_events, int kind) {
     if (n_events == 0) return;
-    if constexpr (kCtr) {
-      // event e of this kind reads its own sequence and registers at once
-      MB_REGION(cta, tid) {
-        u32 registered = 0;
-        for (u32 e = tid; e < n_events; e += cta.nt()) {
-          u32 b1, b2;
-          const u64 o = ctr_pack(S.epoch, kDrLoop + static_cast<u32>(kind), e);
-          sampling_event(o, kind, o + kCtrDrawsPerItem, &b1, &b2);
-          if (b1 == kUnbound) continue;
-          if (kind == 2) {
-            if (K.occ1d) {
-              MB_ATOMIC_ADD_U64(K.occ1d + b1, u64(1));
-              MB_ATOMIC_ADD_U64(K.occ1d + b2, u64(1));
-            }
-          } else {
-            band_increment(b1, b2);
-            ++registered;
-          }
-        }
-        if (registered) MB_ATOMIC_ADD_U64(&S.tmp_u64[1], u64(registered));
-      }
-      cta.sync();
-      return;
-    }
     const u32 n_act = S.num_active;
     const u32 base_draws = n_act > 1 ? 1u : 0u;
     const u32 stride = base_draws + (P.noisify ? 2u : 0u) + (kind == 1 ? 2u : 0u);
@@ -1343,9 +1319,38 @@ struct CellSimT {
     cta.sync();
     const u32 nloop = S.tmp_u32[1];
     const u32 ntad = static_cast<u32>(nev) - nloop;
-    sampling_events(nloop, 0);
-    sampling_events(ntad, 1);
-    if (P.track_1d) sampling_events(static_cast<u32>(nev), 2);
+    if constexpr (kCtr) {
+      // all three kinds in one pass: an event's draws depend on (kind, number) only, so the
+      // events of an epoch are one pool of independent work items
+      const u32 n1d = P.track_1d ? static_cast<u32>(nev) : 0u;
+      const u32 total = nloop + ntad + n1d;
+      MB_REGION(cta, tid) {
+        u32 registered = 0;
+        for (u32 w = tid; w < total; w += cta.nt()) {
+          const int kind = w < nloop ? 0 : (w < nloop + ntad ? 1 : 2);
+          const u32 e = kind == 0 ? w : (kind == 1 ? w - nloop : w - nloop - ntad);
+          u32 b1, b2;
+          const u64 o = ctr_pack(S.epoch, kDrLoop + static_cast<u32>(kind), e);
+          sampling_event(o, kind, o + kCtrDrawsPerItem, &b1, &b2);
+          if (b1 == kUnbound) continue;
+          if (kind == 2) {
+            if (K.occ1d) {
+              MB_ATOMIC_ADD_U64(K.occ1d + b1, u64(1));
+              MB_ATOMIC_ADD_U64(K.occ1d + b2, u64(1));
+            }
+          } else {
+            band_increment(b1, b2);
+            ++registered;
+          }
+        }
+        if (registered) MB_ATOMIC_ADD_U64(&S.tmp_u64[1], u64(registered));
+      }
+      cta.sync();
+    } else {
+      sampling_events(nloop, 0);
+      sampling_events(ntad, 1);
+      if (P.track_1d) sampling_events(static_cast<u32>(nev), 2);
+    }
     MB_REGION(cta, tid) {
       if (cta.leader(tid)) S.num_contacts += S.tmp_u64[1];
     }
