@@ -42,7 +42,7 @@ CASES = {
                            rev_extrusion_speed_std=0.0, fwd_extrusion_speed_std=0.0),
     "max_burnin_forced": dict(size=4_000_000, ncells=2, nbar=60, target_contact_density=0.01,
                               max_burnin_epochs=150),
-    "tiny_interval": dict(size=120_000, ncells=3, nbar=3, target_contact_density=0.05),
+    "tiny_interval": dict(size=120_000, ncells=3, nbar=3, target_contact_density=0.002),
     "no_barriers": dict(size=2_000_000, ncells=2, nbar=0, target_contact_density=0.01),
 }
 
