@@ -223,8 +223,8 @@ def run_ours(args, rank, world, local_rank):
     engine = distributed.DeviceEngine(local_rank, num_streams=args.streams, rng_mode=rng_mode)
     ctx = engine.ctx
     barrier_dt, task_dt, stats_dt = abi.np_dtypes()
-    shards = distributed.plan_shards(
-        [iv.num_lefs if len(iv.barriers) else 0 for iv in sim.intervals], int(p.num_cells), world)
+    shards = distributed.plan_shards(distributed.interval_weights(sim.intervals),
+                                     int(p.num_cells), world)
     roots = distributed.interval_roots(shards)
     split = sorted(i for i, (_, ranks) in roots.items() if len(ranks) > 1)
 

@@ -370,6 +370,14 @@ int modle_b200_lef_occupancy_profile(modle_b200_context* ctx, const uint64_t* oc
 #define MODLE_B200_NUM_PHASES 26
 int modle_b200_phase_cycles(modle_b200_context* ctx, uint64_t* out, size_t n, int reset);
 
+/* Host-only: how the library would launch cells of an interval with `num_lefs` LEFs and
+ * `num_barriers` barriers -- threads per CTA (one CTA simulates one cell), cells resident per SM
+ * (3, 2 or 1: what the cell's shared-memory state leaves room for) and bytes of shared memory per
+ * cell. Lets a caller weigh (interval, cell) work when it spreads it over several GPUs; the
+ * reference has no counterpart (its workers are interchangeable CPU threads). */
+int modle_b200_launch_geometry(uint64_t num_lefs, uint64_t num_barriers, uint32_t* cta_threads,
+                               uint32_t* cells_per_sm, uint64_t* shared_bytes_per_cell);
+
 /* Number of kernels this library has launched on the context so far (bench bookkeeping). */
 uint64_t modle_b200_kernel_launches(const modle_b200_context* ctx);
 

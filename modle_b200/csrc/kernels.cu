@@ -401,6 +401,23 @@ void modle_b200_destroy(modle_b200_context* ctx) {
   delete ctx;
 }
 
+int modle_b200_launch_geometry(uint64_t num_lefs, uint64_t num_barriers, uint32_t* cta_threads,
+                               uint32_t* cells_per_sm, uint64_t* shared_bytes_per_cell) {
+  if (num_lefs == 0 || num_lefs >= 65535 || num_barriers >= (1u << 24))
+    return fail(MODLE_B200_ERR_INVALID_ARGUMENT, "num_lefs / num_barriers out of range");
+  const StagingConfig sc =
+      pick_staging(static_cast<u32>(num_lefs), static_cast<u32>(num_barriers));
+  if (cta_threads) *cta_threads = sc.cta_threads;
+  if (cells_per_sm)
+    *cells_per_sm = sc.cta_threads == 256 ? MODLE_B200_SMALL_MIN_BLOCKS
+                                          : (sc.cta_threads == 512 ? 2u : 1u);
+  if (shared_bytes_per_cell)
+    *shared_bytes_per_cell =
+        ((sizeof(CellShared) + 15) / 16) * 16 +
+        cell_array_bytes(static_cast<u32>(num_lefs), static_cast<u32>(num_barriers));
+  return MODLE_B200_OK;
+}
+
 int modle_b200_set_rng_mode(modle_b200_context* ctx, int mode) {
   if (!ctx) return fail(MODLE_B200_ERR_INVALID_ARGUMENT, "ctx is NULL");
   if (mode != MODLE_B200_RNG_REFERENCE_ORDER && mode != MODLE_B200_RNG_COUNTER)

@@ -33,6 +33,29 @@ class Shard:
     weight: float = 0.0
 
 
+# SM time of one cell-epoch, in cycles: A[threads per CTA] + B x LEFs, divided by the cells an SM
+# hosts at a time. Fitted to single-interval runs on a B200 (profiles/r01i_stream_sweep.txt:
+# chr1 279 k, chr2 270 k, chr3 238 k cycles per cell-epoch at one cell per SM; class averages
+# 212 k at two and 217 k at three cells per SM); only the ratios matter to the planner.
+_COST_A = {1024: 80e3, 512: 129e3, 256: 166e3}
+_COST_B = 40.0
+
+
+def cell_cost(num_lefs, num_barriers):
+    """Relative SM time of one cell of an interval (epoch counts are the same for every interval
+    to within a few percent, so they drop out)."""
+    if num_lefs <= 0:
+        return 0.0
+    threads, per_sm, _ = host.launch_geometry(num_lefs, num_barriers)
+    return (_COST_A.get(threads, 80e3) + _COST_B * num_lefs) / per_sm
+
+
+def interval_weights(intervals):
+    """Planner weights of simulation.GenomicInterval-like objects (0 = skipped: no barriers)."""
+    return [cell_cost(iv.num_lefs, len(iv.barriers)) if len(iv.barriers) else 0.0
+            for iv in intervals]
+
+
 def _assign(pieces, world):
     """Longest-processing-time-first assignment; returns the per-rank loads."""
     load = [0.0] * world
@@ -46,8 +69,9 @@ def _assign(pieces, world):
 def plan_shards(num_lefs, num_cells, world, tolerance=1.10, max_pieces=None, slice_all=False):
     """Deals (interval, cell range) shards to `world` ranks.
 
-    num_lefs[i] is the LEF count of interval i (0 = interval skipped, e.g. no barriers); the cost
-    of a shard is num_lefs x cells. Starts from whole intervals and, while the heaviest rank
+    num_lefs[i] is the weight of one cell of interval i (0 = interval skipped, e.g. no
+    barriers): its LEF count, or better `interval_weights()` -- the SM time of a cell-epoch, which
+    also knows how many cells of that size share an SM; the cost of a shard is weight x cells. Starts from whole intervals and, while the heaviest rank
     carries more than `tolerance` x the mean load, halves the heaviest splittable piece of that
     rank. Deterministic: every rank computes the same plan.
 
@@ -164,8 +188,7 @@ def run_sharded(engine, params, intervals, rank=0, world=1, dist=None, shards=No
     only. `dist` is torch.distributed (already initialised) when world > 1.
     """
     if shards is None:
-        shards = plan_shards([iv.num_lefs if len(iv.barriers) else 0 for iv in intervals],
-                             int(params.num_cells), world)
+        shards = plan_shards(interval_weights(intervals), int(params.num_cells), world)
     roots = interval_roots(shards)
     _, _, stats_dt = abi.np_dtypes()
     out = {}

@@ -57,6 +57,8 @@ def lib():
         L.modle_b200_init.argtypes = [C.POINTER(C.c_void_p), C.c_int]
         L.modle_b200_destroy.argtypes = [C.c_void_p]
         L.modle_b200_destroy.restype = None
+        L.modle_b200_launch_geometry.argtypes = [C.c_uint64, C.c_uint64, C.POINTER(C.c_uint32),
+                                                 C.POINTER(C.c_uint32), u64p]
         L.modle_b200_set_rng_mode.argtypes = [C.c_void_p, C.c_int]
         L.modle_b200_get_rng_mode.argtypes = [C.c_void_p]
         L.modle_b200_synchronize.argtypes = [C.c_void_p]
@@ -114,7 +116,7 @@ EXPORTED_SYMBOLS = [
     "modle_b200_rng_seed", "modle_b200_rng_next", "modle_b200_rng_jump",
     "modle_b200_stp_active_from_occupancy", "modle_b200_occupancy_from_stp",
     "modle_b200_make_cell_tasks", "modle_b200_init", "modle_b200_destroy",
-    "modle_b200_set_rng_mode", "modle_b200_get_rng_mode",
+    "modle_b200_set_rng_mode", "modle_b200_get_rng_mode", "modle_b200_launch_geometry",
     "modle_b200_simulate_interval", "modle_b200_simulate_interval_logged",
     "modle_b200_simulate_interval_device",
     "modle_b200_synchronize", "modle_b200_snapshot_cell", "modle_b200_register_contacts_device",
@@ -149,6 +151,14 @@ def transform_params(p, rev_speed_given=False, fwd_speed_given=False,
     check(lib().modle_b200_transform_params(C.byref(p), int(rev_speed_given), int(fwd_speed_given),
                                             int(barrier_occupancy_given)))
     return p
+
+
+def launch_geometry(num_lefs, num_barriers):
+    """(threads per CTA, cells resident per SM, shared-memory bytes per cell) for an interval."""
+    t, c, b = C.c_uint32(0), C.c_uint32(0), C.c_uint64(0)
+    check(lib().modle_b200_launch_geometry(int(num_lefs), int(num_barriers), C.byref(t),
+                                           C.byref(c), C.byref(b)))
+    return int(t.value), int(c.value), int(b.value)
 
 
 def compute_num_lefs(p, size_bp):

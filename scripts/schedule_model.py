@@ -169,8 +169,10 @@ def compare_plans(intervals, args, ideal):
     print("\nshard plans (max over ranks of the modelled per-rank time; reduce not included)")
     for world in [int(x) for x in args.ranks.split(",")]:
         row = [f"{world} ranks: perfect {ideal / world:6.3f} s"]
-        for name, kw in (("whole", dict()), ("sliced", dict(slice_all=True))):
-            shards = distributed.plan_shards(n_lefs, args.cells, world, **kw)
+        cost = [distributed.cell_cost(d["n"], d["nb"]) for d in intervals]
+        for name, w, kw in (("whole/LEFs", n_lefs, dict()), ("whole/cost", cost, dict()),
+                            ("sliced", cost, dict(slice_all=True))):
+            shards = distributed.plan_shards(w, args.cells, world, **kw)
             ts = rank_makespans(intervals, shards, world, args.streams)
             nsplit = sum(1 for _, (_, rk) in distributed.interval_roots(shards).items() if len(rk) > 1)
             row.append(f"{name} {max(ts):6.3f} s ({ideal / world / max(ts):5.1%}, {nsplit} split)")

@@ -41,6 +41,27 @@ def test_sliced_plan_gives_every_rank_the_same_mix_and_rotates_the_roots():
     assert all(len(roots[i][1]) == 8 for i in range(4))
 
 
+def test_cost_weights_follow_the_launch_geometry(product_lib):
+    from modle_b200 import host
+
+    # chr20 / chr13 / chr1 shapes: three, two and one cell per SM
+    assert host.launch_geometry(1289, 1132)[:2] == (256, 3)
+    assert host.launch_geometry(2287, 943)[:2] == (512, 2)
+    assert host.launch_geometry(4979, 3518)[:2] == (1024, 1)
+    assert host.launch_geometry(4979, 3518)[2] < 227 * 1024
+    c20, c13, c1 = (distributed.cell_cost(*x) for x in ((1289, 1132), (2287, 943), (4979, 3518)))
+    assert c20 < c13 < c1
+    # a chr1 cell owns its SM: it costs more per LEF than three co-resident chr20 cells do
+    assert c1 / 4979 > 0.9 * c20 / 1289 and c1 > 3.0 * c20
+    assert distributed.cell_cost(0, 10) == 0.0
+
+    class Iv:
+        def __init__(self, n, nb):
+            self.num_lefs, self.barriers = n, [0] * nb
+    w = distributed.interval_weights([Iv(1289, 1132), Iv(900, 0), Iv(4979, 3518)])
+    assert w[1] == 0.0 and w[0] == c20 and w[2] == c1
+
+
 def test_plan_balances_and_prefers_whole_intervals():
     # one big chromosome, 8 ranks: equal cell ranges, one per rank
     sh = distributed.plan_shards([4979], 8192, 8)
