@@ -33,12 +33,20 @@ class Shard:
     weight: float = 0.0
 
 
-# SM time of one cell-epoch, in cycles: A[threads per CTA] + B x LEFs, divided by the cells an SM
-# hosts at a time. Fitted to single-interval runs on a B200 (profiles/r01i_stream_sweep.txt:
-# chr1 279 k, chr2 270 k, chr3 238 k cycles per cell-epoch at one cell per SM; class averages
-# 212 k at two and 217 k at three cells per SM); only the ratios matter to the planner.
-_COST_A = {1024: 80e3, 512: 129e3, 256: 166e3}
-_COST_B = 40.0
+# SM time of one cell-epoch, in cycles: A[threads per CTA] + B[threads] x LEFs, divided by the
+# cells an SM hosts at a time. One CTA of 1024 threads: 80 k + 40 per LEF, fitted to
+# single-interval runs on a B200 (profiles/r01i_stream_sweep.txt: chr1 279 k, chr2 270 k, chr3
+# 238 k cycles per cell-epoch). A LEF costs a narrower CTA proportionally more (each thread owns
+# more of them), and the constants then follow from the measured class averages (212 k at 512
+# threads / ~2070 LEFs, 217 k at 256 threads / ~1280 LEFs). Only the ratios matter to the planner.
+_COST_A = {1024: 80e3, 512: 46e3, 256: 12e3}
+_COST_B = {1024: 40.0, 512: 80.0, 256: 160.0}
+
+
+def cell_epoch_cycles(num_lefs, num_barriers):
+    """(modelled SM-clock cycles of one cell-epoch, cells resident per SM) for an interval."""
+    threads, per_sm, _ = host.launch_geometry(num_lefs, num_barriers)
+    return _COST_A.get(threads, 80e3) + _COST_B.get(threads, 40.0) * num_lefs, per_sm
 
 
 def cell_cost(num_lefs, num_barriers):
@@ -46,8 +54,8 @@ def cell_cost(num_lefs, num_barriers):
     to within a few percent, so they drop out)."""
     if num_lefs <= 0:
         return 0.0
-    threads, per_sm, _ = host.launch_geometry(num_lefs, num_barriers)
-    return (_COST_A.get(threads, 80e3) + _COST_B * num_lefs) / per_sm
+    cycles, per_sm = cell_epoch_cycles(num_lefs, num_barriers)
+    return cycles / per_sm
 
 
 def interval_weights(intervals):

@@ -21,14 +21,10 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
-# cycles per cell-epoch = A + B x LEFs. Large class from single-interval runs of
-# profiles/r01i_stream_sweep.txt (chr1 279 k, chr2 270 k, chr3 238 k; chr1-6 average 243 k);
-# the other classes keep that slope and match their measured class averages (212 k / 217 k).
-# Everything is then scaled by CAL so that the modelled 3-stream single-GPU step equals the
-# measured one (4.70 s, profiles/r01i_bench_default_c2.json).
-CAL = 1.07
-CYC_A = {"large": 80e3 * CAL, "mid": 129e3 * CAL, "small": 166e3 * CAL}
-CYC_B = 40.0 * CAL
+# cycles per cell-epoch: modle_b200.distributed.cell_epoch_cycles (the planner's cost model,
+# fitted to profiles/r01i_stream_sweep.txt), scaled by CAL so that the modelled 3-stream
+# single-GPU step equals the measured one (4.70 s, profiles/r01i_bench_default_c2.json).
+CAL = 4.70 / 4.342
 CAP = {"large": 1, "mid": 2, "small": 3}                  # resident cells per SM
 CLOCK = 1.965e9
 SMS = 148
@@ -101,7 +97,7 @@ def main():
     ap.add_argument("--ranks", default="", help="comma list of world sizes: compare shard plans")
     ap.add_argument("--streams", type=int, default=3)
     args = ap.parse_args()
-    from modle_b200 import host, workloads
+    from modle_b200 import distributed, host, workloads
     from modle_b200.simulation import Simulation
     from oracle import pyoracle
 
@@ -126,7 +122,7 @@ def main():
         k = klass(iv.num_lefs, len(iv.barriers))
         # bootstrap the interval's 512 cells from the sample
         epochs = rng.choice(ep, size=args.cells, replace=True)
-        dur = epochs * (CYC_A[k] + CYC_B * iv.num_lefs) / CLOCK
+        dur = epochs * CAL * distributed.cell_epoch_cycles(iv.num_lefs, len(iv.barriers))[0] / CLOCK
         intervals.append(dict(name=iv.chrom_name, k=k, n=iv.num_lefs, nb=len(iv.barriers), dur=dur,
                               mean_epochs=ep.mean(), max_over_mean=ep.max() / ep.mean()))
         print(f"{iv.chrom_name:6s} {k:5s} N={iv.num_lefs:5d} epochs mean {ep.mean():7.1f} "

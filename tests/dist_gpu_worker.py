@@ -30,10 +30,10 @@ def main():
     genome = [(n, s, 0, s, workloads.synthetic_barrier_records(s, nb, seed=31 + k))
               for k, (n, s, nb) in enumerate(sizes)]
     sim = Simulation(cfg, genome, device=local, rank=rank, world_size=world)
-    shards = distributed.plan_shards(
-        [iv.num_lefs if len(iv.barriers) else 0 for iv in sim.intervals], 16, world)
+    # the plan run_simulate() makes (every rank computes the same one)
+    shards = distributed.plan_shards(distributed.interval_weights(sim.intervals), 16, world)
     roots = distributed.interval_roots(shards)
-    assert len(roots[0][1]) == world, "chrA should be split over all ranks"
+    assert len(roots[0][1]) > 1, "chrA should be split over several ranks"
     sim.run_simulate()
     ok = 1
     p = cfg.params
