@@ -199,6 +199,12 @@ void oracle_zig_tables(double* nx, double* ny, double* ex, double* ey) {
   std::memcpy(ey, t.ey, sizeof(t.ey));
 }
 
+// The burn-in statistics of compute_loop_size_stats (simulation.cpp:795-819) on given loop sizes:
+// out = {mean, standard deviation} (the reference's stats KATs, test/units/stats/descriptive_test.cpp)
+void oracle_loop_size_stats(const u64* loop_sizes, std::size_t n, double* out) {
+  CellSim::loop_size_mean_sd(n, [&](std::size_t i) { return loop_sizes[i]; }, &out[0], &out[1]);
+}
+
 void oracle_rank_lefs(const u64* rev, const u64* fwd, const u64* ep, u64* rr, u64* fr,
                       std::size_t n, int init_buffers) {
   rank_lefs(rev, fwd, ep, rr, fr, n, init_buffers != 0);

@@ -710,6 +710,22 @@ class CellSim {
     } while (s.num_active == 0);
   }
 
+  // stats::mean and stats::standard_dev over the loop sizes (src/stats/descriptive_impl.hpp:
+  // 22-32, 64-101): left-to-right double accumulation, population variance (divides by n)
+  template <class LoopFn>
+  static void loop_size_mean_sd(std::size_t n, LoopFn loop, double* mean_out, double* sd_out) {
+    double acc = 0.0;
+    for (std::size_t i = 0; i < n; ++i) acc = acc + static_cast<double>(loop(i));
+    const double mean = acc / static_cast<double>(n);
+    double ssd = 0.0;
+    for (std::size_t i = 0; i < n; ++i) {
+      const double d = static_cast<double>(loop(i)) - mean;
+      ssd = ssd + (d * d);
+    }
+    *mean_out = mean;
+    *sd_out = std::sqrt(ssd / static_cast<double>(n));
+  }
+
   void loop_size_stats() {
     CellState& s = s_;
     const std::size_t n = s.num_active;
@@ -718,16 +734,9 @@ class CellSim {
       s.avg_buff.clear();
       return;
     }
-    auto loop = [&](std::size_t i) -> u64 { return s.bound(i) ? s.fwd[i] - s.rev[i] : 0; };
-    double acc = 0.0;  // stats::mean (src/stats/descriptive_impl.hpp:22-32)
-    for (std::size_t i = 0; i < n; ++i) acc = acc + static_cast<double>(loop(i));
-    const double mean = acc / static_cast<double>(n);
-    double ssd = 0.0;  // sum_of_squared_deviations (:64-76)
-    for (std::size_t i = 0; i < n; ++i) {
-      const double d = static_cast<double>(loop(i)) - mean;
-      ssd = ssd + (d * d);
-    }
-    const double sd = std::sqrt(ssd / static_cast<double>(n));
+    double mean = 0.0, sd = 0.0;
+    loop_size_mean_sd(n, [&](std::size_t i) -> u64 { return s.bound(i) ? s.fwd[i] - s.rev[i] : 0; },
+                      &mean, &sd);
     if (s.avg_buff.size() == p_.burnin_history) {
       s.avg_buff.pop_front();
       s.cv_buff.pop_front();

@@ -276,6 +276,38 @@ int emu_collision_steps(u32 steps, u64 start, u64 end, size_t n, u64* rev, u64* 
   return 0;
 }
 
+// One burn-in step of the kernel source on LEFs with the given loop sizes (all active and bound):
+// out = {mean loop size, coefficient of variation} as pushed into the burn-in history.
+int emu_loop_size_stats(const u64* loop_sizes, size_t n, double* out, int virtual_threads) {
+  modle_b200_sim_params p;
+  modle_b200_default_params(&p);
+  modle_b200_transform_params(&p, 0, 0, 0);
+  u64 end = 16;
+  for (size_t i = 0; i < n; ++i) end = std::max<u64>(end, loop_sizes[i] + 16);
+  modle_b200_interval iv{end, 0, end, n};
+  EmuCell cell;
+  g_emu_error = cell.setup(p, iv, nullptr, 0, 0);
+  if (!g_emu_error.empty()) return -1;
+  u64 missed = 0;
+  Sinks K{nullptr, nullptr, &missed};
+  Cta cta{&cell.shared->scratch, virtual_threads};
+  modle_b200_cell_task t{};
+  CellSim sim{cell.kp, cell.D, cell.A, *cell.shared, K, cta, to_task(t)};
+  sim.init_cell();
+  CellShared& S = *cell.shared;
+  S.num_active = static_cast<u32>(n);
+  for (size_t i = 0; i < n; ++i) {
+    cell.A.rev[i] = 8;
+    cell.A.fwd[i] = static_cast<u32>(8 + loop_sizes[i]);
+    cell.A.ep[i] = 0;
+  }
+  sim.burnin_step();
+  if (S.hist_len != 1 || S.fault) return -2;
+  out[0] = S.avg_hist[S.hist_head];
+  out[1] = S.cv_hist[S.hist_head];
+  return 0;
+}
+
 int emu_rank_lefs(const u64* rev, const u64* fwd, const u64* ep, u64* rr, u64* fr, size_t n,
                   int virtual_threads) {
   modle_b200_sim_params p;

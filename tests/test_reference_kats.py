@@ -126,3 +126,33 @@ def test_index_encoding_roundtrip():
     got = sorted((int(a), int(b), int(c)) for a, b, c, _ in px.tolist())
     assert got == sorted(want)
     assert band[9] == 10 and (1, 2, 10) in got  # encode_idx(1, 2, nrows = 4) == 9
+
+
+def test_burnin_statistics_reference_kats():
+    """test/units/stats/descriptive_test.cpp "Mean" / "Sum of squared deviations" / "Variance" /
+    "Standard Deviation" on {0..10}: mean 5, SSD 110, population variance 10, standard deviation
+    3.1622776601683795 -- the statistics compute_loop_size_stats (simulation.cpp:795-819) feeds the
+    burn-in history with, here through the oracle's and the kernel source's burn-in step."""
+    v = np.arange(11, dtype=np.uint64)
+    out = (C.c_double * 2)()
+    L = pyoracle.lib()
+    L.oracle_loop_size_stats.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_double)]
+    L.oracle_loop_size_stats.restype = None
+    L.oracle_loop_size_stats(v.ctypes.data, len(v), out)
+    assert out[0] == 5.0 and out[1] == 3.1622776601683795
+    assert out[1] ** 2 * len(v) == pytest.approx(110.0, rel=1e-15)
+    E = emu_lib.lib()
+    E.emu_loop_size_stats.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_double), C.c_int]
+    for threads in (1, 4, 64):
+        assert E.emu_loop_size_stats(v.ctypes.data, len(v), out, threads) == 0
+        assert out[0] == 5.0
+        assert out[1] == pytest.approx(3.1622776601683795 / 5.0, rel=1e-15)  # cv = sd / mean
+    # a loop-size vector of the size of a real chromosome: kernel (tree order) vs oracle
+    # (left to right, as the reference) agree to a few ulp (DESIGN.md 3, "FP fidelity")
+    rng = np.random.default_rng(9)
+    big = rng.integers(0, 400_000, 4979).astype(np.uint64)
+    L.oracle_loop_size_stats(big.ctypes.data, len(big), out)
+    mean_o, sd_o = out[0], out[1]
+    assert E.emu_loop_size_stats(big.ctypes.data, len(big), out, 1024) == 0
+    assert out[0] == mean_o
+    assert abs(out[1] - sd_o / mean_o) <= 8 * np.spacing(sd_o / mean_o)
