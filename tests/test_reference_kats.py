@@ -156,3 +156,34 @@ def test_burnin_statistics_reference_kats():
     assert E.emu_loop_size_stats(big.ctypes.data, len(big), out, 1024) == 0
     assert out[0] == mean_o
     assert abs(out[1] - sd_o / mean_o) <= 8 * np.spacing(sd_o / mean_o)
+
+
+@pytest.mark.parametrize("impl", ["oracle", "kernel source"])
+def test_bind_lefs_reference_properties(impl):
+    """test/units/simulation_cpu/simulation_simple_unit_test.cpp "Bind LEFs 001 / 003": every LEF
+    selected for binding ends up bound at one position inside [start, end) and both rank arrays
+    are sorted. Here after the first epoch of a --skip-burnin run (all LEFs are selected at epoch
+    0; one epoch of extrusion later a LEF is either released or holds rev <= fwd inside the
+    interval, bound at epoch 0), and with extrusion speed 1 bp / no release the bound position
+    itself is visible: fwd - rev <= 2."""
+    from common import make_case
+
+    for kw in (dict(), dict(rev_extrusion_speed=1, fwd_extrusion_speed=1,
+                            rev_extrusion_speed_std=0.0, fwd_extrusion_speed_std=0.0,
+                            avg_lef_processivity=10**12)):
+        p, iv, bars, tasks = make_case(size=4_000_000, start=500_000, end=3_500_000, ncells=1,
+                                       nbar=40, seed=2, skip_burnin=1, debug_max_epochs=1, **kw)
+        snap = (pyoracle.snapshot_cell(p, iv, bars, tasks[0]) if impl == "oracle"
+                else emu_lib.snapshot_cell(p, iv, bars, tasks[0], virtual_threads=32))
+        n = int(iv.num_lefs)
+        unbound = np.uint64(2**64 - 1)
+        rev, fwd, ep = snap["rev_pos"], snap["fwd_pos"], snap["binding_epoch"]
+        bound = ep != unbound
+        assert snap["num_active_lefs"] == n and bound.sum() > 0.9 * n
+        assert np.all(rev[bound] >= int(iv.start)) and np.all(fwd[bound] < int(iv.end))
+        assert np.all(rev[bound] <= fwd[bound]) and np.all(ep[bound] == 0)
+        assert np.all(rev[~bound] == unbound) and np.all(fwd[~bound] == unbound)
+        if kw:
+            assert bound.all() and np.all(fwd - rev <= 2)
+        for ranks, pos in ((snap["rev_ranks"], rev), (snap["fwd_ranks"], fwd)):
+            assert sorted(ranks.tolist()) == list(range(n))  # check_that_lefs_are_sorted_by_idx
