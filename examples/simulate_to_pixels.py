@@ -9,6 +9,7 @@
 
     python examples/simulate_to_pixels.py hg38.chrom.sizes barriers.bed out_prefix \
         [--intervals regions.bed] [--ncells 64] [--target-contact-density 0.1] [--seed 0]
+        [--throughput-mode]
 
 Writes <out_prefix>.pixels.tsv (bin1_id, bin2_id, count: the cooler pixel table of the run) and
 <out_prefix>.lef_occupancy.bedgraph. Needs a CUDA GPU (there is no CPU fallback). Plain-text
@@ -36,6 +37,9 @@ def main():
     ap.add_argument("--target-contact-density", type=float, default=0.1)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--device", type=int, default=0)
+    ap.add_argument("--throughput-mode", action="store_true",
+                    help="counter-based draws (statistically equivalent, not bit-identical to the "
+                         "reference's draw order; modle_b200_set_rng_mode)")
     args = ap.parse_args()
 
     p = host.default_params()
@@ -44,7 +48,7 @@ def main():
     p.seed = args.seed
     host.transform_params(p)
     genome = host.import_genome(args.chrom_sizes, args.extrusion_barriers, p, args.intervals)
-    ctx = Context(args.device)
+    ctx = Context(args.device, rng_mode=1 if args.throughput_mode else 0)
     with open(args.out_prefix + ".pixels.tsv", "w") as px_out, \
             open(args.out_prefix + ".lef_occupancy.bedgraph", "w") as occ_out:
         for g in genome:
