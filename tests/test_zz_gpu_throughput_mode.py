@@ -45,7 +45,7 @@ def test_device_equals_emulation(thr_ctx, emu_throughput, name):
     gpu = thr_ctx.simulate_interval(p, iv, bars, tasks)
     assert gpu[2]["device_fault"].max() == 0
     assert gpu[2]["num_rng_draws"].max() == 0
-    emu = emu_lib.simulate_interval(p, iv, bars, tasks, virtual_threads=128)
+    emu = emu_lib.simulate_interval(p, iv, bars, tasks, virtual_threads=32)  # (any width: same result)
     assert results_equal(gpu, emu) == []
 
 
