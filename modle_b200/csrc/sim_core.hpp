@@ -987,7 +987,10 @@ struct CellSimT {
         c += u64(A.ep[f] == cur) << 32;
       }
       cnt[tid] = c;
-      if (cta.leader(tid)) S.tmp_u32[5] = 0;
+      if (cta.leader(tid)) {
+        S.tmp_u32[5] = 0;
+        if constexpr (kCtr) S.tmp_u32[6] = S.tmp_u32[7] = 0;
+      }
     }
     const u64 tot = cta.exscan_sum(cnt);
     const u32 nc = static_cast<u32>(tot & 0xFFFFFFFFu);
@@ -996,6 +999,69 @@ struct CellSimT {
       return;
     }
     if (nc != 0) rank_lefs_merge(cnt, nc, prev_r, prev_f);
+    if constexpr (kCtr) {
+      // Window repair (tried in the throughput mode first; the result of a sort does not depend
+      // on how it is reached). The odd-even passes below move a rank one slot per sweep and
+      // typically need three passes = six sweeps; here every thread insertion-sorts
+      // its own chunk of consecutive ranks, then the chunk shifted by half its length, and a
+      // read-only sweep over all adjacent pairs verifies: three sweeps in the usual case. (Needs
+      // chunks of at least two ranks for the shifted windows to straddle the chunk boundaries;
+      // the few LEFs of the first burn-in epochs take the general repair.)
+      for (u32 round = 0; round < 4 && n >= 2 * static_cast<u32>(cta.nt()); ++round) {
+        for (u32 half = 0; half < 2; ++half) {
+          MB_REGION(cta, tid) {
+            u32 lo, hi;
+            chunk(tid, n, &lo, &hi);
+            if (half == 1) {
+              u32 lo2 = n, hi2 = n;
+              if (tid + 1 < cta.nt()) chunk(tid + 1, n, &lo2, &hi2);
+              lo = lo + (hi - lo) / 2;
+              hi = lo2 + (hi2 - lo2) / 2;
+            }
+            bool moved = false;
+            for (u32 k = lo + 1; k < hi; ++k) {
+              const u16 x = A.rr[k];
+              u32 j = k;
+              while (j > lo && rank_less<true>(x, A.rr[j - 1], prev_r)) {
+                A.rr[j] = A.rr[j - 1];
+                --j;
+              }
+              if (j != k) {
+                A.rr[j] = x;
+                moved = true;
+              }
+              const u16 y = A.fr[k];
+              j = k;
+              while (j > lo && rank_less<false>(y, A.fr[j - 1], prev_f)) {
+                A.fr[j] = A.fr[j - 1];
+                --j;
+              }
+              if (j != k) {
+                A.fr[j] = y;
+                moved = true;
+              }
+            }
+            (void)moved;
+          }
+          cta.sync();
+        }
+        MB_REGION(cta, tid) {
+          u32 lo, hi;
+          chunk(tid, n, &lo, &hi);
+          bool bad = false;
+          for (u32 k = lo; k < hi && k + 1 < n; ++k) {
+            bad |= rank_less<true>(A.rr[k + 1], A.rr[k], prev_r);
+            bad |= rank_less<false>(A.fr[k + 1], A.fr[k], prev_f);
+          }
+          if (bad) MB_SHARED_STORE_U32(&S.tmp_u32[6 + (round & 1)], 1u);
+          // the other flag was last read before this round's first barrier: safe to reset now
+          if (cta.leader(tid)) S.tmp_u32[6 + ((round + 1) & 1)] = 0;
+        }
+        cta.sync();
+        if (S.tmp_u32[6 + (round & 1)] == 0) return;
+      }
+      cta.sync();  // (not sorted after four rounds, or too few LEFs: the general repair)
+    }
     // Verify / repair: units can legitimately cross during extrude() (a unit is not tested
     // against the unit behind an avoided secondary collision) and new ties need their epoch
     // order, so run odd-even transposition passes until one finds nothing to swap.
