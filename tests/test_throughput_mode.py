@@ -259,3 +259,39 @@ def test_stripe_pearson_matches_a_pixel_by_pixel_loop():
                 assert np.isnan(got[i])
             else:
                 assert abs(got[i] - np.corrcoef(x, y)[0, 1]) < 1e-12
+
+
+def test_internal_state_statistics_match_the_oracle(throughput):
+    """The per-epoch quantities of Simulation::dump_stats (collisions by kind, stalled units,
+    occupied barriers, mean loop size) are much more sensitive to a mis-wired trial probability
+    than the contact matrix is: compare their per-cell averages over the epochs 300-599 between
+    the throughput mode and the oracle (independent seeds; every collision Bernoulli fractional),
+    against the cell-to-cell spread (4 standard errors)."""
+    kw = dict(size=10_000_000, ncells=48, nbar=180, name="chrL", target_contact_density=20.0,
+              lef_bar_major_collision_pblock=0.7, lef_bar_minor_collision_pblock=0.2,
+              probability_of_extrusion_unit_bypass=0.3)
+    cap = 600
+    p, iv, bars, _ = make_case(seed=7, **kw)
+    p.seed = 1
+    t_thr = host.make_cell_tasks(p, "chrL", iv)
+
+    def part(chunk):
+        emu_lib.set_rng_mode(1)
+        return emu_lib.simulate_interval(p, iv, bars, chunk, virtual_threads=64,
+                                         log_capacity_per_cell=cap)[4]
+    with ThreadPoolExecutor(8) as ex:
+        log_t = np.concatenate(list(ex.map(part, np.array_split(t_thr, 8))))
+    p2 = p.copy()
+    p2.seed = 2
+    log_o = pyoracle.simulate_interval(p2, iv, bars, host.make_cell_tasks(p2, "chrL", iv),
+                                       nthreads=8, log_capacity_per_cell=cap)[4]
+    assert log_t.shape == log_o.shape == (48, cap)
+    fields = ["barriers_occupied", "lefs_stalled_rev", "lefs_stalled_fwd", "lefs_stalled_both",
+              "lef_bar_collisions", "lef_lef_primary_collisions", "lef_lef_secondary_collisions",
+              "loop_size_sum", "num_lefs"]
+    for f in fields:
+        a = log_t[f][:, 300:].astype(np.float64).mean(axis=1)  # one average per cell
+        b = log_o[f][:, 300:].astype(np.float64).mean(axis=1)
+        se = np.sqrt(a.var(ddof=1) / len(a) + b.var(ddof=1) / len(b))
+        assert abs(a.mean() - b.mean()) <= 4 * se + 1e-9, (f, a.mean(), b.mean(), se)
+        assert b.mean() > 0 or f == "lefs_stalled_both", f
