@@ -107,7 +107,8 @@ typedef struct modle_b200_interval {
   uint64_t num_lefs; /* Simulation::compute_num_lefs (simulation.cpp:1086-1090) */
 } modle_b200_interval;
 
-/* One extrusion barrier (ExtrusionBarrier, extrusion_barriers.hpp:32-60); array sorted by pos. */
+/* One extrusion barrier (ExtrusionBarrier, extrusion_barriers.hpp:32-60); array sorted by pos
+ * (a position outside [start, end) is allowed: the reference keeps such barriers). */
 typedef struct modle_b200_barrier {
   uint64_t pos;
   double stp_active;

@@ -185,7 +185,10 @@ inline std::string prepare_interval(const modle_b200_sim_params& p, const modle_
   hd->stp_inactive.resize(nb);
   hd->occupancy.resize(nb);
   for (size_t i = 0; i < nb; ++i) {
-    if (bars[i].pos < iv.start || bars[i].pos >= iv.end) return "barrier outside the interval";
+    // A barrier outside [start, end) is legal: the reference keeps a record that overlaps a
+    // --genomic-intervals range while its midpoint falls outside it (add_extrusion_barriers only
+    // asserts, genome.cpp:285-294); no unit can reach it, but it still takes its draws.
+    if (bars[i].pos >= 0xFFFFFFF0ull) return "barrier position does not fit 32-bit coordinates";
     if (i && bars[i].pos < bars[i - 1].pos) return "barriers are not sorted by position";
     if (bars[i].blocking_direction != MODLE_B200_DIR_REV &&
         bars[i].blocking_direction != MODLE_B200_DIR_FWD)

@@ -228,3 +228,32 @@ def test_reference_goldens_under_other_thread_orders(mode, thread_order):
                 pass
     for case in trg.RANK_CASES:
         trg.test_rank_lefs_goldens(case)
+
+
+@pytest.mark.parametrize("mode", [0, 1], ids=["deterministic", "throughput"])
+def test_barriers_outside_the_interval_are_dead_but_draw(mode):
+    """A barrier record can overlap a --genomic-intervals range while its midpoint falls outside
+    it; the reference keeps such a barrier (genome.cpp:285-294 only asserts): no unit reaches it,
+    but it takes its draws, so the cell's trajectory differs from the run without it."""
+    p, iv, bars, tasks = make_case(size=9_000_000, start=2_000_000, end=5_000_000, ncells=2,
+                                   nbar=40, seed=4, target_contact_density=0.02)
+    extra = np.zeros(2, dtype=bars.dtype)
+    extra["pos"] = [int(iv.start) - 7, int(iv.end) + 3]
+    extra["stp_active"], extra["stp_inactive"] = bars["stp_active"][:2], bars["stp_inactive"][:2]
+    extra["blocking_direction"] = [1, 2]
+    with_dead = np.concatenate([extra[:1], bars, extra[1:]])
+    emu_lib.set_rng_mode(mode)
+    try:
+        a = emu_lib.simulate_interval(p, iv, with_dead, tasks, virtual_threads=48)
+        b = emu_lib.simulate_interval(p, iv, bars, tasks, virtual_threads=48)
+    finally:
+        emu_lib.set_rng_mode(0)
+    assert a[2]["device_fault"].max() == 0
+    assert np.array_equal(a[2]["num_contacts"], tasks["num_target_contacts"])
+    if mode == 0:
+        o = pyoracle.simulate_interval(p, iv, with_dead, tasks, nthreads=2)
+        assert results_equal(a, o) == []
+        assert results_equal(a, b) != []  # the dead barriers shifted the stream
+    else:
+        # counter-based draws are keyed by barrier index: the leading dead barrier renumbers them
+        assert results_equal(a, b) != []

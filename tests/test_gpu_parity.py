@@ -305,3 +305,19 @@ def test_internal_state_log_matches_oracle(gpu_ctx, name):
         assert (rec["lefs_stalled_both"] <= np.minimum(rec["lefs_stalled_rev"],
                                                        rec["lefs_stalled_fwd"])).all()
         assert (rec["barriers_occupied"][:ne] <= len(bars)).all()
+
+
+def test_barriers_outside_the_interval_are_dead_but_draw(gpu_ctx):
+    """A barrier whose midpoint falls outside a --genomic-intervals range is kept by the reference
+    (genome.cpp:285-294): unreachable, but it takes its draws. GPU == oracle with two of them."""
+    p, iv, bars, tasks = make_case(size=9_000_000, start=2_000_000, end=5_000_000, ncells=4,
+                                   nbar=40, seed=4, target_contact_density=0.02)
+    extra = np.zeros(2, dtype=bars.dtype)
+    extra["pos"] = [int(iv.start) - 7, int(iv.end) + 3]
+    extra["stp_active"], extra["stp_inactive"] = bars["stp_active"][:2], bars["stp_inactive"][:2]
+    extra["blocking_direction"] = [1, 2]
+    with_dead = np.concatenate([extra[:1], bars, extra[1:]])
+    a = gpu_ctx.simulate_interval(p, iv, with_dead, tasks)
+    o = pyoracle.simulate_interval(p, iv, with_dead, tasks, nthreads=4)
+    assert results_equal(a, o) == []
+    assert results_equal(a, gpu_ctx.simulate_interval(p, iv, bars, tasks)) != []
