@@ -29,3 +29,28 @@ def gpu_ctx(product_lib):
     ctx = Context(0, rng_mode=0)
     yield ctx
     ctx.close()
+
+
+# `-m gpu` tests written after the round's GPU budget was spent have not met a device yet
+# (profiles/README.md, "Not re-measured after the last code changes"). The driver runs the GPU
+# suite with `-x`, so they go last: a surprise in one of them must not hide the parity tests
+# that have already passed on a B200. Drop a name from this list once it has run on a device.
+_NOT_YET_RUN_ON_A_DEVICE = (
+    "test_zz_gpu_throughput_mode.py",
+    "test_statistical_parity.py",
+    "test_internal_state_log_matches_oracle",
+    "test_barriers_outside_the_interval_are_dead_but_draw",
+    "test_cuda_occupancy_profile_matches_oracle",
+)
+
+
+def pytest_collection_modifyitems(config, items):
+    def unproven(item):
+        return any(tag in item.nodeid for tag in _NOT_YET_RUN_ON_A_DEVICE)
+
+    items.sort(key=unproven)  # stable: keeps file order inside each group
+    # A kernel that has never run could also hang; a blocked cudaDeviceSynchronize only yields to
+    # pytest-timeout's thread method (stack dump + os._exit), which also tears the context down.
+    for item in items:
+        if unproven(item) and item.get_closest_marker("gpu") is not None:
+            item.add_marker(pytest.mark.timeout(900, method="thread"))
