@@ -143,6 +143,14 @@ MB_FN u64 mix64(u64 z) {  // SplitMix64 output function
 }
 
 // The per-cell simulator. All member functions are CTA-collective unless noted.
+// Experiment switch (default off: the product's deterministic kernels are unchanged): compile
+// with -DMODLE_B200_WINDOW_RANK_REPAIR=1 to give the deterministic mode the window repair of
+// rank_lefs() that the throughput mode uses (same permutation, fewer sweeps and barriers).
+// `modle_b200.build.build(variant=..., defines=[...])` builds such a copy for an A/B on a B200;
+// tests/test_emulation_parity.py checks the variant against the oracle on the CPU.
+#ifndef MODLE_B200_WINDOW_RANK_REPAIR
+#define MODLE_B200_WINDOW_RANK_REPAIR 0
+#endif
 // kCtr = false: deterministic mode (the reference's draw order); true: throughput mode.
 template <bool kCtr>
 struct CellSimT {
@@ -966,6 +974,7 @@ struct CellSimT {
   // between unchanged LEFs are repaired by odd-even transposition passes, and anything else
   // (more changed LEFs than the scratch holds, a still unsorted list) takes the full sort.
   MB_FN void rank_lefs() {
+    constexpr bool kWindowRepair = kCtr || MODLE_B200_WINDOW_RANK_REPAIR != 0;
     const u32 n = S.num_active;
     if (n < 2) return;
     // scratch areas that are dead at this point of the epoch: moves, collision words, scratch
@@ -989,7 +998,7 @@ struct CellSimT {
       cnt[tid] = c;
       if (cta.leader(tid)) {
         S.tmp_u32[5] = 0;
-        if constexpr (kCtr) S.tmp_u32[6] = S.tmp_u32[7] = 0;
+        if constexpr (kWindowRepair) S.tmp_u32[6] = S.tmp_u32[7] = 0;
       }
     }
     const u64 tot = cta.exscan_sum(cnt);
@@ -999,7 +1008,7 @@ struct CellSimT {
       return;
     }
     if (nc != 0) rank_lefs_merge(cnt, nc, prev_r, prev_f);
-    if constexpr (kCtr) {
+    if constexpr (kWindowRepair) {
       // Window repair (tried in the throughput mode first; the result of a sort does not depend
       // on how it is reached). The odd-even passes below move a rank one slot per sweep and
       // typically need three passes = six sweeps; here every thread insertion-sorts

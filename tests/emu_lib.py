@@ -24,11 +24,16 @@ def build(force=False):
                                         "host_rng.hpp", "host.cpp", "status.hpp", "ziggurat_tables.inc")]
     deps.append(os.path.join(_HERE, "..", "..", "include", "modle_b200.h"))
     cxx = os.environ.get("CXX", "g++")
+    # MODLE_B200_EMU_DEFINES="A=1,B=2": an experimental copy of the kernel source (the switches of
+    # sim_core.hpp, e.g. MODLE_B200_WINDOW_RANK_REPAIR=1) in its own library next to the default one
+    defines = [d for d in os.environ.get("MODLE_B200_EMU_DEFINES", "").split(",") if d]
+    name = "libemu.so" if not defines else "libemu_variant.so"
+    flags = CXXFLAGS + ["-D" + d for d in defines]
     return buildutil.ensure_built(
-        os.path.join(_HERE, "libemu.so"), deps,
-        lambda tmp: [cxx] + CXXFLAGS + ["-o", tmp, os.path.join(_HERE, "emu_capi.cpp"),
-                                        os.path.join(csrc, "host.cpp")],
-        extra=" ".join(CXXFLAGS), force=force)
+        os.path.join(_HERE, name), deps,
+        lambda tmp: [cxx] + flags + ["-o", tmp, os.path.join(_HERE, "emu_capi.cpp"),
+                                     os.path.join(csrc, "host.cpp")],
+        extra=" ".join(flags), force=force)
 
 
 def lib():
