@@ -53,4 +53,4 @@ def pytest_collection_modifyitems(config, items):
     # pytest-timeout's thread method (stack dump + os._exit), which also tears the context down.
     for item in items:
         if unproven(item) and item.get_closest_marker("gpu") is not None:
-            item.add_marker(pytest.mark.timeout(900, method="thread"))
+            item.add_marker(pytest.mark.timeout(300, method="thread"))
