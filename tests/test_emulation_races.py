@@ -84,12 +84,15 @@ def tsan_binary(tsan_cxx):
                                         "host_rng.hpp", "host.cpp", "status.hpp",
                                         "ziggurat_tables.inc")]
     cxx = tsan_cxx
-    out = os.path.join(EMU, "emu_mt_main")
+    # MODLE_B200_EMU_DEFINES: the same experiment switches as tests/emu_lib.py, in a binary of its own
+    defines = [d for d in os.environ.get("MODLE_B200_EMU_DEFINES", "").split(",") if d]
+    flags = CXXFLAGS + ["-D" + d for d in defines]
+    out = os.path.join(EMU, "emu_mt_main" if not defines else "emu_mt_main_variant")
     try:
         buildutil.ensure_built(
-            out, deps, lambda tmp: [cxx] + CXXFLAGS + ["-o", tmp, os.path.join(EMU, "emu_mt_main.cpp"),
-                                                      os.path.join(csrc, "host.cpp")],
-            extra=" ".join(CXXFLAGS))
+            out, deps, lambda tmp: [cxx] + flags + ["-o", tmp, os.path.join(EMU, "emu_mt_main.cpp"),
+                                                   os.path.join(csrc, "host.cpp")],
+            extra=" ".join(flags))
     except Exception as e:  # no libtsan in this toolchain
         pytest.skip(f"cannot build the ThreadSanitizer harness: {e}")
     return out
