@@ -26,6 +26,7 @@ split over ranks -- workload c3 -- is summed with one NCCL reduce). Total work i
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -112,89 +113,124 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(self.samples)}
 
 
-def build_workload(name, cells):
+WORKLOAD_DESC = {
+    "c1": "C1 chr20 shape, %d cells, 5 kb bins, default parameters",
+    "c2": "C2 GRCh38 genome-wide shape (24 chromosomes, 38,815 synthetic barriers), %d cells, "
+          "5 kb bins, default parameters",
+    "c3": "C3 chr1 shape, %d cells, 5 kb bins, default parameters",
+    "c4": "C4 high-collision: chr20 size, 80 LEFs/Mbp, barriers 1/15 kb, bypass 0.01, %d cells",
+    "c5": "C5 fine-resolution scatter: chr2 shape, 1 kb bins, 3 Mbp diagonal width, %d cells",
+}
+
+
+def build_workload_desc(name, cells):
+    """(Config overrides, genome, description) as plain data (no native code involved)."""
     from modle_b200 import workloads
 
-    if name == "c1":
-        cfg, genome = workloads.config_c1(cells or 512)
-        desc = "C1 chr20 shape, %d cells, 5 kb bins, default parameters"
-    elif name == "c3":
-        cfg, genome = workloads.config_c3(cells or 8192)
-        desc = "C3 chr1 shape, %d cells, 5 kb bins, default parameters"
-    elif name == "c4":
-        cfg, genome = workloads.config_c4(cells or 512)
-        desc = "C4 high-collision: chr20 size, 80 LEFs/Mbp, barriers 1/15 kb, bypass 0.01, %d cells"
-    else:
-        cfg, genome = workloads.config_c2(cells or 512)
-        desc = "C2 GRCh38 genome-wide shape (24 chromosomes, 38,815 synthetic barriers), " \
-               "%d cells, 5 kb bins, default parameters"
+    overrides, genome = workloads.spec(name, cells or None)
+    desc = WORKLOAD_DESC[name]
     chroms = os.environ.get("MODLE_B200_BENCH_CHROMS")  # diagnostics: restrict the genome
     if chroms:
         keep = set(chroms.split(","))
         genome = [g for g in genome if g[0] in keep]
         desc += " [only " + chroms + "]"
-    return cfg, genome, desc % int(cfg.num_cells)
+    return overrides, genome, desc % int(overrides["num_cells"])
+
+
+def build_workload(name, cells, **more):
+    from modle_b200.simulation import Config
+
+    overrides, genome, desc = build_workload_desc(name, cells)
+    overrides.update(more)
+    return Config(**overrides).transform(), genome, desc
 
 
 # ------------------------------------------------------------------------------- CPU (oracle)
-def cpu_sample_cells(cfg, genome, cores, target_seconds=10.0, lu_per_core_s=4.5e6):
-    """Cells per interval for the bounded CPU sample: a multiple of the core count sized for
-    about `target_seconds` of wall time (the oracle does ~4-5 M LEF-updates/s per core)."""
-    from modle_b200 import host
+# The reference feeds the (interval, cell) tasks of the WHOLE run through one queue that all
+# worker threads pop from (scheduler_simulate.cpp:104-160 produce, :190-271 consume), so the CPU
+# arm does the same: one queue over every sampled task, `cores` workers, at least
+# CPU_MIN_CELLS_PER_THREAD cells per worker (burn-in lengths vary 3x from cell to cell; with one
+# cell per thread the wall time would be the slowest cell's). Inputs are built by oracle-side code
+# only (oracle/pyparams.py, the oracle's own task fan-out): the product library is not loaded.
+CPU_MIN_CELLS_PER_THREAD = 8
+CPU_LU_PER_CORE_S = 3.0e6   # what the oracle does per core, to size the sample (a guess is fine)
 
-    p = cfg.params
-    lu_per_cell = sum(host.compute_num_lefs(p, e - s) for _, _, s, e, _ in genome) * 545.0
-    k = max(1, int(round(target_seconds * lu_per_core_s / lu_per_cell)))
-    return max(1, min(int(cfg.num_cells), cores * k))
+
+def cpu_sample_plan(overrides, genome, cores, target_seconds):
+    """Cells per interval so that the sample is about `target_seconds` of wall time and every
+    worker gets >= CPU_MIN_CELLS_PER_THREAD tasks from the queue."""
+    from oracle import pyparams
+
+    p = pyparams.make_params(**overrides)
+    n_iv = max(1, len(genome))
+    lu_per_cell_all = sum(pyparams.compute_num_lefs(p, e - s) for _, _, s, e, _ in genome) * 545.0
+    by_time = target_seconds * cores * CPU_LU_PER_CORE_S / max(1.0, lu_per_cell_all)
+    by_queue = CPU_MIN_CELLS_PER_THREAD * cores / n_iv
+    return int(max(1, min(int(p.num_cells), math.ceil(max(by_time, by_queue)))))
 
 
-def oracle_sample_run(cfg, genome, cells_per_interval, nthreads_total):
-    """Simulates the first `cells_per_interval` cells of every interval with the CPU oracle, one
-    interval after the other, cells spread over `nthreads_total` threads (the reference's
-    one-cell-per-worker-thread layout). Returns (lef_updates, seconds, cores_used)."""
-    from modle_b200 import abi, host
+def oracle_sample_run(overrides, genome, cells_per_interval, cores, jobs=None):
+    """Simulates the first `cells_per_interval` cells of every interval with the CPU oracle through
+    one task queue. Returns (lef_updates, seconds, params_and_jobs)."""
     from oracle import pyoracle
 
-    p = cfg.params
-    jobs = []
-    for name, size, start, end, recs in genome:
-        iv = abi.Interval(size, start, end, host.compute_num_lefs(p, end - start))
-        bars = host.barriers_from_records(recs, p)
-        tasks = host.make_cell_tasks(p, name, iv)[:cells_per_interval]
-        jobs.append((iv, bars, tasks))
+    if jobs is None:
+        jobs = pyoracle.genome_jobs(overrides, genome, cells_per_interval)
+    p, j = jobs
     pyoracle.lib()
-    used = max(1, min(nthreads_total, cells_per_interval))
     t0 = time.perf_counter()
-    res = [pyoracle.simulate_interval(p, iv, bars, tasks, nthreads=used)
-           for iv, bars, tasks in jobs]
+    res = pyoracle.simulate_genome(p, j, nthreads=cores)
     dt = time.perf_counter() - t0
     lu = sum(int(r[2]["num_lef_updates"].sum()) for r in res)
-    return lu, dt, used
+    return lu, dt, jobs
+
+
+def cpu_arm(workload, cells, cores, target_seconds, warmup, steps):
+    """Times the oracle on a bounded sample; returns (value, seconds per step, cpu_baseline dict)."""
+    from modle_b200 import workloads
+
+    overrides, genome = workloads.spec(workload, cells or None)
+    chroms = os.environ.get("MODLE_B200_BENCH_CHROMS")
+    if chroms:
+        genome = [g for g in genome if g[0] in set(chroms.split(","))]
+    cpi = cpu_sample_plan(overrides, genome, cores, target_seconds)
+    jobs = None
+    for _ in range(max(1, warmup)):   # first call: page faults, thread start-up, table set-up
+        _, _, jobs = oracle_sample_run(overrides, genome, max(1, cpi // 8), cores)
+    jobs = None
+    lu_tot, t_tot = 0, 0.0
+    for _ in range(steps):
+        lu, dt, jobs = oracle_sample_run(overrides, genome, cpi, cores, jobs)
+        lu_tot += lu
+        t_tot += dt
+    n_tasks = sum(len(j[2]) for j in jobs[1])
+    sample = (f"first {cpi} cell(s) of each of the {len(jobs[1])} intervals per step = {n_tasks} "
+              f"(interval, cell) tasks in ONE queue over {cores} worker threads "
+              f"({n_tasks / cores:.1f} per thread); {lu_tot // max(1, steps)} LEF-updates, "
+              f"{t_tot / max(1, steps):.1f} s per step; warm-up run excluded")
+    value = lu_tot / t_tot
+    return value, t_tot / max(1, steps), {
+        "value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+        "cells_per_thread": n_tasks / cores, "same_config": False,
+        "note": "in-repo oracle port (the real modle cannot be built offline); a sub-sample of "
+                "the cells of the same workload"}
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    cfg, genome, desc = build_workload(args.workload, args.cells)
     cores = os.cpu_count() or 1
-    # bounded sample: every interval, a few cells each (work scales with the core count)
-    cpi = cpu_sample_cells(cfg, genome, cores)
-    sample = f"first {cpi} cell(s) of each of the {len(genome)} intervals of the workload per step"
-    for _ in range(args.warmup):
-        oracle_sample_run(cfg, genome, cpi, cores)
-    lu_tot, t_tot, used = 0, 0.0, cores
-    for _ in range(args.steps):
-        lu, dt, used = oracle_sample_run(cfg, genome, cpi, cores)
-        lu_tot += lu
-        t_tot += dt
-    value = lu_tot / t_tot
+    steps = max(1, args.steps)
+    # the whole --steps K --warmup W run should end within a few minutes
+    target = max(4.0, min(20.0, 180.0 / (steps + 1)))
+    value, s_per_step, cpu = cpu_arm(args.workload, args.cells, cores, target, args.warmup, steps)
+    _, _, desc = build_workload_desc(args.workload, args.cells)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
+        "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * s_per_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int64/f64",
-        "data": "synthetic", "config": {"workload": desc, "sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": "port",
-                         "sample": sample},
+        "data": "synthetic", "config": {"workload": desc, "sample": cpu["sample"]},
+        "cpu_baseline": cpu,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference cannot be built offline (SURVEY 8c); oracle restatement timed instead",
     }
@@ -358,12 +394,7 @@ def run_ours(args, rank, world, local_rank):
     # ---- CPU baseline (rank 0, single-GPU runs only) ------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        cpi = cpu_sample_cells(cfg, genome, cores)
-        lu, dt, used = oracle_sample_run(cfg, genome, cpi, cores)
-        cpu = {"value": lu / dt, "unit": UNIT, "cores": used, "kind": "port",
-               "sample": f"first {cpi} cell(s) of each of the {len(genome)} intervals "
-                         f"({lu} LEF-updates, {dt:.1f} s)"}
+        _, _, cpu = cpu_arm(args.workload, args.cells, os.cpu_count() or 1, 12.0, 1, 1)
 
     if rank == 0:
         tot_cyc = max(1, phases.get("total", 1))
@@ -420,7 +451,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4"])
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--cells", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--rng-mode", default="deterministic", choices=["deterministic", "throughput"],

@@ -323,6 +323,74 @@ int oracle_simulate_interval(const modle_b200_sim_params* params,
                                          missed_updates_out, nthreads, nullptr, 0);
 }
 
+// The reference's scheduling for a whole run (scheduler_simulate.cpp:104-160 produce, :190-271
+// consume): ONE queue holds the (interval, cell) tasks of every interval in genome order and
+// `nthreads` workers pop from it until it is empty, so a worker that finishes a short cell moves
+// on to the next task whatever interval it belongs to. All arrays are indexed by interval;
+// band / occ1d / stats / missed are caller-owned (zeroed). Used by bench.py's CPU arm.
+int oracle_simulate_genome(const modle_b200_sim_params* params, std::size_t num_intervals,
+                           const modle_b200_interval* intervals,
+                           const modle_b200_barrier* const* barriers,
+                           const std::size_t* num_barriers,
+                           const modle_b200_cell_task* const* tasks, const std::size_t* num_cells,
+                           u32* const* band_out, u64* const* occ1d_out,
+                           modle_b200_cell_stats* const* stats_out, u64* missed_updates_out,
+                           int nthreads) {
+  struct PerInterval {
+    Params p;
+    Barriers B;
+    Interval iv;
+    ContactSink sink;
+    std::size_t first_task;
+  };
+  std::vector<PerInterval> ivs(num_intervals);
+  std::size_t total = 0;
+  for (std::size_t i = 0; i < num_intervals; ++i) {
+    PerInterval& x = ivs[i];
+    x.p = to_params(*params, intervals[i].num_lefs);
+    x.B = to_barriers(barriers[i], num_barriers[i]);
+    x.iv = Interval{intervals[i].start, intervals[i].end};
+    x.sink.geom = Band::make(x.iv.end - x.iv.start, params->diagonal_width, x.p.bin_size);
+    x.sink.band = band_out[i];
+    x.sink.occ1d = x.p.track_1d ? occ1d_out[i] : nullptr;
+    x.sink.missed = &missed_updates_out[i];
+    x.first_task = total;
+    total += num_cells[i];
+  }
+  if (nthreads < 1) nthreads = 1;
+  std::atomic<std::size_t> next{0};
+  auto worker = [&]() {
+    for (;;) {
+      const std::size_t t = next.fetch_add(1);
+      if (t >= total) return;
+      std::size_t i = 0;  // owning interval: last one whose first task is <= t
+      {
+        std::size_t lo = 0, hi = num_intervals;
+        while (hi - lo > 1) {
+          const std::size_t mid = (lo + hi) / 2;
+          if (ivs[mid].first_task <= t) lo = mid; else hi = mid;
+        }
+        i = lo;
+        while (i + 1 < num_intervals && ivs[i + 1].first_task <= t) ++i;  // (empty intervals)
+      }
+      const PerInterval& x = ivs[i];
+      const std::size_t c = t - x.first_task;
+      modle_b200_cell_stats st{};
+      const bool epochs_mode = x.p.stop_on_epochs != 0;
+      if (epochs_mode || tasks[i][c].num_target_contacts != 0) {
+        CellSim sim(x.p, x.iv, x.B, intervals[i].num_lefs, to_task(tasks[i][c]), x.sink);
+        fill_stats(st, sim.run());
+      }
+      if (stats_out && stats_out[i]) stats_out[i][c] = st;
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < nthreads; ++t) pool.emplace_back(worker);
+  worker();
+  for (auto& t : pool) t.join();
+  return 0;
+}
+
 // Runs one cell for params->debug_max_epochs epochs and dumps its state.
 int oracle_snapshot_cell(const modle_b200_sim_params* params, const modle_b200_interval* interval,
                          const modle_b200_barrier* barriers, std::size_t num_barriers,

@@ -224,6 +224,62 @@ def simulate_interval(params, interval, barriers, tasks, nthreads=1, want_occ=Tr
     return band, occ, stats, int(missed.value)
 
 
+def genome_jobs(overrides, genome, cells_per_interval=None):
+    """Inputs of a whole run built by oracle-side code only (oracle/pyparams.py + the oracle's own
+    task fan-out): (params, [(abi.Interval, barriers, tasks)]). `genome` is the plain list
+    modle_b200.workloads.spec() returns; intervals without barriers are skipped like the reference
+    does (scheduler_simulate.cpp:111-124)."""
+    from . import pyparams
+
+    p = pyparams.make_params(**overrides)
+    jobs = []
+    for name, size, start, end, recs in genome:
+        bars = pyparams.barriers_from_records([r for r in recs], p)
+        if len(bars) == 0:
+            continue
+        iv = abi.Interval(size, start, end, pyparams.compute_num_lefs(p, end - start))
+        tasks = make_cell_tasks(p, name, iv)
+        if cells_per_interval is not None:
+            tasks = tasks[:cells_per_interval]
+        jobs.append((iv, bars, np.ascontiguousarray(tasks)))
+    return p, jobs
+
+
+def simulate_genome(params, jobs, nthreads=1):
+    """All (interval, cell) tasks of `jobs` through ONE work queue served by `nthreads` workers
+    (the reference's scheduling, scheduler_simulate.cpp:104-160,190-271). Returns a list of
+    (band, occ1d, stats, missed) per job."""
+    from . import pyparams
+
+    _, _, stats_dt = abi.np_dtypes()
+    n = len(jobs)
+    ivs = (abi.Interval * n)(*[j[0] for j in jobs])
+    bands, occs, stats = [], [], []
+    for iv, _, tasks in jobs:
+        nrows, ncols = pyparams.band_shape(params, int(iv.end - iv.start))
+        bands.append(np.zeros(nrows * ncols + 1, dtype=np.uint32))
+        occs.append(np.zeros(ncols, dtype=np.uint64))
+        stats.append(np.zeros(len(tasks), dtype=stats_dt))
+    missed = np.zeros(n, dtype=np.uint64)
+
+    def ptrs(arrs):
+        return (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+
+    def sizes(arrs):
+        return (C.c_size_t * n)(*[len(a) for a in arrs])
+
+    L = lib()
+    L.oracle_simulate_genome.argtypes = [
+        C.POINTER(abi.SimParams), C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    rc = L.oracle_simulate_genome(
+        C.byref(params), n, ivs, ptrs([j[1] for j in jobs]), sizes([j[1] for j in jobs]),
+        ptrs([j[2] for j in jobs]), sizes([j[2] for j in jobs]), ptrs(bands), ptrs(occs),
+        ptrs(stats), missed.ctypes.data, int(nthreads))
+    assert rc == 0
+    return [(bands[i], occs[i], stats[i], int(missed[i])) for i in range(n)]
+
+
 def band_to_pixels(band, nrows, ncols, bin_offset=0):
     """CPU counterpart of modle_b200_band_to_pixels (the reference's .cool pixel loop)."""
     band = np.ascontiguousarray(band, dtype=np.uint32)
