@@ -375,9 +375,6 @@ def run_ours(args, rank, world, local_rank):
         sum(e["ntasks"] * stats_dt.itemsize for e in mine)
 
     def step_e2e():
-        for iv in sim.intervals:
-            iv.contacts = None
-            iv.lef_1d_occupancy = None
         sim.run_simulate(num_workers=args.streams)
 
     e2e_steps = max(1, min(args.steps, 2))

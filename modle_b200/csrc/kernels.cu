@@ -17,6 +17,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/modle_b200.h"
@@ -118,17 +119,22 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks)
 // Contact register: scatters (bin1, bin2) pairs into the band with RED.ADD.U32. Each thread
 // takes four pairs per iteration through two 16-byte loads (streaming, evict-first) so that four
 // independent reductions are in flight per thread; out-of-band pairs are counted once per warp.
-__device__ __forceinline__ u32 register_one(u32 b1, u32 b2, u32 nrows, u32* __restrict__ band) {
+// A pair whose larger bin lies outside the matrix (j >= ncols) would land past the buffer: the
+// reference throws for it (bound_check_coords) before touching memory; here it is skipped and
+// counted with the out-of-band pairs.
+__device__ __forceinline__ u32 register_one(u32 b1, u32 b2, u32 nrows, u32 ncols,
+                                            u32* __restrict__ band) {
   const u32 i = b1 > b2 ? b1 - b2 : b2 - b1;
   const u32 j = b1 > b2 ? b1 : b2;
-  if (i >= nrows) return 1;
+  if (i >= nrows || j >= ncols) return 1;
   atomicAdd(band + (size_t(j) * nrows + i), 1u);  // result unused -> RED.E.ADD
   return 0;
 }
 
 __global__ void __launch_bounds__(256) k_register_contacts(const u32* __restrict__ bin1,
                                                            const u32* __restrict__ bin2, size_t n,
-                                                           u32 nrows, u32* __restrict__ band,
+                                                           u32 nrows, u32 ncols,
+                                                           u32* __restrict__ band,
                                                            u64* __restrict__ missed, int vec_ok) {
   const size_t stride = size_t(gridDim.x) * blockDim.x;
   const size_t tid = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -140,15 +146,15 @@ __global__ void __launch_bounds__(256) k_register_contacts(const u32* __restrict
     const uint4* v2 = reinterpret_cast<const uint4*>(bin2);
     for (size_t e = tid; e < n4; e += stride) {
       const uint4 a = __ldcs(v1 + e), b = __ldcs(v2 + e);
-      my_missed += register_one(a.x, b.x, nrows, band);
-      my_missed += register_one(a.y, b.y, nrows, band);
-      my_missed += register_one(a.z, b.z, nrows, band);
-      my_missed += register_one(a.w, b.w, nrows, band);
+      my_missed += register_one(a.x, b.x, nrows, ncols, band);
+      my_missed += register_one(a.y, b.y, nrows, ncols, band);
+      my_missed += register_one(a.z, b.z, nrows, ncols, band);
+      my_missed += register_one(a.w, b.w, nrows, ncols, band);
     }
     done = n4 * 4;
   }
   for (size_t e = done + tid; e < n; e += stride)
-    my_missed += register_one(__ldcs(bin1 + e), __ldcs(bin2 + e), nrows, band);
+    my_missed += register_one(__ldcs(bin1 + e), __ldcs(bin2 + e), nrows, ncols, band);
   const u32 warp_missed = __reduce_add_sync(0xffffffffu, my_missed);
   if ((threadIdx.x & 31) == 0 && warp_missed)
     atomicAdd(reinterpret_cast<unsigned long long*>(missed),
@@ -167,15 +173,15 @@ constexpr u32 kBinThreads = 512;     // k_bin_scatter: one tile counter per thre
 constexpr u32 kBinBatch = 16;        // contacts per thread per batch of k_bin_scatter
 static_assert(kBinThreads == kMaxTiles, "k_bin_scatter scans one tile counter per thread");
 
-__device__ __forceinline__ u32 band_pixel(u32 b1, u32 b2, u32 nrows) {
+__device__ __forceinline__ u32 band_pixel(u32 b1, u32 b2, u32 nrows, u32 ncols) {
   const u32 i = b1 > b2 ? b1 - b2 : b2 - b1;
   const u32 j = b1 > b2 ? b1 : b2;
-  return i >= nrows ? 0xFFFFFFFFu : j * nrows + i;
+  return (i >= nrows || j >= ncols) ? 0xFFFFFFFFu : j * nrows + i;
 }
 
 __global__ void __launch_bounds__(256) k_bin_count(const u32* __restrict__ bin1,
                                                    const u32* __restrict__ bin2, size_t n, u32 nrows,
-                                                   u32 tile_shift, u32* __restrict__ tile_counts,
+                                                   u32 ncols, u32 tile_shift, u32* __restrict__ tile_counts,
                                                    u64* __restrict__ missed) {
   __shared__ u32 hist[kMaxTiles];
   for (u32 t = threadIdx.x; t < kMaxTiles; t += blockDim.x) hist[t] = 0;
@@ -183,7 +189,7 @@ __global__ void __launch_bounds__(256) k_bin_count(const u32* __restrict__ bin1,
   const size_t stride = size_t(gridDim.x) * blockDim.x;
   u32 my_missed = 0;
   for (size_t e = size_t(blockIdx.x) * blockDim.x + threadIdx.x; e < n; e += stride) {
-    const u32 p = band_pixel(__ldcs(bin1 + e), __ldcs(bin2 + e), nrows);
+    const u32 p = band_pixel(__ldcs(bin1 + e), __ldcs(bin2 + e), nrows, ncols);
     if (p == 0xFFFFFFFFu) {
       ++my_missed;
     } else {
@@ -235,7 +241,7 @@ __global__ void __launch_bounds__(kBinThreads) k_bin_offsets(const u32* __restri
 
 __global__ void __launch_bounds__(kBinThreads) k_bin_scatter(const u32* __restrict__ bin1,
                                                              const u32* __restrict__ bin2, size_t n,
-                                                             u32 nrows, u32 tile_shift,
+                                                             u32 nrows, u32 ncols, u32 tile_shift,
                                                              u32* __restrict__ tile_cursor,
                                                              u32* __restrict__ binned) {
   // Per batch of 512 x kBinBatch contacts: count per tile, exclusive scan of the counts (start of
@@ -255,7 +261,7 @@ __global__ void __launch_bounds__(kBinThreads) k_bin_scatter(const u32* __restri
 #pragma unroll
     for (u32 k = 0; k < kBinBatch; ++k) {
       const size_t e = b0 + size_t(k) * kBinThreads + threadIdx.x;  // coalesced reads
-      px[k] = e < n ? band_pixel(__ldcs(bin1 + e), __ldcs(bin2 + e), nrows) : 0xFFFFFFFFu;
+      px[k] = e < n ? band_pixel(__ldcs(bin1 + e), __ldcs(bin2 + e), nrows, ncols) : 0xFFFFFFFFu;
     }
 #pragma unroll
     for (u32 k = 0; k < kBinBatch; ++k)
@@ -460,6 +466,26 @@ int modle_b200_synchronize(modle_b200_context* ctx) {
 }  // extern "C"
 
 namespace {
+
+// dst[i] += src[i] over a band (up to 2.9 GB): split over a few host threads, since one thread
+// adds ~2 G words/s and the genome-wide run brings 370 M words back per step.
+void add_into_u32(u32* dst, const u32* src, size_t n) {
+  const size_t kMinPerThread = size_t(1) << 22;
+  unsigned nt = std::thread::hardware_concurrency();
+  nt = std::max(1u, std::min(8u, nt));
+  nt = static_cast<unsigned>(std::min<size_t>(nt, std::max<size_t>(1, n / kMinPerThread)));
+  auto work = [=](size_t lo, size_t hi) {
+    for (size_t i = lo; i < hi; ++i) dst[i] += src[i];
+  };
+  if (nt <= 1) {
+    work(0, n);
+    return;
+  }
+  std::vector<std::thread> pool;
+  for (unsigned t = 1; t < nt; ++t) pool.emplace_back(work, n * t / nt, n * (t + 1) / nt);
+  work(0, n / nt);
+  for (auto& th : pool) th.join();
+}
 
 // Shared implementation of the two simulate entry points. All pointers are device pointers.
 int launch_simulate(modle_b200_context* ctx, const modle_b200_sim_params* params,
@@ -683,7 +709,7 @@ static int simulate_interval_host(modle_b200_context* ctx, const modle_b200_sim_
                            sizeof(modle_b200_cell_stats) * num_cells, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaMemcpyAsync(hs + off_missed, ctx->d_missed.p, sizeof(u64), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
-  for (size_t i = 0; i < npx; ++i) band_out[i] += h_band[i];
+  add_into_u32(band_out, h_band, npx);
   if (occ1d_out)
     for (size_t i = 0; i < ncols; ++i) occ1d_out[i] += h_occ[i];
   if (missed_updates_out) *missed_updates_out += *h_missed;
@@ -820,10 +846,12 @@ int modle_b200_register_contacts_device(modle_b200_context* ctx, const uint32_t*
     tile_shift = std::min(26u, std::max(kMinTileShift, tile_shift));
     while ((npx >> tile_shift) >= kMaxTiles) ++tile_shift;
     k_bin_count<<<grid, threads, 0, stream>>>(d_bin1, d_bin2, n, static_cast<u32>(nrows),
-                                              tile_shift, counts, d_missed_updates);
+                                              static_cast<u32>(ncols), tile_shift, counts,
+                                              d_missed_updates);
     k_bin_offsets<<<1, kBinThreads, 0, stream>>>(counts, cursor);
     k_bin_scatter<<<static_cast<u32>(ctx->num_sms) * 2, kBinThreads, 0, stream>>>(
-        d_bin1, d_bin2, n, static_cast<u32>(nrows), tile_shift, cursor, d_binned);
+        d_bin1, d_bin2, n, static_cast<u32>(nrows), static_cast<u32>(ncols), tile_shift, cursor,
+        d_binned);
     {
       // after k_bin_scatter cursor[t] is the END of tile t's run
       int per_sm = 0;
@@ -848,7 +876,8 @@ int modle_b200_register_contacts_device(modle_b200_context* ctx, const uint32_t*
   const size_t want = (items + threads - 1) / threads;
   const u32 grid = static_cast<u32>(std::min<size_t>(want, size_t(ctx->num_sms) * 8));
   k_register_contacts<<<grid, threads, 0, stream>>>(d_bin1, d_bin2, n, static_cast<u32>(nrows),
-                                                    d_band, d_missed_updates, vec_ok);
+                                                    static_cast<u32>(ncols), d_band,
+                                                    d_missed_updates, vec_ok);
   CUDA_TRY(cudaGetLastError());
   ++ctx->launches;
   return MODLE_B200_OK;

@@ -137,7 +137,12 @@ def interval_roots(shards):
 
 class DeviceEngine:
     """Runs shards on one GPU through the device-resident C-ABI call; buffers are torch tensors
-    (torch is the allocator / stream / collective plumbing here, nothing more)."""
+    (torch is the allocator / stream / collective plumbing here, nothing more).
+
+    Besides the launch streams it owns a reduce stream and a copy stream: an interval's reduce
+    and its device->host copy (into pinned staging that persists across calls) are queued behind
+    that interval's own launches only, so they overlap the kernels of the intervals still
+    running."""
 
     def __init__(self, device=0, num_streams=3, rng_mode=0):
         import torch
@@ -149,10 +154,14 @@ class DeviceEngine:
         torch.cuda.set_device(self.device)
         self.ctx = Context(device, rng_mode)
         self.streams = [torch.cuda.Stream(device=self.device) for _ in range(max(1, num_streams))]
+        self.reduce_stream = torch.cuda.Stream(device=self.device)
+        self.copy_stream = torch.cuda.Stream(device=self.device)
         self._next = 0
+        self._pinned = {}   # (tag, dtype, numel) -> pinned host tensor, reused across calls
 
     def close(self):
         self.torch.cuda.synchronize(self.device)
+        self._pinned.clear()
         self.ctx.close()
 
     def alloc_outputs(self, nrows, ncols):
@@ -164,7 +173,8 @@ class DeviceEngine:
 
     def run(self, params, abi_interval, barriers, tasks, band, occ, missed):
         """Asynchronous: adds the cells in `tasks` into band / occ / missed; returns the device
-        tensor that will hold the per-cell stats and the stream the work was queued on."""
+        tensor that will hold the per-cell stats and a token (CUDA event) that fires when the
+        launch is done."""
         t = self.torch
         _, _, stats_dt = abi.np_dtypes()
         stream = self.streams[self._next % len(self.streams)]
@@ -179,21 +189,82 @@ class DeviceEngine:
                 occ.data_ptr(), d_stats.data_ptr(), missed.data_ptr(), stream.cuda_stream)
             for x in (d_tasks, d_stats, band, occ, missed):
                 x.record_stream(stream)
-        return d_stats, stream
+            done = t.cuda.Event()
+            done.record(stream)
+        return d_stats, done
 
     def join(self):
         cur = self.torch.cuda.current_stream(self.device)
-        for s in self.streams:
+        for s in self.streams + [self.reduce_stream, self.copy_stream]:
             cur.wait_stream(s)
+
+    # -- hooks of run_sharded ------------------------------------------------------------------
+    def reduce(self, bufs, root, tokens, dist):
+        """Sums `bufs` onto `root` (one NCCL reduce per buffer) once `tokens` have fired; returns
+        the token of the reduce."""
+        t = self.torch
+        for ev in tokens:
+            self.reduce_stream.wait_event(ev)
+        with t.cuda.stream(self.reduce_stream):
+            for b in bufs:
+                dist.reduce(b, dst=root, op=dist.ReduceOp.SUM)
+                b.record_stream(self.reduce_stream)
+            done = t.cuda.Event()
+            done.record(self.reduce_stream)
+        return done
+
+    def to_host(self, tag, tensors, tokens):
+        """Queues device->host copies of `tensors` into pinned staging behind `tokens`; returns
+        the host tensors (valid after finish())."""
+        t = self.torch
+        for ev in tokens:
+            self.copy_stream.wait_event(ev)
+        out = []
+        with t.cuda.stream(self.copy_stream):
+            for k, x in enumerate(tensors):
+                key = (tag, k, x.dtype, x.numel())
+                h = self._pinned.get(key)
+                if h is None:
+                    h = t.empty(x.numel(), dtype=x.dtype, pin_memory=True)
+                    self._pinned[key] = h
+                h.copy_(x, non_blocking=True)
+                x.record_stream(self.copy_stream)
+                out.append(h)
+        return out
+
+    def finish(self):
+        self.join()
+        self.torch.cuda.current_stream(self.device).synchronize()
+
+
+class HostEngineHooks:
+    """Synchronous versions of the DeviceEngine hooks for engines that compute on the host (the
+    CPU tests plug the kernel emulation in through these)."""
+
+    def reduce(self, bufs, root, tokens, dist):
+        for b in bufs:
+            dist.reduce(b, dst=root, op=dist.ReduceOp.SUM)
+        return None
+
+    def to_host(self, tag, tensors, tokens):
+        return list(tensors)
+
+    def finish(self):
+        pass
 
 
 def run_sharded(engine, params, intervals, rank=0, world=1, dist=None, shards=None):
-    """Simulates this rank's shards and reduces split intervals onto their roots.
+    """Simulates this rank's shards, reduces split intervals onto their roots and brings every
+    interval this rank is the root of to the host.
 
     `intervals`: objects with chrom_name, abi_interval(), barriers, num_lefs, nrows, ncols (see
-    simulation.GenomicInterval). Returns {interval index: dict(band, occ1d, missed, stats)} with
-    torch tensors on the engine's device; an interval's band/occ1d are complete on its root rank
-    only. `dist` is torch.distributed (already initialised) when world > 1.
+    simulation.GenomicInterval). Returns {interval index: dict(band, occ1d, missed, stats, root,
+    host)}: band / occ1d / missed are tensors on the engine's device (complete on the root rank
+    only), `host` = (band, occ1d, missed) as host tensors on the root (None elsewhere), `stats`
+    numpy records per shard. `dist` is torch.distributed (already initialised) when world > 1.
+
+    Nothing here waits for the whole rank: an interval's reduce is queued behind that interval's
+    launches, its device->host copy behind its reduce (or launches), both on their own streams.
     """
     if shards is None:
         shards = plan_shards(interval_weights(intervals), int(params.num_cells), world)
@@ -201,34 +272,75 @@ def run_sharded(engine, params, intervals, rank=0, world=1, dist=None, shards=No
     _, _, stats_dt = abi.np_dtypes()
     out = {}
     # heaviest intervals first, so that the short ones fill the tail
-    mine = sorted((s for s in shards if s.rank == rank), key=lambda s: (-s.weight, s.interval))
-    for s in mine:
+    order = sorted(shards, key=lambda s: (-s.weight, s.interval, s.cell_lo))
+    for s in order:
+        if s.rank != rank:
+            continue
         iv = intervals[s.interval]
         if s.interval not in out:
             band, occ, missed = engine.alloc_outputs(iv.nrows, iv.ncols)
-            out[s.interval] = dict(band=band, occ1d=occ, missed=missed, stats=[], cells=[])
+            out[s.interval] = dict(band=band, occ1d=occ, missed=missed, stats=[], cells=[],
+                                   tokens=[])
         o = out[s.interval]
         tasks = host.make_cell_tasks(params, iv.chrom_name, iv.abi_interval())[s.cell_lo:s.cell_hi]
-        d_stats, _ = engine.run(params, iv.abi_interval(), iv.barriers, tasks, o["band"],
-                                o["occ1d"], o["missed"])
+        d_stats, token = engine.run(params, iv.abi_interval(), iv.barriers, tasks, o["band"],
+                                    o["occ1d"], o["missed"])
         o["stats"].append(d_stats)
         o["cells"].append((s.cell_lo, s.cell_hi))
-    engine.join()
-    if world > 1:
-        # Every rank walks the split intervals in the same order and joins one reduce per buffer
-        # on the world group; a rank that holds no piece of the interval contributes zeros (the
-        # volume is trivial next to NVLink bandwidth, and no sub-communicators are needed).
-        for idx in sorted(roots):
-            root, ranks = roots[idx]
-            if len(ranks) < 2:
-                continue
+        if token is not None:
+            o["tokens"].append(token)
+    # Every rank walks the intervals in the same order (that of their first launch in the global
+    # plan) and joins one reduce per buffer of a split interval on the world group; a rank that
+    # holds no piece of it contributes zeros (no sub-communicators needed, and the volume is
+    # trivial next to NVLink bandwidth).
+    seen = []
+    for s in order:
+        if s.interval not in seen:
+            seen.append(s.interval)
+    for idx in seen:
+        root, ranks = roots[idx]
+        o = out.get(idx)
+        tokens = list(o["tokens"]) if o is not None else []
+        if world > 1 and len(ranks) > 1:
             iv = intervals[idx]
-            o = out.get(idx)
             bufs = (o["band"], o["occ1d"], o["missed"]) if o is not None else \
                 engine.alloc_outputs(iv.nrows, iv.ncols)
-            for b in bufs:
-                dist.reduce(b, dst=root, op=dist.ReduceOp.SUM)
-    for idx, o in out.items():
-        o["root"] = roots[idx][0]
+            tok = engine.reduce(bufs, root, tokens, dist)
+            tokens = [tok] if tok is not None else []
+        if o is not None:
+            o["root"] = root
+            o["host"] = engine.to_host(idx, (o["band"], o["occ1d"], o["missed"]), tokens) \
+                if root == rank else None
+    engine.finish()
+    for o in out.values():
         o["stats"] = [np.frombuffer(x.cpu().numpy().tobytes(), dtype=stats_dt) for x in o["stats"]]
+        del o["tokens"]
+    check_device_faults(out, rank, world, dist, engine)
     return out
+
+
+def check_device_faults(out, rank=0, world=1, dist=None, engine=None):
+    """A cell that reports a device fault stopped early, so its interval's band is incomplete:
+    the host-buffer call returns MODLE_B200_ERR_DEVICE_FAULT for that, and so does the sharded
+    path. The flag is MAX-all-reduced so that every rank raises (no rank is left waiting in a
+    later collective with partial results in hand)."""
+    worst, where = 0, None
+    for idx, o in out.items():
+        for st, (lo, _) in zip(o["stats"], o["cells"]):
+            bad = np.nonzero(st["device_fault"])[0]
+            if len(bad) and worst == 0:
+                worst = int(st["device_fault"][bad[0]])
+                where = (idx, lo + int(bad[0]))
+    code = worst
+    if world > 1:
+        import torch
+
+        # (host engines of the CPU tests run over gloo: the flag lives on the CPU there)
+        t = torch.tensor([worst], dtype=torch.int64, device=getattr(engine, "device", "cpu"))
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        code = int(t.item())
+    if code != 0:
+        msg = f"device fault {code}"
+        msg += f" in cell {where[1]} of interval {where[0]} on rank {rank}" if where else \
+            " reported by another rank"
+        raise host.ModleB200Error(abi.ERR_DEVICE_FAULT, msg + "; the results are incomplete")

@@ -275,24 +275,15 @@ class Simulation:
         p = self.config.params
         for name, size, start, end, records in self.genome:
             iv = GenomicInterval(name, size, start, end)
-            iv.barriers = host.barriers_from_records(
-                [r for r in records if start <= r[0] < end], p)
+            # `records` are the barriers the genome importer ASSIGNED to this interval (BED records
+            # that overlap it): one whose midpoint falls outside [start, end) is kept, like the
+            # reference keeps it (genome.cpp:285-294) -- unreachable, but it takes its draws --
+            # so this mirror and modle_b200_genome_import feed the kernel the same barrier set.
+            iv.barriers = host.barriers_from_records(list(records), p)
             iv.num_lefs = host.compute_num_lefs(p, end - start)
             iv.nrows, iv.ncols = host.band_shape(p, end - start)
             iv.nrows_lazy = (int(p.diagonal_width) + int(p.bin_size) - 1) // int(p.bin_size)
             self.intervals.append(iv)
-
-    def partition(self):
-        """Whole-interval owner per interval index (see distributed.plan_shards for the general
-        plan, which also splits an interval's cells when whole intervals do not balance)."""
-        order = sorted(range(len(self.intervals)), key=lambda i: -self.intervals[i].num_lefs)
-        load = [0] * self.world_size
-        owner = {}
-        for i in order:
-            r = min(range(self.world_size), key=lambda k: load[k])
-            owner[i] = r
-            load[r] += self.intervals[i].num_lefs
-        return owner
 
     def run_simulate(self, ctx=None, num_workers=3):
         """Simulation::run_simulate (scheduler_simulate.cpp:43-170) for this process' share.
@@ -313,11 +304,12 @@ class Simulation:
                       key=lambda i: -self.intervals[i].num_lefs)
 
         def one(c, idx):
+            # every call starts from fresh output buffers (a second run_simulate() replaces the
+            # results, band / occupancy / missed / stats alike; the sharded path does the same)
             iv = self.intervals[idx]
             tasks = host.make_cell_tasks(p, iv.chrom_name, iv.abi_interval())
             iv.contacts, iv.lef_1d_occupancy, iv.stats, iv.missed_updates = \
-                c.simulate_interval(p, iv.abi_interval(), iv.barriers, tasks,
-                                    band=iv.contacts, occ1d=iv.lef_1d_occupancy)
+                c.simulate_interval(p, iv.abi_interval(), iv.barriers, tasks)
 
         if ctx is not None:
             for idx in todo:
@@ -374,9 +366,10 @@ class Simulation:
             iv.stats = np.concatenate(o["stats"]) if o["stats"] else None
             if o["root"] != self.rank:
                 continue
-            iv.contacts = o["band"].cpu().numpy().view(np.uint32)
-            iv.lef_1d_occupancy = o["occ1d"].cpu().numpy().view(np.uint64)[:iv.ncols]
-            iv.missed_updates = int(o["missed"].item())
+            band, occ, missed = o["host"]  # pinned staging, copied while other intervals ran
+            iv.contacts = band.numpy().view(np.uint32)
+            iv.lef_1d_occupancy = occ.numpy().view(np.uint64)[:iv.ncols]
+            iv.missed_updates = int(missed[0])
         return self.intervals
 
     def close(self):

@@ -12,7 +12,10 @@ for p in (os.path.dirname(HERE), HERE):
         sys.path.insert(0, p)
 
 
-class EmuEngine:
+from modle_b200.distributed import HostEngineHooks  # noqa: E402
+
+
+class EmuEngine(HostEngineHooks):
     """Same interface as modle_b200.distributed.DeviceEngine, CPU tensors, emulated kernel."""
 
     def __init__(self):
@@ -36,6 +39,9 @@ class EmuEngine:
         occ[:len(o)] += t.from_numpy(o.view(np.int64))
         missed += ms
         self.calls += 1
+        if os.environ.get("MODLE_B200_TEST_INJECT_FAULT") == os.environ.get("MODLE_B200_TEST_RANK"):
+            st = st.copy()
+            st["device_fault"][-1] = 4  # what a cell that ran out of serial draws would report
         return t.from_numpy(st.view(np.uint8).copy()), None
 
     def join(self):
@@ -85,7 +91,19 @@ def main(rank, world, port, outdir, force_split):
         S = distributed.Shard
         shards = [S(0, 0, 2, 0, 2.0), S(0, 2, 6, 1, 4.0), S(1, 0, 6, 1, 1.0)]
     eng = EmuEngine()
-    out = distributed.run_sharded(eng, p, intervals, rank, world, dist, shards=shards)
+    os.environ["MODLE_B200_TEST_RANK"] = str(rank)
+    try:
+        out = distributed.run_sharded(eng, p, intervals, rank, world, dist, shards=shards)
+    except Exception as e:  # the fault-injection test expects this on EVERY rank
+        from modle_b200 import abi, host
+
+        ok = isinstance(e, host.ModleB200Error) and e.code == abi.ERR_DEVICE_FAULT
+        if not ok:
+            import traceback
+
+            traceback.print_exc()
+        dist.destroy_process_group()
+        sys.exit(7 if ok else 1)
     res = {}
     for idx, o in out.items():
         res[f"band{idx}"] = o["band"].numpy().view(np.uint32)

@@ -144,3 +144,15 @@ def test_run_sharded_world2_gloo_matches_oracle(tmp_path, force_split):
         assert sum(int(r[f"contacts{idx}"][0]) for r in holders) == int(stats["num_contacts"].sum())
     if force_split:
         assert int(res[0]["calls"][0]) == 1 and int(res[1]["calls"][0]) == 2
+
+
+@pytest.mark.parametrize("faulty_rank", [0, 1])
+def test_a_device_fault_on_one_rank_fails_the_sharded_run_on_every_rank(tmp_path, faulty_rank):
+    """A faulting cell leaves a truncated band: run_sharded must not return it as a result, and
+    every rank has to learn about it (MAX all-reduce of the fault code)."""
+    port = _free_port()
+    env = dict(os.environ, MODLE_B200_TEST_INJECT_FAULT=str(faulty_rank))
+    procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "dist_worker.py"), str(r), "2",
+                               str(port), str(tmp_path), "1"], env=env) for r in range(2)]
+    assert [pr.wait(timeout=600) for pr in procs] == [7, 7]
+    assert not list(tmp_path.glob("rank*.npz"))

@@ -194,10 +194,7 @@ def test_run_simulate_with_worker_threads_matches_oracle(product_lib):
     genome = _small_genome()
     sim = Simulation(cfg, genome)
     try:
-        for _ in range(2):  # the second call reuses the contexts and must not accumulate
-            for iv in sim.intervals:
-                iv.contacts = None
-                iv.lef_1d_occupancy = None
+        for _ in range(2):  # the second call reuses the contexts and replaces the results
             sim.run_simulate(num_workers=3)
     finally:
         sim.close()
