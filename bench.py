@@ -46,15 +46,16 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
-def ncu_traffic_per_lef_update():
+def ncu_traffic_per_lef_update(rng_mode=0):
     """DRAM bytes (read + written) per LEF-update of k_simulate_cells from the committed
     `ncu --set full` capture (profiles/ncu_traffic.json; one launch of the chr1 shape). The
     bench scales it by the LEF-updates of an average launch."""
+    key = "k_simulate_cells" if rng_mode == 0 else "k_simulate_cells_throughput_mode"
     try:
         d = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-        return float(d["k_simulate_cells"]["dram_bytes_per_lef_update"]), d["k_simulate_cells"]["source"]
+        return float(d[key]["dram_bytes_per_lef_update"]), d[key]["source"]
     except Exception:
-        return None, None
+        return None, ("no ncu capture of the throughput-mode kernel yet" if rng_mode else None)
 
 
 def measured_peaks():
@@ -238,12 +239,311 @@ def run_reference(args, rank, world):
 
 
 # ------------------------------------------------------------------------------- GPU
+class DeviceJob:
+    """One workload staged on this rank's GPU: cell tasks and band matrices resident in HBM, the
+    shard plan of modle_b200.distributed, and `step()` = one whole simulation of the workload
+    (kernels + band memsets + the reduce of every interval whose cells are split over ranks)."""
+
+    def __init__(self, torch, dist, engine, cfg, genome, rank, world, local_rank, rng_mode,
+                 slice_all=False):
+        from modle_b200 import abi, distributed, host
+        from modle_b200.simulation import Simulation
+
+        self.torch, self.dist, self.engine = torch, dist, engine
+        self.rank, self.world = rank, world
+        self.p = cfg.params
+        self.dev = torch.device("cuda", local_rank)
+        self.sim = Simulation(cfg, genome, device=local_rank, rank=rank, world_size=world,
+                              rng_mode=rng_mode, slice_all=slice_all)
+        _, self.task_dt, self.stats_dt = abi.np_dtypes()
+        self.barrier_dt = abi.np_dtypes()[0]
+        ivs = self.sim.intervals
+        self.shards = distributed.plan_shards(distributed.interval_weights(ivs),
+                                              int(self.p.num_cells), world, slice_all=slice_all)
+        self.roots = distributed.interval_roots(self.shards)
+        self.split = [i for i, (_, ranks) in self.roots.items() if len(ranks) > 1]
+        order = sorted(self.shards, key=lambda s: (-s.weight, s.interval, s.cell_lo))
+        # reduces are issued in the same order on every rank: that of the first launch of each
+        # split interval in the global plan
+        self.split.sort(key=lambda i: next(k for k, s in enumerate(order) if s.interval == i))
+        self.bufs, self.mine = {}, []
+        for s in order:
+            if s.rank != rank:
+                continue
+            iv = ivs[s.interval]
+            if s.interval not in self.bufs:
+                self.bufs[s.interval] = engine.alloc_outputs(iv.nrows, iv.ncols)
+            tasks = host.make_cell_tasks(self.p, iv.chrom_name, iv.abi_interval())[s.cell_lo:s.cell_hi]
+            h_tasks = torch.from_numpy(tasks.view(np.uint8).reshape(-1).copy()).pin_memory()
+            self.mine.append(dict(
+                iv=iv, idx=s.interval, abi_iv=iv.abi_interval(), ntasks=len(tasks),
+                cells=(s.cell_lo, s.cell_hi), d_tasks=h_tasks.to(self.dev),
+                d_stats=torch.zeros(len(tasks) * self.stats_dt.itemsize, dtype=torch.uint8,
+                                    device=self.dev)))
+        for idx in self.split:  # a rank without a piece of a split interval contributes zeros
+            if idx not in self.bufs:
+                self.bufs[idx] = engine.alloc_outputs(ivs[idx].nrows, ivs[idx].ncols)
+        self.reduce_bytes = sum(b.numel() * b.element_size() for i in self.split
+                                for b in self.bufs[i])
+
+    def parallelism(self):
+        return (f"{self.world} rank(s), {len(self.shards)} (interval, cell-range) shards dealt "
+                f"heaviest-first, {len(self.split)} interval(s) split over ranks and summed with "
+                "one NCCL reduce each")
+
+    def step(self, main_stream, events=None, reduce_events=None):
+        torch, engine, ctx = self.torch, self.engine, self.engine.ctx
+        for band, occ, missed in self.bufs.values():
+            band.zero_()
+            occ.zero_()
+            missed.zero_()
+        done = {}
+        for k, e in enumerate(self.mine):
+            stream = engine.streams[k % len(engine.streams)]
+            stream.wait_stream(main_stream)
+            band, occ, missed = self.bufs[e["idx"]]
+            if events is not None:
+                ev0 = torch.cuda.Event(enable_timing=True)
+                ev1 = torch.cuda.Event(enable_timing=True)
+                ev0.record(stream)
+            ctx.simulate_interval_device(self.p, e["abi_iv"], e["iv"].barriers,
+                                         e["d_tasks"].data_ptr(), e["ntasks"], band.data_ptr(),
+                                         occ.data_ptr(), e["d_stats"].data_ptr(),
+                                         missed.data_ptr(), stream.cuda_stream)
+            if events is not None:
+                ev1.record(stream)
+                events.append((e, ev0, ev1))
+            if e["idx"] in self.split:
+                ev = torch.cuda.Event()
+                ev.record(stream)
+                done.setdefault(e["idx"], []).append(ev)
+        # the one exchange step: a split interval is summed onto its root as soon as ITS launches
+        # are done, on the reduce stream, while the other intervals keep running
+        for idx in self.split:
+            for ev in done.get(idx, []):
+                engine.reduce_stream.wait_event(ev)
+            engine.reduce_stream.wait_stream(main_stream)  # (the memsets above)
+            with torch.cuda.stream(engine.reduce_stream):
+                if reduce_events is not None:
+                    r0 = torch.cuda.Event(enable_timing=True)
+                    r1 = torch.cuda.Event(enable_timing=True)
+                    r0.record(engine.reduce_stream)
+                for b in self.bufs[idx]:
+                    self.dist.reduce(b, dst=self.roots[idx][0], op=self.dist.ReduceOp.SUM)
+                if reduce_events is not None:
+                    r1.record(engine.reduce_stream)
+                    reduce_events.append((r0, r1))
+        for stream in engine.streams + [engine.reduce_stream]:
+            main_stream.wait_stream(stream)
+
+    def work(self):
+        """(lef_updates, contacts, epochs, faults, algorithmic bytes) of this rank's last step."""
+        lu = contacts = epochs = faults = alg = 0
+        for e in self.mine:
+            st = e["d_stats"].cpu().numpy().view(self.stats_dt)
+            lu += int(st["num_lef_updates"].sum())
+            contacts += int(st["num_contacts"].sum())
+            epochs += int(st["num_epochs"].sum())
+            faults += int((st["device_fault"] != 0).sum())
+            alg += 32 * int(st["num_lef_updates"].sum()) + \
+                2 * len(e["iv"].barriers) * int(st["num_epochs"].sum())
+        return lu, contacts, epochs, faults, alg
+
+    def close(self):
+        self.sim.close()
+
+
+def band_checksums(torch, band, occ, missed):
+    """Order-independent and position-weighted checksums of a device band (u32 bit pattern in an
+    int32 tensor) and its 1D track."""
+    b = band.to(torch.int64) & 0xFFFFFFFF
+    w = (torch.arange(b.numel(), device=b.device, dtype=torch.int64) % 65521) + 1
+    return {"band_sum": int(b.sum().item()), "band_weighted": int((b * w).sum().item()),
+            "occ_sum": int(occ.sum().item()),
+            "occ_weighted": int((occ * w[:occ.numel()]).sum().item()),
+            "missed": int(missed.item())}
+
+
+C3_GOLDEN = os.path.join(ROOT, "tests", "golden", "c3_chr1_8192cells_checksums.json")
+C3_SAMPLED_CELLS = (0, 1, 1023, 1024, 4097, 6143, 8190, 8191)
+
+
+def extra_c3(torch, dist, engine, rank, world, local_rank, main_stream, sync_all, all_reduce, args):
+    """BASELINE config C3 (chr1 x 8192 cells): timed, and PROVEN -- the cells are split over the
+    ranks (8 x 1024 at N = 8) and the band is summed with one NCCL reduce onto its root, whose
+    checksums must equal the committed single-GPU ones (tests/golden/, written by
+    `bench.py --workload c3 --write-c3-golden` on one GPU) at every N; 8 sampled cells are also
+    run alone and compared with the CPU oracle bit for bit. Any mismatch ends the bench with a
+    non-zero exit code. Reference: the shared-matrix accumulation of
+    scheduler_simulate.cpp:129-159 + contact_matrix_dense_safe_impl.hpp:54-68."""
+    from modle_b200 import abi, host
+
+    cfg, genome, desc = build_workload("c3", args.c3_cells)
+    job = DeviceJob(torch, dist, engine, cfg, genome, rank, world, local_rank, 0)
+    ncells = int(cfg.params.num_cells)
+    job.step(main_stream)  # warm-up
+    sync_all()
+    revents = []
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record(main_stream)
+    job.step(main_stream, reduce_events=revents)
+    t1.record(main_stream)
+    sync_all()
+    ms = all_reduce(t0.elapsed_time(t1), "max")
+    reduce_ms = all_reduce(sum(a.elapsed_time(b) for a, b in revents) if revents else 0.0, "max")
+    lu, contacts, epochs, faults, _ = job.work()
+    total_lu = all_reduce(float(lu), "sum")
+    total_contacts = all_reduce(float(contacts), "sum")
+    total_faults = all_reduce(float(faults), "sum")
+    out = {"workload": desc, "ms_per_step": ms, "value": total_lu / (ms * 1e-3), "unit": UNIT,
+           "lef_updates_per_step": total_lu, "contacts_per_step": total_contacts,
+           "parallelism": job.parallelism(), "reduce_ms": reduce_ms,
+           "reduce_bytes_per_rank": int(job.reduce_bytes),
+           "nvlink_bytes_per_step": int(job.reduce_bytes) * max(0, world - 1),
+           "checks": {}}
+    errors = []
+    if total_faults:
+        errors.append(f"{int(total_faults)} cells reported a device fault")
+    iv = job.sim.intervals[0]
+    p = cfg.params
+    all_tasks = host.make_cell_tasks(p, iv.chrom_name, iv.abi_interval())
+    if int(total_contacts) != int(all_tasks["num_target_contacts"].sum()):
+        errors.append("contacts registered != sum of the cells' targets")
+    root = job.roots[0][0]
+    if rank == root:
+        got = band_checksums(torch, *job.bufs[0])
+        out["checks"]["checksums"] = got
+        if got["band_sum"] + got["missed"] != int(total_contacts):
+            errors.append("band sum + missed updates != contacts registered")
+        if args.write_c3_golden:
+            if world != 1:
+                raise SystemExit("--write-c3-golden needs a single-GPU run")
+            with open(C3_GOLDEN, "w") as f:
+                json.dump({"workload": desc, "cells": ncells, "written_by": "bench.py --workload "
+                           "c3 --write-c3-golden (1 GPU, unsharded)", **got}, f, indent=1)
+        if os.path.exists(C3_GOLDEN):
+            gold = json.load(open(C3_GOLDEN))
+            if int(gold.get("cells", -1)) == ncells:
+                bad = [k for k in got if got[k] != gold[k]]
+                out["checks"]["equals_single_gpu_golden"] = not bad
+                if bad:
+                    errors.append("reduced band differs from the single-GPU golden in " + ",".join(bad))
+            else:
+                out["checks"]["equals_single_gpu_golden"] = None
+        else:
+            out["checks"]["equals_single_gpu_golden"] = None
+    if rank == 0:
+        # sampled cells alone, against the oracle (kernel == oracle at the full C3 geometry)
+        from oracle import pyoracle
+
+        sel = np.array([c for c in C3_SAMPLED_CELLS if c < ncells])
+        tasks = np.ascontiguousarray(all_tasks[sel])
+        band, occ, missed = engine.alloc_outputs(iv.nrows, iv.ncols)
+        d_tasks = torch.from_numpy(tasks.view(np.uint8).reshape(-1).copy()).to(job.dev)
+        d_stats = torch.zeros(len(tasks) * job.stats_dt.itemsize, dtype=torch.uint8, device=job.dev)
+        engine.ctx.simulate_interval_device(p, iv.abi_interval(), iv.barriers, d_tasks.data_ptr(),
+                                            len(tasks), band.data_ptr(), occ.data_ptr(),
+                                            d_stats.data_ptr(), missed.data_ptr(),
+                                            main_stream.cuda_stream)
+        main_stream.synchronize()
+        o_band, o_occ, o_stats, o_missed = pyoracle.simulate_interval(
+            p, iv.abi_interval(), iv.barriers, tasks, nthreads=min(len(tasks), os.cpu_count() or 1))
+        st = d_stats.cpu().numpy().view(job.stats_dt)
+        same = (np.array_equal(band.cpu().numpy().view(np.uint32), o_band) and
+                np.array_equal(occ.cpu().numpy().view(np.uint64)[:len(o_occ)], o_occ) and
+                int(missed.item()) == o_missed and
+                all(np.array_equal(st[f], o_stats[f]) for f in
+                    ("num_contacts", "num_epochs", "num_burnin_epochs", "num_lef_updates",
+                     "num_rng_draws")))
+        out["checks"]["sampled_cells_equal_oracle"] = {"cells": [int(c) for c in sel], "ok": bool(same)}
+        if not same:
+            errors.append("sampled cells differ from the CPU oracle")
+    nerr = all_reduce(float(len(errors)), "sum")
+    out["checks"]["errors"] = errors
+    job.close()
+    return out, int(nerr), errors
+
+
+def extra_register(torch, ctx, dev, peak):
+    """The contact-register kernel in isolation at the C5 geometry (chr2, 1 kb bins: 3000 x
+    242,194 pixels = 2.9 GB, density 1 = 726.6 M contacts), loop-like and uniform streams, with
+    the figures SURVEY 8(d) defines: algorithmic GB/s (8 B per contact) and, for the path the
+    library took (binned: count pass, scatter-by-tile pass, paced replay), the bytes that path
+    cannot avoid. Next to it the calibration the survey asks for: plain random red.global.add.u32
+    over the same footprint (independent kernel, no stream to read)."""
+    nrows, ncols = 3000, 242_194
+    npx = nrows * ncols + 1
+    n = nrows * ncols
+    g = torch.Generator(device=dev)
+    g.manual_seed(20260117)
+    stream = torch.cuda.Stream(device=dev)
+    band = torch.zeros(npx, dtype=torch.int32, device=dev)
+    missed = torch.zeros(1, dtype=torch.int64, device=dev)
+    res = {"geometry": "C5: 3000 x 242,194 px (2.9 GB band), 726.6 M contacts (density 1)",
+           "hbm_peak_GBps": peak, "streams": {}}
+
+    def timed(fn, reps=3):
+        ts = []
+        with torch.cuda.stream(stream):
+            for r in range(reps + 1):
+                band.zero_()
+                missed.zero_()
+                e0 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                fn()
+                e1.record(stream)
+                stream.synchronize()
+                if r >= 1:
+                    ts.append(e0.elapsed_time(e1))
+        return sorted(ts)[len(ts) // 2]
+
+    # bytes the binned path cannot avoid: the (bin1, bin2) stream is read twice (count, scatter),
+    # the 4-byte pixel indices are written once and read once, every band sector comes in and
+    # goes out once
+    compulsory = 2 * 8 * n + 2 * 4 * n + 2 * 4 * npx
+    for kind in ("loop", "uniform"):
+        b2 = torch.randint(0, ncols, (n,), device=dev, generator=g, dtype=torch.int64)
+        if kind == "loop":
+            d = torch.empty(n, device=dev, dtype=torch.float32).exponential_(1.0 / 100.0, generator=g)
+            d = d.to(torch.int64).clamp_(0, nrows - 1)
+        else:
+            d = torch.randint(0, nrows, (n,), device=dev, generator=g, dtype=torch.int64)
+        b1 = (b2 - d).clamp_(min=0).to(torch.int32).contiguous()
+        b2 = b2.to(torch.int32).contiguous()
+        del d
+        ms = timed(lambda: ctx.register_contacts_device(b1.data_ptr(), b2.data_ptr(), n, nrows,
+                                                        ncols, band.data_ptr(), missed.data_ptr(),
+                                                        stream.cuda_stream))
+        total = int((band.to(torch.int64) & 0xFFFFFFFF).sum().item()) + int(missed.item())
+        rate = n / (ms * 1e-3)
+        res["streams"][kind] = {
+            "ms": ms, "contacts_per_s": rate, "all_contacts_accounted_for": total == n,
+            "algorithmic_GBps": 8 * rate / 1e9, "algorithmic_frac_of_hbm": 8 * rate / 1e9 / peak,
+            "compulsory_bytes_of_the_binned_path": compulsory,
+            "compulsory_GBps": compulsory / (ms * 1e-3) / 1e9,
+            "compulsory_frac_of_hbm": compulsory / (ms * 1e-3) / 1e9 / peak}
+        del b1, b2
+    # calibration: random reductions over the 2.9 GB footprint (HBM regime: every reduction is a
+    # 32 B sector in and one out) and over the C1 footprint (30.9 MB: L2 regime)
+    ms = timed(lambda: ctx.calibrate_red_device(band.data_ptr(), npx, n, 1, stream.cuda_stream))
+    res["calibration_random_red_2.9GB"] = {
+        "ms": ms, "reductions_per_s": n / (ms * 1e-3),
+        "sector_traffic_GBps": 64 * n / (ms * 1e-3) / 1e9,
+        "sector_traffic_frac_of_hbm": 64 * n / (ms * 1e-3) / 1e9 / peak}
+    small = 600 * 12_889 + 1
+    n2 = 1 << 28
+    ms = timed(lambda: ctx.calibrate_red_device(band.data_ptr(), small, n2, 2, stream.cuda_stream))
+    res["calibration_random_red_30.9MB_L2"] = {"ms": ms, "reductions_per_s": n2 / (ms * 1e-3)}
+    return res
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
 
-    from modle_b200 import abi, build, distributed, host
-    from modle_b200.simulation import Simulation
+    from modle_b200 import build, distributed
 
     build.build()
     if not torch.cuda.is_available():
@@ -253,61 +553,14 @@ def run_ours(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
     cfg, genome, desc = build_workload(args.workload, args.cells)
-    p = cfg.params
     rng_mode = 1 if args.rng_mode == "throughput" else 0
-    sim = Simulation(cfg, genome, device=local_rank, rank=rank, world_size=world, rng_mode=rng_mode)
     engine = distributed.DeviceEngine(local_rank, num_streams=args.streams, rng_mode=rng_mode)
     ctx = engine.ctx
-    barrier_dt, task_dt, stats_dt = abi.np_dtypes()
-    shards = distributed.plan_shards(distributed.interval_weights(sim.intervals),
-                                     int(p.num_cells), world)
-    roots = distributed.interval_roots(shards)
-    split = sorted(i for i, (_, ranks) in roots.items() if len(ranks) > 1)
-
-    # ---- stage my share of the work on the device ------------------------------------------
-    bufs = {}   # interval -> (band, occ, missed)
-    mine = []
-    for s in sorted((s for s in shards if s.rank == rank), key=lambda s: (-s.weight, s.interval)):
-        iv = sim.intervals[s.interval]
-        if s.interval not in bufs:
-            bufs[s.interval] = engine.alloc_outputs(iv.nrows, iv.ncols)
-        tasks = host.make_cell_tasks(p, iv.chrom_name, iv.abi_interval())[s.cell_lo:s.cell_hi]
-        h_tasks = torch.from_numpy(tasks.view(np.uint8).reshape(-1).copy()).pin_memory()
-        mine.append(dict(iv=iv, idx=s.interval, abi_iv=iv.abi_interval(), ntasks=len(tasks),
-                         d_tasks=h_tasks.to(dev),
-                         d_stats=torch.zeros(len(tasks) * stats_dt.itemsize, dtype=torch.uint8,
-                                             device=dev)))
-    for idx in split:  # a rank without a piece of a split interval contributes zeros to its reduce
-        if idx not in bufs:
-            bufs[idx] = engine.alloc_outputs(sim.intervals[idx].nrows, sim.intervals[idx].ncols)
+    job = DeviceJob(torch, dist, engine, cfg, genome, rank, world, local_rank, rng_mode,
+                    slice_all=args.plan == "slices")
+    sim = job.sim
     main_stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(main_stream)
-
-    def step_device(events=None):
-        for band, occ, missed in bufs.values():
-            band.zero_()
-            occ.zero_()
-            missed.zero_()
-        for k, e in enumerate(mine):
-            stream = engine.streams[k % len(engine.streams)]
-            stream.wait_stream(main_stream)
-            band, occ, missed = bufs[e["idx"]]
-            if events is not None:
-                ev0 = torch.cuda.Event(enable_timing=True)
-                ev1 = torch.cuda.Event(enable_timing=True)
-                ev0.record(stream)
-            ctx.simulate_interval_device(p, e["abi_iv"], e["iv"].barriers, e["d_tasks"].data_ptr(),
-                                         e["ntasks"], band.data_ptr(), occ.data_ptr(),
-                                         e["d_stats"].data_ptr(), missed.data_ptr(),
-                                         stream.cuda_stream)
-            if events is not None:
-                ev1.record(stream)
-                events.append((e, ev0, ev1))
-        for stream in engine.streams:
-            main_stream.wait_stream(stream)
-        for idx in split:  # the one exchange step: sum a split interval onto its root
-            for b in bufs[idx]:
-                dist.reduce(b, dst=roots[idx][0], op=dist.ReduceOp.SUM)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -319,60 +572,57 @@ def run_ours(args, rank, world, local_rank):
         if world == 1:
             return x
         t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=op)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM)
         return float(t.item())
+
+    def timed_steps(steps, warmup, events=None):
+        for _ in range(warmup):
+            job.step(main_stream)
+        sync_all()
+        t_start = torch.cuda.Event(enable_timing=True)
+        t_end = torch.cuda.Event(enable_timing=True)
+        sync_all()
+        t_start.record(main_stream)
+        for _ in range(steps):
+            job.step(main_stream, events)
+        t_end.record(main_stream)
+        sync_all()
+        mine_ms = t_start.elapsed_time(t_end)
+        return all_reduce(mine_ms, "max"), mine_ms
 
     # ---- device-resident timing -------------------------------------------------------------
     for _ in range(args.warmup):
-        step_device()
+        job.step(main_stream)
     sync_all()
     launches0 = ctx.kernel_launches()
     ctx.phase_cycles(reset=True)
     events = []
-    t_start = torch.cuda.Event(enable_timing=True)
-    t_end = torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
-        sync_all()
-        t_start.record(main_stream)
-        for _ in range(args.steps):
-            step_device(events)
-        t_end.record(main_stream)
-        sync_all()
-    elapsed_ms = all_reduce(t_start.elapsed_time(t_end), dist.ReduceOp.MAX if world > 1 else None)
+        elapsed_ms, my_ms = timed_steps(args.steps, 0, events)
     launches = ctx.kernel_launches() - launches0
     phases = ctx.phase_cycles(reset=True)
 
     # work done per step (identical every step: the simulation is deterministic)
-    lef_updates = contacts = faults = alg_bytes = epochs = 0
-    for e in mine:
-        st = e["d_stats"].cpu().numpy().view(stats_dt)
-        lef_updates += int(st["num_lef_updates"].sum())
-        contacts += int(st["num_contacts"].sum())
-        epochs += int(st["num_epochs"].sum())
-        faults += int((st["device_fault"] != 0).sum())
-        alg_bytes += 32 * int(st["num_lef_updates"].sum()) + \
-            2 * len(e["iv"].barriers) * int(st["num_epochs"].sum())
-    if faults:
+    lef_updates, contacts, epochs, faults, alg_bytes = job.work()
+    if all_reduce(float(faults), "sum"):
         raise SystemExit(f"bench.py: {faults} cells reported a device fault")
-    total_lu = all_reduce(float(lef_updates), dist.ReduceOp.SUM if world > 1 else None)
-    total_contacts = all_reduce(float(contacts), dist.ReduceOp.SUM if world > 1 else None)
+    total_lu = all_reduce(float(lef_updates), "sum")
+    total_contacts = all_reduce(float(contacts), "sum")
     value = total_lu * args.steps / (elapsed_ms * 1e-3)
     launch_ms = [ev0.elapsed_time(ev1) for _, ev0, ev1 in events]
     peak, peak_src = measured_peaks()
     # launches overlap (several streams), so the kernel's rate is taken over the timed region
-    my_ms = t_start.elapsed_time(t_end)
     achieved = (alg_bytes * args.steps / 1e9) / (my_ms * 1e-3) if my_ms > 0 else 0.0
-    dram_per_lu, traffic_src = ncu_traffic_per_lef_update()
-    traffic = dram_per_lu * lef_updates / max(1, len(mine)) if dram_per_lu else None
-    if rng_mode != 0:  # the committed ncu capture is of the deterministic kernel (staged draws)
-        traffic, traffic_src = None, "no ncu capture of the throughput-mode kernel yet"
+    dram_per_lu, traffic_src = ncu_traffic_per_lef_update(rng_mode)
+    traffic = dram_per_lu * lef_updates / max(1, len(job.mine)) if dram_per_lu else None
 
     # ---- end to end through the public API (host buffers; copies inside the timed region) ------
+    task_dt, stats_dt, barrier_dt = job.task_dt, job.stats_dt, job.barrier_dt
     h2d = sum(e["ntasks"] * task_dt.itemsize + len(e["iv"].barriers) * barrier_dt.itemsize
-              for e in mine)
+              for e in job.mine)
     d2h = sum((sim.intervals[i].nrows * sim.intervals[i].ncols + 1) * 4 + sim.intervals[i].ncols * 8
-              + 8 for i in bufs if roots[i][0] == rank) + \
-        sum(e["ntasks"] * stats_dt.itemsize for e in mine)
+              + 8 for i in job.bufs if job.roots[i][0] == rank) + \
+        sum(e["ntasks"] * stats_dt.itemsize for e in job.mine)
 
     def step_e2e():
         sim.run_simulate(num_workers=args.streams)
@@ -384,9 +634,38 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(e2e_steps):
         step_e2e()
     sync_all()
-    e2e_s = all_reduce(time.perf_counter() - t0, dist.ReduceOp.MAX if world > 1 else None)
+    e2e_s = all_reduce(time.perf_counter() - t0, "max")
     e2e_value = total_lu * e2e_steps / e2e_s
-    launches_e2e = sum(c.kernel_launches() for c in sim._ctxs)
+    sim.close()  # (frees the e2e path's contexts and staging before the extras allocate theirs)
+
+    # ---- extras: the second RNG mode, config C3 with its reduce, the register kernel -----------
+    extra, failed = {}, []
+    if not args.no_extras and args.workload == "c2" and rng_mode == 0:
+        ctx.set_rng_mode(1)
+        thr_ms, _ = timed_steps(2, 1)
+        ctx.set_rng_mode(0)
+        lu_t, _, _, faults_t, _ = job.work()
+        thr_lu = all_reduce(float(lu_t), "sum")
+        extra["throughput_mode"] = {
+            "value": thr_lu * 2 / (thr_ms * 1e-3), "unit": UNIT, "ms_per_step": thr_ms / 2,
+            "steps": 2, "warmup": 1, "lef_updates_per_step": thr_lu,
+            "rng_mode": "throughput (counter-based draws; statistically equivalent, "
+                        "tests/test_zz_gpu_throughput_mode.py holds the gate)"}
+        if all_reduce(float(faults_t), "sum"):
+            failed.append("throughput mode: device fault")
+    if (not args.no_extras and args.workload == "c2") or args.write_c3_golden:
+        extra["c3"], nerr, errs = extra_c3(torch, dist, engine, rank, world, local_rank,
+                                           main_stream, sync_all, all_reduce, args)
+        if nerr:
+            failed.append("c3: " + "; ".join(errs) if errs else "c3: check failed on another rank")
+    if not args.no_extras and rank == 0 and world == 1 and args.workload == "c2":
+        for band, occ, missed in job.bufs.values():  # make room: 4 x 2.9 GB for the C5 replay
+            del band, occ, missed
+        job.bufs.clear()
+        torch.cuda.empty_cache()
+        extra["register"] = extra_register(torch, ctx, dev, peak)
+        if not all(v["all_contacts_accounted_for"] for v in extra["register"]["streams"].values()):
+            failed.append("register: contacts lost")
 
     # ---- CPU baseline (rank 0, single-GPU runs only) ------------------------------------------
     cpu = None
@@ -408,9 +687,8 @@ def run_ours(args, rank, world, local_rank):
                        "rng_mode": "deterministic (reference draw order, bit-exact)"
                                    if rng_mode == 0 else
                                    "throughput (counter-based draws, statistically equivalent)",
-                       "parallelism": f"{world} rank(s), {len(shards)} (interval, cell-range) "
-                                      f"shards dealt heaviest-first, {len(split)} interval(s) "
-                                      "split over ranks and summed with one NCCL reduce each"},
+                       "parallelism": job.parallelism() +
+                       ("; extra.c3: " + extra["c3"]["parallelism"] if "c3" in extra else "")},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
                     "ms_per_step": 1e3 * e2e_s / e2e_steps,
@@ -433,13 +711,19 @@ def run_ours(args, rank, world, local_rank):
             "cycles_per_cell_epoch": tot_cyc / max(1, epochs * args.steps),
             "clocks": clocks.summary(),
         }
+        if extra:
+            line["extra"] = extra
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if failed:
+            line["failed_checks"] = failed
         print(json.dumps(line), flush=True)
-    sim.close()
+    job.close()
     engine.close()
     if world > 1:
         dist.destroy_process_group()
+    if failed:
+        raise SystemExit("bench.py: result check failed: " + " | ".join(failed))
 
 
 def main():
@@ -454,6 +738,15 @@ def main():
     ap.add_argument("--rng-mode", default="deterministic", choices=["deterministic", "throughput"],
                     help="deterministic: the reference's draw order, bit-exact (the headline); "
                          "throughput: counter-based draws, statistically equivalent")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip extra.throughput_mode / extra.c3 / extra.register")
+    ap.add_argument("--c3-cells", type=int, default=8192, help="cells of the extra C3 run")
+    ap.add_argument("--write-c3-golden", action="store_true",
+                    help="(1 GPU) run the extra C3 step and write its checksums to "
+                         "tests/golden/c3_chr1_8192cells_checksums.json")
+    ap.add_argument("--plan", default="whole", choices=["whole", "slices"],
+                    help="whole: whole intervals per rank, cells split only to balance (default); "
+                         "slices: every interval cut into one cell slice per rank + one reduce each")
     ap.add_argument("--streams", type=int, default=3,
                     help="concurrent launches per GPU (streams / host worker threads)")
     args = ap.parse_args()

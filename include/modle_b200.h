@@ -319,6 +319,14 @@ int modle_b200_register_contacts_device(modle_b200_context* ctx, const uint32_t*
                                         uint64_t ncols, uint32_t* d_band,
                                         uint64_t* d_missed_updates, void* cuda_stream);
 
+/* Measurement aid for that kernel's roofline ("calibrate an atomic roofline on the box
+ * with a micro-benchmark: uniform random red.global.add.u32 over a buffer of the same footprint"):
+ * issues num_reductions reductions of +1 on pseudo-random words of d_band[0..num_words) -- the
+ * addresses come from a counter hash, nothing is read -- asynchronously on `cuda_stream`. The
+ * caller times it; the sum over d_band grows by num_reductions. No reference counterpart. */
+int modle_b200_calibrate_red_device(modle_b200_context* ctx, uint32_t* d_band, uint64_t num_words,
+                                    uint64_t num_reductions, uint64_t seed, void* cuda_stream);
+
 /* ---- band -> sorted COO pixels: the hand-off to the .cool writer -------------------------------
  * Replaces the pixel loop of modle::io::internal::append_contact_matrix_to_cooler
  * (src/libmodle_io/contact_matrix_dense_io_impl.hpp:50-71): for i in [0, ncols), j in
@@ -378,6 +386,46 @@ int modle_b200_phase_cycles(modle_b200_context* ctx, uint64_t* out, size_t n, in
  * reference has no counterpart (its workers are interchangeable CPU threads). */
 int modle_b200_launch_geometry(uint64_t num_lefs, uint64_t num_barriers, uint32_t* cta_threads,
                                uint32_t* cells_per_sm, uint64_t* shared_bytes_per_cell);
+
+/* ---- several GPUs (one host thread or process per GPU, one context each) ------------------------
+ * The reference's parallelism is its pool of worker threads popping (interval, cell) tasks that
+ * all add into the interval's shared matrix (scheduler_simulate.cpp:104-160, 190-271;
+ * contact_matrix_dense_safe_impl.hpp:54-68). Over several GPUs the tasks are dealt out as
+ * (interval, cell range) shards; an interval whose cells sit on several GPUs has its band summed
+ * onto its root with ONE reduce. Every cell keeps the task it has in the unsharded run
+ * (modle_b200_make_cell_tasks over all cells, then sliced), so results do not depend on the plan. */
+typedef struct modle_b200_shard {
+  uint64_t interval; /* index into the caller's interval list */
+  uint64_t cell_lo;  /* cells [cell_lo, cell_hi) of that interval */
+  uint64_t cell_hi;
+  int32_t rank;      /* GPU / process that simulates the shard */
+  int32_t reserved_;
+  double weight;     /* modelled cost (cell weight x cells) */
+} modle_b200_shard;
+
+/* Planner weight of ONE cell of an interval (relative SM time: launch geometry + per-LEF cost). */
+double modle_b200_cell_weight(uint64_t num_lefs, uint64_t num_barriers);
+
+/* Deals the cells of `num_intervals` intervals (`num_cells` cells each; cell_weights[i] from
+ * modle_b200_cell_weight, 0 = interval skipped, e.g. no barriers) to `world_size` ranks: whole
+ * intervals heaviest-first; while the heaviest rank carries more than `tolerance` (<= 0: 1.10) x
+ * the mean, the heaviest piece of that rank is halved by cells. slice_all != 0: every interval is
+ * cut into one cell range per rank instead (one reduce per interval). Shards come out sorted by
+ * (interval, cell_lo); the root of an interval is the rank of its first shard. Deterministic:
+ * every rank computes the same plan. shards_out == NULL with capacity 0 is a size query. */
+int modle_b200_plan_shards(const double* cell_weights, size_t num_intervals, uint64_t num_cells,
+                           int world_size, int slice_all, double tolerance,
+                           modle_b200_shard* shards_out, size_t capacity, size_t* num_shards_out);
+
+/* The one collective of the path: sums a split interval's device buffers onto `root` -- band
+ * (nrows*ncols+1 uint32), and when not NULL the 1D track (ncols uint64) and the missed-update
+ * counter (1 uint64) -- with ncclReduce(sum), in place, asynchronously on `cuda_stream`. Called
+ * by every rank of `nccl_comm` (an ncclComm_t; a rank without a piece of the interval passes
+ * zeroed buffers). NCCL is loaded at run time (libnccl.so.2); MODLE_B200_ERR_UNSUPPORTED if it
+ * cannot be. Inside an ncclGroupStart/End when one thread drives several GPUs. */
+int modle_b200_reduce_band(modle_b200_context* ctx, void* nccl_comm, uint32_t* d_band,
+                           uint64_t nrows, uint64_t ncols, uint64_t* d_occ1d,
+                           uint64_t* d_missed_updates, int root, void* cuda_stream);
 
 /* Number of kernels this library has launched on the context so far (bench bookkeeping). */
 uint64_t modle_b200_kernel_launches(const modle_b200_context* ctx);

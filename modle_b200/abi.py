@@ -142,6 +142,27 @@ def epoch_record_dtype():
     return dt
 
 
+class ShardRecord(C.Structure):
+    """modle_b200_shard."""
+    _fields_ = [
+        ("interval", C.c_uint64),
+        ("cell_lo", C.c_uint64),
+        ("cell_hi", C.c_uint64),
+        ("rank", C.c_int32),
+        ("reserved_", C.c_int32),
+        ("weight", C.c_double),
+    ]
+
+
+def shard_dtype():
+    import numpy as np
+
+    dt = np.dtype([("interval", "<u8"), ("cell_lo", "<u8"), ("cell_hi", "<u8"), ("rank", "<i4"),
+                   ("reserved_", "<i4"), ("weight", "<f8")])
+    assert dt.itemsize == C.sizeof(ShardRecord) == 40
+    return dt
+
+
 def pixel_dtype():
     import numpy as np
 

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmodle_b200.so")
-SOURCES = ["host.cpp", "genome.cpp", "kernels.cu", "pixels.cu"]
+SOURCES = ["host.cpp", "genome.cpp", "shards.cpp", "kernels.cu", "pixels.cu"]
 HEADERS = ["cta.hpp", "sim_types.hpp", "sim_core.hpp", "launch_prep.hpp", "host_rng.hpp",
            "status.hpp", "context.hpp", "ziggurat_tables.inc", os.path.join("..", "..", "include", "modle_b200.h")]
 
@@ -15,7 +15,8 @@ NVCC_FLAGS = [
     # strict IEEE double arithmetic: no FMA contraction, so results match the CPU oracle
     # (built with -ffp-contract=off) operation for operation
     "-fmad=false",
-    "-Xcompiler", "-fPIC,-O2,-ffp-contract=off", "-shared", "-cudart", "static", "--threads", "0",
+    "-Xcompiler", "-fPIC,-O2,-ffp-contract=off", "-shared", "-cudart", "static", "--threads", "0", "-ldl",
+    "-Xlinker", "-soname=libmodle_b200.so",
 ]
 
 

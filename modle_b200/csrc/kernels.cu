@@ -161,6 +161,23 @@ __global__ void __launch_bounds__(256) k_register_contacts(const u32* __restrict
               static_cast<unsigned long long>(warp_missed));
 }
 
+// Calibration of the "atomic roofline" (regime 2), independent of the register
+// kernels above: every thread derives pseudo-random pixel addresses from a counter hash (no
+// memory is read) and issues plain red.global.add.u32 on them -- the rate random 4-byte
+// reductions can reach over a footprint of `npx` words with nothing else in the way.
+__global__ void __launch_bounds__(256) k_calibrate_red(u32* __restrict__ band, u64 npx, u64 n,
+                                                       u64 seed) {
+  const u64 stride = u64(gridDim.x) * blockDim.x;
+  for (u64 e = u64(blockIdx.x) * blockDim.x + threadIdx.x; e < n; e += stride) {
+    u64 z = (e + seed) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    const u64 px = __umul64hi(z, npx);  // uniform in [0, npx)
+    atomicAdd(band + px, 1u);
+  }
+}
+
 // ---- binned contact register (bands much larger than the L2) ---------------------------------
 // A band that does not fit the L2 turns every contact into a random DRAM read-modify-write
 // (one 32-byte sector in, one out). The binned path first groups the contacts by 32 MB tile of
@@ -878,6 +895,20 @@ int modle_b200_register_contacts_device(modle_b200_context* ctx, const uint32_t*
   k_register_contacts<<<grid, threads, 0, stream>>>(d_bin1, d_bin2, n, static_cast<u32>(nrows),
                                                     static_cast<u32>(ncols), d_band,
                                                     d_missed_updates, vec_ok);
+  CUDA_TRY(cudaGetLastError());
+  ++ctx->launches;
+  return MODLE_B200_OK;
+}
+
+int modle_b200_calibrate_red_device(modle_b200_context* ctx, uint32_t* d_band, uint64_t num_words,
+                                    uint64_t num_reductions, uint64_t seed, void* cuda_stream) {
+  if (!ctx || !d_band || num_words == 0)
+    return fail(MODLE_B200_ERR_INVALID_ARGUMENT, "NULL argument");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  cudaStream_t stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
+  if (num_reductions == 0) return MODLE_B200_OK;
+  k_calibrate_red<<<static_cast<u32>(ctx->num_sms) * 8, 256, 0, stream>>>(d_band, num_words,
+                                                                        num_reductions, seed);
   CUDA_TRY(cudaGetLastError());
   ++ctx->launches;
   return MODLE_B200_OK;

@@ -17,6 +17,7 @@ computed for all cells of the interval and then sliced), so outputs are identica
 size. The compute engine is pluggable: `DeviceEngine` drives the CUDA library; the CPU tests plug
 an engine backed by the kernel emulation to exercise this module over gloo.
 """
+import ctypes as C
 from dataclasses import dataclass
 
 import numpy as np
@@ -33,29 +34,21 @@ class Shard:
     weight: float = 0.0
 
 
-# SM time of one cell-epoch, in cycles: A[threads per CTA] + B[threads] x LEFs, divided by the
-# cells an SM hosts at a time. One CTA of 1024 threads: 80 k + 40 per LEF, fitted to
-# single-interval runs on a B200 (profiles/r01i_stream_sweep.txt: chr1 279 k, chr2 270 k, chr3
-# 238 k cycles per cell-epoch). A LEF costs a narrower CTA proportionally more (each thread owns
-# more of them), and the constants then follow from the measured class averages (212 k at 512
-# threads / ~2070 LEFs, 217 k at 256 threads / ~1280 LEFs). Only the ratios matter to the planner.
-_COST_A = {1024: 80e3, 512: 46e3, 256: 12e3}
-_COST_B = {1024: 40.0, 512: 80.0, 256: 160.0}
-
-
-def cell_epoch_cycles(num_lefs, num_barriers):
-    """(modelled SM-clock cycles of one cell-epoch, cells resident per SM) for an interval."""
-    threads, per_sm, _ = host.launch_geometry(num_lefs, num_barriers)
-    return _COST_A.get(threads, 80e3) + _COST_B.get(threads, 40.0) * num_lefs, per_sm
-
-
+# The planner itself lives in the C ABI (modle_b200_plan_shards / modle_b200_cell_weight,
+# csrc/shards.cpp) so that a C++ host and this Python mirror deal the same shards; what follows are
+# thin wrappers. Cost model, for the record: the SM time of one cell-epoch is A[threads per CTA] +
+# B[threads] x LEFs cycles, divided by the cells an SM hosts at a time. One CTA of 1024 threads:
+# 80 k + 40 per LEF, fitted to single-interval runs on a B200 (profiles/r01i_stream_sweep.txt:
+# chr1 279 k, chr2 270 k, chr3 238 k cycles per cell-epoch); a LEF costs a narrower CTA
+# proportionally more (212 k at 512 threads / ~2070 LEFs, 217 k at 256 threads / ~1280 LEFs).
+# Only the ratios matter to the planner.
 def cell_cost(num_lefs, num_barriers):
     """Relative SM time of one cell of an interval (epoch counts are the same for every interval
     to within a few percent, so they drop out)."""
-    if num_lefs <= 0:
-        return 0.0
-    cycles, per_sm = cell_epoch_cycles(num_lefs, num_barriers)
-    return cycles / per_sm
+    L = host.lib()
+    L.modle_b200_cell_weight.restype = C.c_double
+    L.modle_b200_cell_weight.argtypes = [C.c_uint64, C.c_uint64]
+    return float(L.modle_b200_cell_weight(int(num_lefs), int(num_barriers))) if num_lefs > 0 else 0.0
 
 
 def interval_weights(intervals):
@@ -64,24 +57,15 @@ def interval_weights(intervals):
             for iv in intervals]
 
 
-def _assign(pieces, world):
-    """Longest-processing-time-first assignment; returns the per-rank loads."""
-    load = [0.0] * world
-    for p in sorted(pieces, key=lambda s: (-s.weight, s.interval, s.cell_lo)):
-        r = min(range(world), key=lambda k: (load[k], k))
-        p.rank = r
-        load[r] += p.weight
-    return load
-
-
-def plan_shards(num_lefs, num_cells, world, tolerance=1.10, max_pieces=None, slice_all=False):
-    """Deals (interval, cell range) shards to `world` ranks.
+def plan_shards(num_lefs, num_cells, world, tolerance=1.10, slice_all=False):
+    """Deals (interval, cell range) shards to `world` ranks (modle_b200_plan_shards).
 
     num_lefs[i] is the weight of one cell of interval i (0 = interval skipped, e.g. no
     barriers): its LEF count, or better `interval_weights()` -- the SM time of a cell-epoch, which
-    also knows how many cells of that size share an SM; the cost of a shard is weight x cells. Starts from whole intervals and, while the heaviest rank
-    carries more than `tolerance` x the mean load, halves the heaviest splittable piece of that
-    rank. Deterministic: every rank computes the same plan.
+    also knows how many cells of that size share an SM; the cost of a shard is weight x cells.
+    Starts from whole intervals and, while the heaviest rank carries more than `tolerance` x the
+    mean load, halves the heaviest splittable piece of that rank. Deterministic: every rank
+    computes the same plan.
 
     slice_all: every interval is cut into `world` equal cell ranges instead, one per rank (the
     first range of interval i goes to rank i % world, so the roots -- and with them the reduce
@@ -89,39 +73,19 @@ def plan_shards(num_lefs, num_cells, world, tolerance=1.10, max_pieces=None, sli
     same mix of work, which removes both the imbalance between ranks and most of the tail of a
     rank's last launches, at the price of one reduce per interval.
     """
-    if slice_all and world > 1:
-        out = []
-        for i, n in enumerate(num_lefs):
-            if n <= 0 or num_cells <= 0:
-                continue
-            for k in range(world):
-                lo, hi = num_cells * k // world, num_cells * (k + 1) // world
-                if hi > lo:
-                    out.append(Shard(i, lo, hi, (i + k) % world, float(n) * (hi - lo)))
-        return out
-    pieces = [Shard(i, 0, num_cells, -1, float(n) * num_cells)
-              for i, n in enumerate(num_lefs) if n > 0 and num_cells > 0]
-    if not pieces:
-        return []
-    if max_pieces is None:
-        max_pieces = len(pieces) + 8 * world
-    total = sum(p.weight for p in pieces)
-    while True:
-        load = _assign(pieces, world)
-        worst = max(range(world), key=lambda k: (load[k], -k))
-        if world == 1 or load[worst] <= tolerance * total / world or len(pieces) >= max_pieces:
-            break
-        cand = [p for p in pieces if p.rank == worst and p.cell_hi - p.cell_lo >= 2]
-        if not cand:
-            break
-        p = max(cand, key=lambda s: (s.weight, -s.interval, -s.cell_lo))
-        mid = (p.cell_lo + p.cell_hi) // 2
-        per_cell = p.weight / (p.cell_hi - p.cell_lo)
-        q = Shard(p.interval, mid, p.cell_hi, -1, per_cell * (p.cell_hi - mid))
-        p.cell_hi = mid
-        p.weight = per_cell * (mid - p.cell_lo)
-        pieces.append(q)
-    return sorted(pieces, key=lambda s: (s.interval, s.cell_lo))
+    L = host.lib()
+    L.modle_b200_plan_shards.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64, C.c_int, C.c_int,
+                                         C.c_double, C.c_void_p, C.c_size_t,
+                                         C.POINTER(C.c_size_t)]
+    w = np.ascontiguousarray(num_lefs, dtype=np.float64)
+    n = C.c_size_t(0)
+    args = (w.ctypes.data, len(w), int(num_cells), int(world), int(bool(slice_all)), float(tolerance))
+    host.check(L.modle_b200_plan_shards(*args, None, 0, C.byref(n)))
+    out = np.zeros(n.value, dtype=abi.shard_dtype())
+    if n.value:
+        host.check(L.modle_b200_plan_shards(*args, out.ctypes.data, len(out), C.byref(n)))
+    return [Shard(int(s["interval"]), int(s["cell_lo"]), int(s["cell_hi"]), int(s["rank"]),
+                  float(s["weight"])) for s in out]
 
 
 def interval_roots(shards):

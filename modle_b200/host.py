@@ -80,6 +80,8 @@ def lib():
         L.modle_b200_register_contacts_device.argtypes = [
             C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_void_p,
             C.c_void_p, C.c_void_p]
+        L.modle_b200_calibrate_red_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64,
+                                                      C.c_uint64, C.c_uint64, C.c_void_p]
         L.modle_b200_count_pixels_device.argtypes = [
             C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
         L.modle_b200_fill_pixels_device.argtypes = [
@@ -120,7 +122,8 @@ EXPORTED_SYMBOLS = [
     "modle_b200_simulate_interval", "modle_b200_simulate_interval_logged",
     "modle_b200_simulate_interval_device",
     "modle_b200_synchronize", "modle_b200_snapshot_cell", "modle_b200_register_contacts_device",
-    "modle_b200_kernel_launches", "modle_b200_phase_cycles",
+    "modle_b200_kernel_launches", "modle_b200_phase_cycles", "modle_b200_calibrate_red_device",
+    "modle_b200_cell_weight", "modle_b200_plan_shards", "modle_b200_reduce_band",
     "modle_b200_count_pixels_device", "modle_b200_fill_pixels_device", "modle_b200_band_to_pixels",
     "modle_b200_lef_occupancy_profile_device", "modle_b200_lef_occupancy_profile",
     "modle_b200_genome_import", "modle_b200_genome_free", "modle_b200_genome_num_chromosomes",

@@ -186,6 +186,13 @@ class Context:
             C.c_void_p(d_missed), C.c_void_p(stream) if stream else None)
         host.check(rc)
 
+    def calibrate_red_device(self, d_band, num_words, num_reductions, seed=0, stream=None):
+        """Plain random red.global.add.u32 over d_band[0..num_words): the calibration of the
+        contact-register kernel's atomic roofline (the caller times it)."""
+        host.check(host.lib().modle_b200_calibrate_red_device(
+            self._h, C.c_void_p(d_band), num_words, num_reductions, seed,
+            C.c_void_p(stream) if stream else None))
+
     # -- band -> sorted COO pixels (the .cool writer hand-off) ---------------------------------
     def band_to_pixels(self, band, nrows, ncols, bin_offset=0):
         """append_contact_matrix_to_cooler's pixel loop (contact_matrix_dense_io_impl.hpp:50-71)
@@ -267,6 +274,7 @@ class Simulation:
     rank: int = 0
     world_size: int = 1
     rng_mode: int = RNG_REFERENCE_ORDER  # RNG_COUNTER selects the throughput mode
+    slice_all: bool = False  # multi-GPU plan: one cell slice of EVERY interval per rank
     intervals: list = field(default_factory=list)
     _ctxs: list = field(default_factory=list, repr=False)
     _engine: object = field(default=None, repr=False)
@@ -359,8 +367,11 @@ class Simulation:
         p = self.config.params
         if self._engine is None:
             self._engine = distributed.DeviceEngine(self.device, rng_mode=self.rng_mode)
+        shards = distributed.plan_shards(distributed.interval_weights(self.intervals),
+                                         int(p.num_cells), self.world_size,
+                                         slice_all=self.slice_all)
         out = distributed.run_sharded(self._engine, p, self.intervals, self.rank, self.world_size,
-                                      dist)
+                                      dist, shards=shards)
         for idx, o in out.items():
             iv = self.intervals[idx]
             iv.stats = np.concatenate(o["stats"]) if o["stats"] else None

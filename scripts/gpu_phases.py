@@ -1,6 +1,6 @@
 """Times one interval on the GPU and prints the kernel's per-phase cycle breakdown.
 
-    python scripts/gpu_phases.py [c1|c3|c4] [cells] [repeat]
+    python scripts/gpu_phases.py [c1|c3|c4|c5] [cells] [repeat]
 
 Uses whatever library MODLE_B200_LIB points to (default: the product build).
 """
@@ -25,6 +25,9 @@ def main():
         cfg, genome = workloads.config_c3(cells)
     elif wl == "c4":
         cfg, genome = workloads.config_c4(cells)
+    elif wl == "c5":  # full C5 geometry (2.9 GB band); density via MODLE_B200_C5_DENSITY
+        cfg, genome = workloads.config_c5(
+            cells, target_contact_density=float(os.environ.get("MODLE_B200_C5_DENSITY", "0.05")))
     else:
         raise SystemExit("unknown workload")
     sim = Simulation(cfg, genome)

@@ -122,7 +122,7 @@ def main():
         k = klass(iv.num_lefs, len(iv.barriers))
         # bootstrap the interval's 512 cells from the sample
         epochs = rng.choice(ep, size=args.cells, replace=True)
-        dur = epochs * CAL * distributed.cell_epoch_cycles(iv.num_lefs, len(iv.barriers))[0] / CLOCK
+        dur = epochs * CAL * (distributed.cell_cost(iv.num_lefs, len(iv.barriers)) * host.launch_geometry(iv.num_lefs, len(iv.barriers))[1]) / CLOCK
         intervals.append(dict(name=iv.chrom_name, k=k, n=iv.num_lefs, nb=len(iv.barriers), dur=dur,
                               mean_epochs=ep.mean(), max_over_mean=ep.max() / ep.mean()))
         print(f"{iv.chrom_name:6s} {k:5s} N={iv.num_lefs:5d} epochs mean {ep.mean():7.1f} "

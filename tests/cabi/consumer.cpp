@@ -34,6 +34,7 @@ static_assert(sizeof(modle_b200_cell_stats) == 48 && offsetof(modle_b200_cell_st
 static_assert(sizeof(modle_b200_cell_snapshot) == 64 && offsetof(modle_b200_cell_snapshot, num_active_lefs) == 48, "");
 static_assert(sizeof(modle_b200_epoch_record) == 56 && offsetof(modle_b200_epoch_record, burnin) == 16, "");
 static_assert(sizeof(modle_b200_pixel) == 24 && offsetof(modle_b200_pixel, count) == 16, "");
+static_assert(sizeof(modle_b200_shard) == 40 && offsetof(modle_b200_shard, weight) == 32, "");
 static_assert(MODLE_B200_NUM_PHASES == 26, "");
 
 #define FIELD(S, f) std::printf("%s\"%s\": %zu", first ? "" : ", ", #f, offsetof(S, f)), first = false
@@ -108,6 +109,11 @@ static int print_layout() {
   BEGIN(modle_b200_pixel);
   FIELD(modle_b200_pixel, bin1_id); FIELD(modle_b200_pixel, bin2_id);
   FIELD(modle_b200_pixel, count); FIELD(modle_b200_pixel, reserved_);
+  END();
+  BEGIN(modle_b200_shard);
+  FIELD(modle_b200_shard, interval); FIELD(modle_b200_shard, cell_lo);
+  FIELD(modle_b200_shard, cell_hi); FIELD(modle_b200_shard, rank);
+  FIELD(modle_b200_shard, reserved_); FIELD(modle_b200_shard, weight);
   END();
   std::printf(", \"abi_version\": %d, \"num_phases\": %d}\n", modle_b200_abi_version(),
               MODLE_B200_NUM_PHASES);

@@ -38,6 +38,7 @@ def gpu_ctx(product_lib):
 _NOT_YET_RUN_ON_A_DEVICE = (
     "test_gpu_full_geometry.py",
     "test_compiled_consumer_equals_the_ctypes_path_and_the_oracle",
+    "test_cpp_host_drives_several_gpus_through_the_c_abi",
 )
 
 

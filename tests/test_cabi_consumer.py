@@ -23,7 +23,7 @@ MIRRORS = {
     "modle_b200_sim_params": abi.SimParams, "modle_b200_interval": abi.Interval,
     "modle_b200_barrier": abi.Barrier, "modle_b200_cell_task": abi.CellTask,
     "modle_b200_cell_stats": abi.CellStats, "modle_b200_cell_snapshot": abi.CellSnapshot,
-    "modle_b200_pixel": abi.Pixel,
+    "modle_b200_pixel": abi.Pixel, "modle_b200_shard": abi.ShardRecord,
 }
 
 
@@ -47,7 +47,8 @@ def test_header_layout_equals_the_ctypes_mirror(consumer):
         assert rec.fields[f][1] == off, f
     barrier_dt, task_dt, stats_dt = abi.np_dtypes()
     for dt, name in ((barrier_dt, "modle_b200_barrier"), (task_dt, "modle_b200_cell_task"),
-                     (stats_dt, "modle_b200_cell_stats"), (abi.pixel_dtype(), "modle_b200_pixel")):
+                     (stats_dt, "modle_b200_cell_stats"), (abi.pixel_dtype(), "modle_b200_pixel"),
+                     (abi.shard_dtype(), "modle_b200_shard")):
         for f, off in lay[name]["fields"].items():
             assert dt.fields[f][1] == off, (name, f)
 
