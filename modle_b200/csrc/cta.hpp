@@ -320,6 +320,62 @@ struct Cta {
     __syncthreads();
   }
 
+  // Two independent exclusive prefix-MIN scans of one i32 per thread (thread order), in one go.
+  // The first thread receives INT32_MAX.
+  MB_FN void exscan_min2_i32(PerThread<i32>& pa, PerThread<i32>& pb) const {
+    const int tid = first();
+    const int lane = tid & 31, warp = tid >> 5, nw = (nt() + 31) >> 5;
+    i32 a = pa.val, b = pb.val;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const i32 oa = __shfl_up_sync(0xffffffffu, a, d);
+      const i32 ob = __shfl_up_sync(0xffffffffu, b, d);
+      if (lane >= d) {
+        a = oa < a ? oa : a;
+        b = ob < b ? ob : b;
+      }
+    }
+    if (lane == 31)
+      scr->warp_u64[warp] = (u64(static_cast<u32>(a)) << 32) | u64(static_cast<u32>(b));
+    __syncthreads();
+    if (warp == 0) {
+      const u64 w = lane < nw ? scr->warp_u64[lane] : ~u64(0);
+      i32 wa = lane < nw ? static_cast<i32>(static_cast<u32>(w >> 32)) : 0x7FFFFFFF;
+      i32 wb = lane < nw ? static_cast<i32>(static_cast<u32>(w)) : 0x7FFFFFFF;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const i32 oa = __shfl_up_sync(0xffffffffu, wa, d);
+        const i32 ob = __shfl_up_sync(0xffffffffu, wb, d);
+        if (lane >= d) {
+          wa = oa < wa ? oa : wa;
+          wb = ob < wb ? ob : wb;
+        }
+      }
+      // exclusive: warp w gets the inclusive value of warp w - 1
+      i32 ea = __shfl_up_sync(0xffffffffu, wa, 1);
+      i32 eb = __shfl_up_sync(0xffffffffu, wb, 1);
+      if (lane == 0) {
+        ea = 0x7FFFFFFF;
+        eb = 0x7FFFFFFF;
+      }
+      if (lane < nw)
+        scr->warp_u64b[lane] = (u64(static_cast<u32>(ea)) << 32) | u64(static_cast<u32>(eb));
+    }
+    __syncthreads();
+    const u64 wp = scr->warp_u64b[warp];
+    const i32 wpa = static_cast<i32>(static_cast<u32>(wp >> 32));
+    const i32 wpb = static_cast<i32>(static_cast<u32>(wp));
+    i32 xa = __shfl_up_sync(0xffffffffu, a, 1);
+    i32 xb = __shfl_up_sync(0xffffffffu, b, 1);
+    if (lane == 0) {
+      xa = 0x7FFFFFFF;
+      xb = 0x7FFFFFFF;
+    }
+    pa.val = wpa < xa ? wpa : xa;
+    pb.val = wpb < xb ? wpb : xb;
+    __syncthreads();
+  }
+
   // ---- collectives over PerThread values (uniform results returned to every thread) ----
   MB_FN u64 exscan_sum(PerThread<u64>& v) const {
     u64 total;
@@ -444,6 +500,7 @@ struct Cta {
 
 #define MB_ATOMIC_MAX_U32(ptr, val) atomicMax((ptr), (val))
 #define MB_ATOMIC_OR_U32(ptr, val) atomicOr((ptr), (val))
+#define MB_ATOMIC_AND_U32(ptr, val) atomicAnd((ptr), (val))
 #define MB_ATOMIC_ADD_U32(ptr, val) atomicAdd((ptr), (val))
 #define MB_ATOMIC_ADD_U64(ptr, val) \
   atomicAdd(reinterpret_cast<unsigned long long*>(ptr), static_cast<unsigned long long>(val))
@@ -560,6 +617,20 @@ struct Cta {
     exscan_minplus(b);
     emu_barrier_count() -= 3;  // one collective on the device
   }
+  void exscan_min2_i32(PerThread<i32>& a, PerThread<i32>& b) const {
+    scr->warp_u64[my] = static_cast<u64>(static_cast<u32>(a.val));
+    scr->warp_u64b[my] = static_cast<u64>(static_cast<u32>(b.val));
+    sync();
+    i32 ma = 0x7FFFFFFF, mb = 0x7FFFFFFF;
+    for (int t = 0; t < my; ++t) {
+      ma = std::min(ma, static_cast<i32>(static_cast<u32>(scr->warp_u64[t])));
+      mb = std::min(mb, static_cast<i32>(static_cast<u32>(scr->warp_u64b[t])));
+    }
+    sync();
+    emu_barrier_count() += 1;  // the device version has three barriers
+    a.val = ma;
+    b.val = mb;
+  }
   void exscan_secop(PerThread<SecOp>& v) const {
     scr->warp_u64[my] = static_cast<u64>(v.val.T);
     scr->warp_u64b[my] = static_cast<u64>(v.val.a);
@@ -599,6 +670,7 @@ inline u32 emu_atomic_min_u32(u32* p, u32 v) {
 #define MB_ATOMIC_MAX_U32(ptr, val) emu_atomic_max_u32((ptr), (val))
 #define MB_ATOMIC_MIN_U32_(ptr, val) emu_atomic_min_u32((ptr), (val))
 #define MB_ATOMIC_OR_U32(ptr, val) __atomic_fetch_or((ptr), (val), __ATOMIC_RELAXED)
+#define MB_ATOMIC_AND_U32(ptr, val) __atomic_fetch_and((ptr), (val), __ATOMIC_RELAXED)
 #define MB_ATOMIC_ADD_U32(ptr, val) __atomic_fetch_add((ptr), (val), __ATOMIC_RELAXED)
 #define MB_ATOMIC_ADD_U64(ptr, val) __atomic_fetch_add((ptr), (val), __ATOMIC_RELAXED)
 #define MB_U64_TO_F64(x) static_cast<double>(x)
@@ -695,6 +767,17 @@ struct Cta {
     exscan_minplus(b);
     emu_barrier_count() -= 3;  // one collective on the device
   }
+  void exscan_min2_i32(PerThread<i32>& a, PerThread<i32>& b) const {
+    emu_barrier_count() += 3;
+    i32 ma = 0x7FFFFFFF, mb = 0x7FFFFFFF;
+    for (int t = 0; t < nthreads; ++t) {
+      const i32 xa = a[t], xb = b[t];
+      a[t] = ma;
+      b[t] = mb;
+      ma = std::min(ma, xa);
+      mb = std::min(mb, xb);
+    }
+  }
   void exscan_secop2(PerThread<SecOp>& a, PerThread<SecOp>& b) const {
     exscan_secop(a);
     exscan_secop(b);
@@ -713,6 +796,7 @@ struct Cta {
 
 #define MB_ATOMIC_MAX_U32(ptr, val) (*(ptr) = std::max<u32>(*(ptr), (val)))
 #define MB_ATOMIC_OR_U32(ptr, val) (*(ptr) |= (val))
+#define MB_ATOMIC_AND_U32(ptr, val) (*(ptr) &= (val))
 #define MB_ATOMIC_ADD_U32(ptr, val) (*(ptr) += (val))
 #define MB_ATOMIC_ADD_U64(ptr, val) (*(ptr) += (val))
 #define MB_U64_TO_F64(x) static_cast<double>(x)

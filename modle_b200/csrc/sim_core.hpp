@@ -143,14 +143,6 @@ MB_FN u64 mix64(u64 z) {  // SplitMix64 output function
 }
 
 // The per-cell simulator. All member functions are CTA-collective unless noted.
-// Experiment switch (default off: the product's deterministic kernels are unchanged): compile
-// with -DMODLE_B200_WINDOW_RANK_REPAIR=1 to give the deterministic mode the window repair of
-// rank_lefs() that the throughput mode uses (same permutation, fewer sweeps and barriers).
-// `modle_b200.build.build(variant=..., defines=[...])` builds such a copy for an A/B on a B200;
-// tests/test_emulation_parity.py checks the variant against the oracle on the CPU.
-#ifndef MODLE_B200_WINDOW_RANK_REPAIR
-#define MODLE_B200_WINDOW_RANK_REPAIR 0
-#endif
 // kCtr = false: deterministic mode (the reference's draw order); true: throughput mode.
 template <bool kCtr>
 struct CellSimT {
@@ -974,12 +966,15 @@ struct CellSimT {
   // between unchanged LEFs are repaired by odd-even transposition passes, and anything else
   // (more changed LEFs than the scratch holds, a still unsorted list) takes the full sort.
   MB_FN void rank_lefs() {
-    constexpr bool kWindowRepair = kCtr || MODLE_B200_WINDOW_RANK_REPAIR != 0;
     const u32 n = S.num_active;
     if (n < 2) return;
-    // scratch areas that are dead at this point of the epoch: moves, collision words, scratch
+    // scratch areas that are dead at this point of the epoch: moves, collision words, scratch,
+    // and the bitmaps of the secondary pass (two "dirty pair" bitmaps live there)
     u16* prev_r = reinterpret_cast<u16*>(A.rc);  // previous slot of every LEF in the rev order
     u16* prev_f = reinterpret_cast<u16*>(A.fc);
+    const u32 nwords = (n + 31) / 32;
+    u32* dirty_r = A.bits;  // bit k: the pair of rank slots (k, k + 1) has to be looked at
+    u32* dirty_f = A.bits + nwords;
     const u32 cur = static_cast<u32>(S.epoch);
     u32 max_changed = static_cast<u32>(cell_scratch_words(P.n_lefs, P.n_bar) / 4);
     if (max_changed > 512) max_changed = 512;
@@ -996,10 +991,8 @@ struct CellSimT {
         c += u64(A.ep[f] == cur) << 32;
       }
       cnt[tid] = c;
-      if (cta.leader(tid)) {
-        S.tmp_u32[5] = 0;
-        if constexpr (kWindowRepair) S.tmp_u32[6] = S.tmp_u32[7] = 0;
-      }
+      for (u32 w = tid; w < 2 * nwords; w += cta.nt()) A.bits[w] = 0;
+      if (cta.leader(tid)) S.tmp_u32[4] = S.tmp_u32[5] = S.tmp_u32[6] = 0;
     }
     const u64 tot = cta.exscan_sum(cnt);
     const u32 nc = static_cast<u32>(tot & 0xFFFFFFFFu);
@@ -1008,101 +1001,73 @@ struct CellSimT {
       return;
     }
     if (nc != 0) rank_lefs_merge(cnt, nc, prev_r, prev_f);
-    if constexpr (kWindowRepair) {
-      // Window repair (tried in the throughput mode first; the result of a sort does not depend
-      // on how it is reached). The odd-even passes below move a rank one slot per sweep and
-      // typically need three passes = six sweeps; here every thread insertion-sorts
-      // its own chunk of consecutive ranks, then the chunk shifted by half its length, and a
-      // read-only sweep over all adjacent pairs verifies: three sweeps in the usual case. (Needs
-      // chunks of at least two ranks for the shifted windows to straddle the chunk boundaries;
-      // the few LEFs of the first burn-in epochs take the general repair.)
-      for (u32 round = 0; round < 4 && n >= 2 * static_cast<u32>(cta.nt()); ++round) {
-        for (u32 half = 0; half < 2; ++half) {
-          MB_REGION(cta, tid) {
-            u32 lo, hi;
-            chunk(tid, n, &lo, &hi);
-            if (half == 1) {
-              u32 lo2 = n, hi2 = n;
-              if (tid + 1 < cta.nt()) chunk(tid + 1, n, &lo2, &hi2);
-              lo = lo + (hi - lo) / 2;
-              hi = lo2 + (hi2 - lo2) / 2;
-            }
-            bool moved = false;
-            for (u32 k = lo + 1; k < hi; ++k) {
-              const u16 x = A.rr[k];
-              u32 j = k;
-              while (j > lo && rank_less<true>(x, A.rr[j - 1], prev_r)) {
-                A.rr[j] = A.rr[j - 1];
-                --j;
-              }
-              if (j != k) {
-                A.rr[j] = x;
-                moved = true;
-              }
-              const u16 y = A.fr[k];
-              j = k;
-              while (j > lo && rank_less<false>(y, A.fr[j - 1], prev_f)) {
-                A.fr[j] = A.fr[j - 1];
-                --j;
-              }
-              if (j != k) {
-                A.fr[j] = y;
-                moved = true;
-              }
-            }
-            (void)moved;
-          }
-          cta.sync();
-        }
-        MB_REGION(cta, tid) {
-          u32 lo, hi;
-          chunk(tid, n, &lo, &hi);
-          bool bad = false;
-          for (u32 k = lo; k < hi && k + 1 < n; ++k) {
-            bad |= rank_less<true>(A.rr[k + 1], A.rr[k], prev_r);
-            bad |= rank_less<false>(A.fr[k + 1], A.fr[k], prev_f);
-          }
-          if (bad) MB_SHARED_STORE_U32(&S.tmp_u32[6 + (round & 1)], 1u);
-          // the other flag was last read before this round's first barrier: safe to reset now
-          if (cta.leader(tid)) S.tmp_u32[6 + ((round + 1) & 1)] = 0;
-        }
-        cta.sync();
-        if (S.tmp_u32[6 + (round & 1)] == 0) return;
-      }
-      cta.sync();  // (not sorted after four rounds, or too few LEFs: the general repair)
-    }
-    // Verify / repair: units can legitimately cross during extrude() (a unit is not tested
+    // Verify / repair. Units can legitimately cross during extrude() (a unit is not tested
     // against the unit behind an avoided secondary collision) and new ties need their epoch
-    // order, so run odd-even transposition passes until one finds nothing to swap.
-    constexpr u32 kRepairPasses = 8;
-    for (u32 pass = 0; pass < kRepairPasses; ++pass) {
-      for (u32 parity = 0; parity < 2; ++parity) {
-        MB_REGION(cta, tid) {
-          bool swapped = false;
-          for (u32 k = parity + 2 * static_cast<u32>(tid); k + 1 < n; k += 2 * cta.nt()) {
-            const u16 a = A.rr[k], b = A.rr[k + 1];
-            if (rank_less<true>(b, a, prev_r)) {
-              A.rr[k] = b;
-              A.rr[k + 1] = a;
-              swapped = true;
-            }
-            const u16 c = A.fr[k], d = A.fr[k + 1];
-            if (rank_less<false>(d, c, prev_f)) {
-              A.fr[k] = d;
-              A.fr[k + 1] = c;
-              swapped = true;
-            }
-          }
-          if (swapped) MB_SHARED_STORE_U32(&S.tmp_u32[5 + (pass & 1)], 1u);
-          // the other flag was last read before this pass's first barrier: safe to reset now
-          if (parity == 1 && cta.leader(tid)) S.tmp_u32[5 + ((pass + 1) & 1)] = 0;
+    // order: typically a handful of adjacent pairs of a few thousand are out of order, each a
+    // slot or two from its place. One sweep over all adjacent pairs marks the out-of-order ones
+    // in a bitmap; after that only marked pairs are looked at: a round takes the marked pairs
+    // of one parity (they are disjoint), swaps those that are out of order and marks their two
+    // neighbours -- the only pairs a swap can break -- for the next round. The invariant "every
+    // out-of-order pair is marked" holds throughout, so when no marks are left the permutation
+    // is the sorted one (the order is total, so any correct sort gives the same result).
+    MB_REGION(cta, tid) {
+      u32 lo, hi;
+      chunk(tid, n, &lo, &hi);
+      bool any = false;
+      for (u32 k = lo; k < hi && k + 1 < n; ++k) {
+        if (rank_less<true>(A.rr[k + 1], A.rr[k], prev_r)) {
+          MB_ATOMIC_OR_U32(&dirty_r[k >> 5], 1u << (k & 31));
+          any = true;
         }
-        cta.sync();
+        if (rank_less<false>(A.fr[k + 1], A.fr[k], prev_f)) {
+          MB_ATOMIC_OR_U32(&dirty_f[k >> 5], 1u << (k & 31));
+          any = true;
+        }
       }
-      if (S.tmp_u32[5 + (pass & 1)] == 0) return;
+      if (any) MB_SHARED_STORE_U32(&S.tmp_u32[4], 1u);
     }
     cta.sync();
-    rank_lefs_full(prev_r, prev_f);
+    constexpr u32 kMaxRounds = 64;
+    for (u32 round = 0; round < kMaxRounds; ++round) {
+      // Three flags take turns: round r reads tmp_u32[4 + r % 3] ("marks were left for this
+      // round"), sets the next one for round r + 1 and clears the third -- which round r - 1 read
+      // before the barrier that ended it, and which nobody writes until round r + 1.
+      // (Shared by design: the word read here is not the one this round's region writes.)
+      if (MB_SHARED_LOAD_U32(&S.tmp_u32[4 + round % 3]) == 0) return;
+      const u32 parity_mask = (round & 1) ? 0xAAAAAAAAu : 0x55555555u;
+      MB_REGION(cta, tid) {
+        bool left = false;
+        for (u32 w = tid; w < 2 * nwords; w += cta.nt()) {
+          const bool is_rev = w < nwords;
+          const u32 ww = is_rev ? w : w - nwords;
+          u32* dirty = is_rev ? dirty_r : dirty_f;
+          u16* ranks = is_rev ? A.rr : A.fr;
+          const u32 all = MB_SHARED_LOAD_U32(&dirty[ww]);
+          u32 mine = all & parity_mask;
+          if (all & ~parity_mask) left = true;
+          if (mine == 0) continue;
+          MB_ATOMIC_AND_U32(&dirty[ww], ~mine);
+          while (mine) {
+            const u32 bit = static_cast<u32>(MB_FFS(mine)) - 1;
+            mine &= mine - 1;
+            const u32 k = 32 * ww + bit;
+            if (k + 1 >= n) continue;
+            const u16 a = ranks[k], b = ranks[k + 1];
+            const bool swap = is_rev ? rank_less<true>(b, a, prev_r) : rank_less<false>(b, a, prev_f);
+            if (!swap) continue;
+            ranks[k] = b;
+            ranks[k + 1] = a;
+            if (k > 0) MB_ATOMIC_OR_U32(&dirty[(k - 1) >> 5], 1u << ((k - 1) & 31));
+            if (k + 2 < n) MB_ATOMIC_OR_U32(&dirty[(k + 1) >> 5], 1u << ((k + 1) & 31));
+            left = true;
+          }
+        }
+        if (left) MB_SHARED_STORE_U32(&S.tmp_u32[4 + (round + 1) % 3], 1u);
+        if (cta.leader(tid)) MB_SHARED_STORE_U32(&S.tmp_u32[4 + (round + 2) % 3], 0u);
+      }
+      cta.sync();
+    }
+    rank_lefs_full(prev_r, prev_f);  // (not sorted after kMaxRounds: cannot happen in practice)
   }
 
   // The merge step of rank_lefs: cnt = per-thread exclusive counts of changed LEFs (rev order in
@@ -1347,7 +1312,9 @@ struct CellSimT {
             ++registered;
           }
         }
-        if (registered) MB_ATOMIC_ADD_U64(&S.tmp_u64[1], u64(registered));
+        // (a 32-bit shared-memory reduction is one native instruction; the 64-bit form is a
+        // compare-and-swap loop that 1,024 threads would fight over)
+        if (registered) MB_ATOMIC_ADD_U32(&S.tmp_u32[7], registered);
         if (cta.leader(tid)) {
           u64 consumed = u64(valid) * stride;
           if (exc != 0xFFFFFFFFu) {
@@ -1388,7 +1355,7 @@ struct CellSimT {
           if constexpr (!kCtr) S.rng_pos = c.pos;
         }
         S.tmp_u32[1] = static_cast<u32>(nloop);
-        S.tmp_u64[1] = 0;
+        S.tmp_u32[7] = 0;  // contacts registered this epoch
       }
     }
     cta.sync();
@@ -1418,7 +1385,9 @@ struct CellSimT {
             ++registered;
           }
         }
-        if (registered) MB_ATOMIC_ADD_U64(&S.tmp_u64[1], u64(registered));
+        // (a 32-bit shared-memory reduction is one native instruction; the 64-bit form is a
+        // compare-and-swap loop that 1,024 threads would fight over)
+        if (registered) MB_ATOMIC_ADD_U32(&S.tmp_u32[7], registered);
       }
       cta.sync();
     } else {
@@ -1427,7 +1396,7 @@ struct CellSimT {
       if (P.track_1d) sampling_events(static_cast<u32>(nev), 2);
     }
     MB_REGION(cta, tid) {
-      if (cta.leader(tid)) S.num_contacts += S.tmp_u64[1];
+      if (cta.leader(tid)) S.num_contacts += S.tmp_u32[7];
     }
     cta.sync();
   }
@@ -1770,6 +1739,23 @@ struct CellSimT {
     }
     return a;
   }
+  MB_FN u32 count_fwd_lt_from_top(u64 thr) const {  // number of fwd ranks with pos < thr
+    u32 c = S.num_active;
+    for (int step = 0; step < 4; ++step) {
+      if (c == 0 || u64(A.fwd[A.fr[c - 1]]) < thr) return c;
+      --c;
+    }
+    u32 a = 0, b = c;
+    while (a < b) {
+      const u32 m = (a + b) >> 1;
+      if (u64(A.fwd[A.fr[m]]) < thr) {
+        a = m + 1;
+      } else {
+        b = m;
+      }
+    }
+    return a;
+  }
   MB_FN u32 count_rev_le(u64 thr) const {  // number of rev ranks with pos <= thr (binary search)
     u32 a = 0, b = S.num_active;
     while (a < b) {
@@ -1824,50 +1810,58 @@ struct CellSimT {
     if (n >= 2) {
       // rev units, walked 3'->5': q'[k-1] = min(q[k-1], q'[k] - 1); fwd units, walked 5'->3':
       // q'[k] = max(q[k], q'[k-1] + 1) (negated: min-plus). Both scans run together.
-      const u32 k_near = count_rev_le(u64(P.start) + mmax + n);  // rev ranks < k_near: serial part
+      // (every thread needs both counts; few units sit that close to an interval end, so a few
+      // linear steps from the end in question almost always settle them)
+      const u32 k_near = count_rev_le_from(u64(P.start) + mmax + n, 0);  // rev ranks < k_near: serial part
       const u32 M = n - k_near;                                  // rev ranks [k_near, n) in parallel
       const u64 far_thr = u64(P.end) - 1 > mmax + n ? u64(P.end) - 1 - mmax - n : 0;
-      const u32 k_far = count_fwd_lt(far_thr);  // fwd ranks [0, k_far) in parallel
-      PerThread<MinPlus> f(cta.nt()), g(cta.nt());
+      const u32 k_far = count_fwd_lt_from_top(far_thr);  // fwd ranks [0, k_far) in parallel
+      // With x[m] the end position of the unit at scan position m, the recurrence
+      // x[m] = min(q[m], x[m-1] - 1) unrolls to x[m] = min_{j <= m}(q[j] + j) - m: a plain
+      // prefix minimum of q[j] + j (positions and moves fit 32 bits with room to spare).
+      PerThread<i32> f(cta.nt()), g(cta.nt());
       MB_REGION(cta, tid) {
         u32 lo, hi;
         chunk(tid, M, &lo, &hi);
-        MinPlus acc = minplus_identity();
+        i32 acc = 0x7FFFFFFF;
         for (u32 m = lo; m < hi; ++m) {
           const u32 idx = A.rr[n - 1 - m];
-          const i64 q = i64(A.rev[idx]) - i64(A.rm[idx]);
-          acc = minplus_then(acc, MinPlus{q, -1});
+          const i32 r = static_cast<i32>(A.rev[idx]) - static_cast<i32>(A.rm[idx]) +
+                        static_cast<i32>(m);
+          acc = r < acc ? r : acc;
         }
         f[tid] = acc;
         chunk(tid, k_far, &lo, &hi);
-        acc = minplus_identity();
+        acc = 0x7FFFFFFF;
         for (u32 k = lo; k < hi; ++k) {
           const u32 idx = A.fr[k];
-          const i64 q = i64(A.fwd[idx]) + i64(A.fm[idx]);
-          acc = minplus_then(acc, MinPlus{-q, -1});
+          const i32 r = static_cast<i32>(k) -
+                        (static_cast<i32>(A.fwd[idx]) + static_cast<i32>(A.fm[idx]));
+          acc = r < acc ? r : acc;
         }
         g[tid] = acc;
       }
-      cta.exscan_minplus2(f, g);
+      cta.exscan_min2_i32(f, g);
       MB_REGION(cta, tid) {
         u32 lo, hi;
         chunk(tid, M, &lo, &hi);
-        i64 x = minplus_apply(f[tid], kMinPlusInf);
+        i32 run = f[tid];
         for (u32 m = lo; m < hi; ++m) {
           const u32 idx = A.rr[n - 1 - m];
-          const i64 q = i64(A.rev[idx]) - i64(A.rm[idx]);
-          const i64 cap = x - 1;
-          x = q < cap ? q : cap;
-          A.rm[idx] = static_cast<u32>(i64(A.rev[idx]) - x);
+          const i32 rev = static_cast<i32>(A.rev[idx]);
+          const i32 r = rev - static_cast<i32>(A.rm[idx]) + static_cast<i32>(m);
+          run = r < run ? r : run;
+          A.rm[idx] = static_cast<u32>(rev - (run - static_cast<i32>(m)));
         }
         chunk(tid, k_far, &lo, &hi);
-        x = minplus_apply(g[tid], kMinPlusInf);
+        run = g[tid];
         for (u32 k = lo; k < hi; ++k) {
           const u32 idx = A.fr[k];
-          const i64 nq = -(i64(A.fwd[idx]) + i64(A.fm[idx]));
-          const i64 cap = x - 1;
-          x = nq < cap ? nq : cap;
-          A.fm[idx] = static_cast<u32>(-x - i64(A.fwd[idx]));
+          const i32 fwd = static_cast<i32>(A.fwd[idx]);
+          const i32 r = static_cast<i32>(k) - (fwd + static_cast<i32>(A.fm[idx]));
+          run = r < run ? r : run;
+          // end position = -(run - k)
+          A.fm[idx] = static_cast<u32>(static_cast<i32>(k) - run - fwd);
         }
       }
       cta.sync();
@@ -2047,21 +2041,92 @@ struct CellSimT {
     const bool frac_min = pmin != 0.0 && pmin != 1.0;
     const u32 tmp_ev = kEvTmp | kEvCollision | kEvLefBar;
     if (!frac_maj && !frac_min) {
-      // (independent full binary searches per barrier: measured faster than walking each
-      // thread's barriers in order with the previous answer as a hint)
+      // No trial needs a draw, so the search can be turned around: instead of two binary
+      // searches over the (doubly indirect) rank orders per barrier, every thread walks its
+      // contiguous share of the rev ranks and of the fwd ranks together with the sorted barrier
+      // positions -- one binary search over bar_pos for the first unit of the share, then the
+      // barrier cursor only moves forward. The barriers that test rev rank k are those with
+      // pos[k-1] <= bp < pos[k] (all below pos[k] for k == j0); the closest one that is active,
+      // blocks this direction with certainty and lies within the unit's move wins, exactly what
+      // the per-barrier atomicMax selected. A hit overrides a boundary mark, as before.
+      const bool rev_hit_maj = pmaj == 1.0, rev_hit_min = pmin == 1.0;
       MB_REGION(cta, tid) {
-        for (u32 b = tid; b < nb; b += cta.nt()) {
-          if (!A.bar_active[b]) continue;
-          const bool brev = bar_blocks_rev(b);
-          u32 unit;
-          u32 nohint_r = 0xFFFFFFFFu, nohint_f = 0xFFFFFFFFu;
-          if ((brev ? pmaj : pmin) == 1.0 && lef_bar_candidate_rev(b, j0, &unit, &nohint_r))
-            MB_ATOMIC_MAX_U32(&A.rc[unit], coll_make(b, tmp_ev));
-          if ((brev ? pmin : pmaj) == 1.0 && lef_bar_candidate_fwd(b, jend, &unit, &nohint_f))
-            MB_ATOMIC_MAX_U32(&A.fc[unit], coll_make(nb - 1 - b, tmp_ev));
+        u32 lo, hi;
+        if (j0 < n && (rev_hit_maj || rev_hit_min)) {
+          chunk(tid, n - j0, &lo, &hi);
+          u32 b = 0;  // number of barriers with bar_pos < pos of the current unit
+          bool first = true;
+          for (u32 k = j0 + lo; k < j0 + hi; ++k) {
+            const u32 idx = A.rr[k];
+            const u32 pos = A.rev[idx];
+            if (first) {
+              u32 a = 0, z = nb;
+              while (a < z) {
+                const u32 mid = (a + z) >> 1;
+                if (A.bar_pos[mid] < pos) {
+                  a = mid + 1;
+                } else {
+                  z = mid;
+                }
+              }
+              b = a;
+              first = false;
+            } else {
+              while (b < nb && A.bar_pos[b] < pos) ++b;
+            }
+            if (b == 0) continue;
+            const u32 lower = k > j0 ? A.rev[A.rr[k - 1]] : 0u;
+            const u32 mv = A.rm[idx];
+            for (u32 t = b; t-- > 0;) {
+              const u32 bp = A.bar_pos[t];
+              if (bp < lower || pos - bp > mv) break;
+              if (!A.bar_active[t]) continue;
+              if (bar_blocks_rev(t) ? rev_hit_maj : rev_hit_min) {
+                A.rc[idx] = coll_make(t, kEvCollision | kEvLefBar);
+                break;
+              }
+            }
+          }
+        }
+        if (rev_hit_maj || rev_hit_min) {  // fwd units: major blocks when the barrier does NOT block rev
+          chunk(tid, jend + 1, &lo, &hi);
+          u32 b = 0;  // number of barriers with bar_pos <= pos of the current unit
+          bool first = true;
+          for (u32 k = lo; k < hi; ++k) {
+            const u32 idx = A.fr[k];
+            const u32 pos = A.fwd[idx];
+            if (first) {
+              u32 a = 0, z = nb;
+              while (a < z) {
+                const u32 mid = (a + z) >> 1;
+                if (A.bar_pos[mid] <= pos) {
+                  a = mid + 1;
+                } else {
+                  z = mid;
+                }
+              }
+              b = a;
+              first = false;
+            } else {
+              while (b < nb && A.bar_pos[b] <= pos) ++b;
+            }
+            if (b == nb) break;  // no barrier downstream of this or any later unit
+            const u32 upper = k < jend ? A.fwd[A.fr[k + 1]] : 0xFFFFFFFFu;
+            const u32 mv = A.fm[idx];
+            for (u32 t = b; t < nb; ++t) {
+              const u32 bp = A.bar_pos[t];
+              if (bp > upper || bp - pos > mv) break;
+              if (!A.bar_active[t]) continue;
+              if (bar_blocks_rev(t) ? rev_hit_min : rev_hit_maj) {
+                A.fc[idx] = coll_make(t, kEvCollision | kEvLefBar);
+                break;
+              }
+            }
+          }
         }
       }
       cta.sync();
+      return;
     } else if constexpr (kCtr) {
       // fractional pblock: trial (barrier b, direction) reads draw 2b / 2b+1 of this epoch
       MB_REGION(cta, tid) {
@@ -2354,59 +2419,75 @@ struct CellSimT {
     u32* head1;  // by scan position: ... directly behind an already stalled unit
   };
 
+  // Candidates of one direction, found by walking from every unit that was stalled BEFORE this
+  // pass (a "head": LEF-BAR, primary or boundary collision): the free units behind it are
+  // candidates for as long as each would reach the site of the one before (q[k] <= v), assuming
+  // the trials of the earlier ones succeed; the run ends at the first unit out of reach or at
+  // the next head (whose owner walks on from there). Runs are disjoint, so the walks of
+  // different heads write different words; a walk may leave its thread's chunk of scan
+  // positions. Every candidate gets its move-if-stalled parked in the index bits of its (so far
+  // empty) collision word, its bit in `cand`, and -- directly behind the head -- in `head1`.
+  // Throughput mode: a candidate's trial is keyed by (pass, scan position), so the walk runs it
+  // on the spot, marks only the candidates it REACHES, records the successful ones in `ok`, and
+  // stops at the first failure (kNever: trials cannot succeed and draw nothing).
   template <bool kRevPass>
-  MB_FN SecOp sec_compose(const SecDir& d, int tid) const {
-    const u32* coll = kRevPass ? A.rc : A.fc;
-    u32 lo, hi;
-    chunk(tid, d.M, &lo, &hi);
-    SecOp acc = secop_identity();
-    for (u32 m = lo; m < hi; ++m) {
-      const u32 idx = sec_idx<kRevPass>(d.first, m);
-      if (coll_occurred(coll[idx])) {
-        acc = secop_const(sec_q<kRevPass>(idx));
-      } else {
-        acc = secop_then(acc, SecOp{sec_q<kRevPass>(idx), sec_pos<kRevPass>(idx), 1});
-      }
-    }
-    return acc;
-  }
-
-  // Marks this thread's candidates and parks each candidate's move-if-stalled in the index bits
-  // of its (so far empty) collision word. Returns the number of candidates.
-  template <bool kRevPass>
-  MB_FN u32 sec_classify(const SecDir& d, int tid, const SecOp& prefix) const {
+  MB_FN void sec_walk(const SecDir& d, int tid, bool draws, bool never, u32* ok) const {
     u32* coll = kRevPass ? A.rc : A.fc;
     u32 lo, hi;
     chunk(tid, d.M, &lo, &hi);
-    bool alive = prefix.b == kSecConst;
-    i64 v = prefix.a;
-    // (the owner of scan position lo - 1 may be parking a move in the index bits of that word;
-    // the event bits read here do not change in this region)
-    bool prev_head = lo > 0 && lo < hi &&
-                     coll_occurred(MB_SHARED_LOAD_U32(&coll[sec_idx<kRevPass>(d.first, lo - 1)]));
-    u32 c = 0;
     for (u32 m = lo; m < hi; ++m) {
       const u32 idx = sec_idx<kRevPass>(d.first, m);
-      if (coll_occurred(coll[idx])) {
-        alive = true;
-        v = sec_q<kRevPass>(idx);
-        prev_head = true;
-        continue;
-      }
-      if (alive && sec_q<kRevPass>(idx) <= v) {
-        const i64 p = sec_pos<kRevPass>(idx);
+      // (a neighbouring walk may be parking a move in the index bits of this word; the event
+      // bits read here do not change in this region)
+      if (!coll_occurred(MB_SHARED_LOAD_U32(&coll[idx]))) continue;
+      i64 v = sec_q<kRevPass>(idx);
+      for (u32 k = m + 1; k < d.M; ++k) {
+        const u32 ik = sec_idx<kRevPass>(d.first, k);
+        if (coll_occurred(MB_SHARED_LOAD_U32(&coll[ik]))) break;
+        if (sec_q<kRevPass>(ik) > v) break;
+        const i64 p = sec_pos<kRevPass>(ik);
         const i64 mv = p - v;  // distance to the blocker's site
-        MB_SHARED_STORE_U32(&coll[idx], static_cast<u32>(mv > 0 ? mv - 1 : 0));  // event bits stay 0
-        MB_ATOMIC_OR_U32(&d.cand[m >> 5], 1u << (m & 31));
-        if (prev_head) MB_ATOMIC_OR_U32(&d.head1[m >> 5], 1u << (m & 31));
+        MB_SHARED_STORE_U32(&coll[ik], static_cast<u32>(mv > 0 ? mv - 1 : 0));  // event bits stay 0
+        MB_ATOMIC_OR_U32(&d.cand[k >> 5], 1u << (k & 31));
+        if (k == m + 1) MB_ATOMIC_OR_U32(&d.head1[k >> 5], 1u << (k & 31));
+        if constexpr (kCtr) {
+          if (never) break;
+          if (draws && !bernoulli_raw(raw(ctr_pack(S.epoch, kDrSecondary,
+                                                   ((kRevPass ? 0u : 1u) << 24) | k)),
+                                      1.0 - P.p_bypass))
+            break;
+          MB_ATOMIC_OR_U32(&ok[k >> 5], 1u << (k & 31));
+        }
         v = p < v + 1 ? p : v + 1;
-        ++c;
-      } else {
-        alive = false;
       }
-      prev_head = false;
     }
+  }
+  // number of candidates among this thread's scan positions
+  MB_FN u32 sec_count(const SecDir& d, int tid) const {
+    u32 lo, hi;
+    chunk(tid, d.M, &lo, &hi);
+    u32 c = 0;
+    for (u32 m = lo; m < hi; ++m) c += (d.cand[m >> 5] >> (m & 31)) & 1u;
     return c;
+  }
+  // Throughput mode: outcome of every reached candidate (`ok` is indexed by scan position).
+  template <bool kRevPass>
+  MB_FN void sec_apply_ctr(const SecDir& d, int tid, const u32* ok) const {
+    u32* coll = kRevPass ? A.rc : A.fc;
+    u32* moves = kRevPass ? A.rm : A.fm;
+    u32 lo, hi;
+    chunk(tid, d.M, &lo, &hi);
+    for (u32 m = lo; m < hi; ++m) {
+      if (!((d.cand[m >> 5] >> (m & 31)) & 1u)) continue;
+      const u32 idx = sec_idx<kRevPass>(d.first, m);
+      const u32 blocker = sec_idx<kRevPass>(d.first, m - 1);
+      if ((ok[m >> 5] >> (m & 31)) & 1u) {
+        moves[idx] = coll[idx];  // parked by sec_walk
+        coll[idx] = coll_make(blocker, kEvCollision | kEvSecondary);
+      } else {
+        coll[idx] = coll_make(blocker, kEvSecondary);
+      }
+    }
   }
 
   // Copies the first-in-run flags of this thread's candidates to their candidate numbers.
@@ -2419,22 +2500,6 @@ struct CellSimT {
       ++c;
     }
   }
-  // Throughput mode: the same walk also runs every candidate's trial -- the candidate at scan
-  // position m of pass `dir` reads draw (dir, m) of this epoch -- and files the failures under the
-  // candidate number (the deterministic mode files them under the draw number instead).
-  MB_FN void sec_number_firsts_and_draw(const SecDir& d, int tid, u32 c, u32 dir, u32* firstc,
-                                        u32* fail) const {
-    u32 lo, hi;
-    chunk(tid, d.M, &lo, &hi);
-    for (u32 m = lo; m < hi; ++m) {
-      if (!((d.cand[m >> 5] >> (m & 31)) & 1u)) continue;
-      if ((d.head1[m >> 5] >> (m & 31)) & 1u) MB_ATOMIC_OR_U32(&firstc[c >> 5], 1u << (c & 31));
-      if (!bernoulli_raw(raw(ctr_pack(S.epoch, kDrSecondary, (dir << 24) | m)), 1.0 - P.p_bypass))
-        MB_ATOMIC_OR_U32(&fail[c >> 5], 1u << (c & 31));
-      ++c;
-    }
-  }
-
   // mode 0: outcomes from the reached / ok bitmaps; 1: every candidate stalls (bypass == 0);
   // 2: trials never succeed and draw nothing (bypass == 1): only run heads are reached.
   template <bool kRevPass>
@@ -2498,21 +2563,36 @@ struct CellSimT {
     u32* bits_fail = A.bits + 10 * nwords;    // by draw
 
     sub_begin();
-    PerThread<SecOp> fr(cta.nt()), ff(cta.nt());
     MB_REGION(cta, tid) {
-      fr[tid] = sec_compose<true>(R, tid);
-      ff[tid] = sec_compose<false>(F, tid);
       for (u32 w = tid; w < 12 * nwords; w += cta.nt()) A.bits[w] = 0;
     }
+    cta.sync();
     sub_lap(kPhSecCompose);
-    cta.exscan_secop2(fr, ff);
+    if constexpr (kCtr) {
+      u32* ok_r = A.bits + 8 * nwords;  // by scan position
+      u32* ok_f = A.bits + 9 * nwords;
+      MB_REGION(cta, tid) {
+        sec_walk<true>(R, tid, draws, never, ok_r);
+        sec_walk<false>(F, tid, draws, never, ok_f);
+      }
+      cta.sync();
+      sub_lap(kPhSecClassify);
+      MB_REGION(cta, tid) {
+        sec_apply_ctr<true>(R, tid, ok_r);
+        sec_apply_ctr<false>(F, tid, ok_f);
+      }
+      cta.sync();
+      sub_lap(kPhSecApply);
+      return;
+    }
+    MB_REGION(cta, tid) {
+      sec_walk<true>(R, tid, draws, never, nullptr);
+      sec_walk<false>(F, tid, draws, never, nullptr);
+    }
+    cta.sync();
     sub_lap(kPhSecScan);
     PerThread<u64> cnt(cta.nt());  // low word: rev candidates, high word: fwd candidates
-    MB_REGION(cta, tid) {
-      const u32 cr = sec_classify<true>(R, tid, fr[tid]);
-      const u32 cf = sec_classify<false>(F, tid, ff[tid]);
-      cnt[tid] = u64(cr) | (u64(cf) << 32);
-    }
+    MB_REGION(cta, tid) { cnt[tid] = u64(sec_count(R, tid)) | (u64(sec_count(F, tid)) << 32); }
     const u64 tot = cta.exscan_sum(cnt);  // cnt[tid]: candidates before this thread's
     const u32 npot_r = static_cast<u32>(tot & 0xFFFFFFFFu);
     const u32 npot = npot_r + static_cast<u32>(tot >> 32);
@@ -2521,18 +2601,11 @@ struct CellSimT {
     if (draws) {
       rng_ensure(S.rng_pos + npot);
       MB_REGION(cta, tid) {
-        if constexpr (kCtr) {
-          sec_number_firsts_and_draw(R, tid, static_cast<u32>(cnt[tid] & 0xFFFFFFFFu), 0u,
-                                     bits_firstc, bits_fail);
-          sec_number_firsts_and_draw(F, tid, npot_r + static_cast<u32>(cnt[tid] >> 32), 1u,
-                                     bits_firstc, bits_fail);
-        } else {
-          sec_number_firsts(R, tid, static_cast<u32>(cnt[tid] & 0xFFFFFFFFu), bits_firstc);
-          sec_number_firsts(F, tid, npot_r + static_cast<u32>(cnt[tid] >> 32), bits_firstc);
-          for (u32 d = tid; d < npot; d += cta.nt()) {
-            if (!bernoulli_raw(raw(S.rng_pos + d), 1.0 - P.p_bypass))
-              MB_ATOMIC_OR_U32(&bits_fail[d >> 5], 1u << (d & 31));
-          }
+        sec_number_firsts(R, tid, static_cast<u32>(cnt[tid] & 0xFFFFFFFFu), bits_firstc);
+        sec_number_firsts(F, tid, npot_r + static_cast<u32>(cnt[tid] >> 32), bits_firstc);
+        for (u32 d = tid; d < npot; d += cta.nt()) {
+          if (!bernoulli_raw(raw(S.rng_pos + d), 1.0 - P.p_bypass))
+            MB_ATOMIC_OR_U32(&bits_fail[d >> 5], 1u << (d & 31));
         }
       }
       cta.sync();
@@ -2561,9 +2634,8 @@ struct CellSimT {
           u32 Rm = __ballot_sync(0xffffffffu, can);
           u32 bad = 0;
           for (int it = 0; it < 34; ++it) {
-            // deterministic mode: the d-th draw belongs to the d-th REACHED candidate;
-            // throughput mode: every candidate owns its trial
-            const u32 dd = kCtr ? 32 * w + lane : d + static_cast<u32>(__popc(Rm & lt));
+            // the d-th draw belongs to the d-th REACHED candidate
+            const u32 dd = d + static_cast<u32>(__popc(Rm & lt));
             const u32 fbit = (bits_fail[dd >> 5] >> (dd & 31)) & 1u;
             bad = __ballot_sync(0xffffffffu, ((Rm >> lane) & 1u) && fbit);
             const u32 Rn = __ballot_sync(0xffffffffu, can && (bad & range) == 0);
@@ -2589,8 +2661,7 @@ struct CellSimT {
           u32 Rm = 0, OK = 0;
           for (u32 i = 0; i < lim; ++i) {
             const u32 reach = ((Fw >> i) & 1u) | alive;
-            const u32 dd = kCtr ? 32 * w + i : d;
-            alive = reach & ~(bits_fail[dd >> 5] >> (dd & 31)) & 1u;
+            alive = reach & ~(bits_fail[d >> 5] >> (d & 31)) & 1u;
             Rm |= reach << i;
             OK |= alive << i;
             d += reach;
@@ -2609,7 +2680,7 @@ struct CellSimT {
       sec_apply<true>(R, tid, static_cast<u32>(cnt[tid] & 0xFFFFFFFFu), mode, bits_reached, bits_ok);
       sec_apply<false>(F, tid, npot_r + static_cast<u32>(cnt[tid] >> 32), mode, bits_reached,
                        bits_ok);
-      if (!kCtr && draws && cta.leader(tid)) S.rng_pos += S.tmp_u32[4];
+      if (draws && cta.leader(tid)) S.rng_pos += S.tmp_u32[4];
     }
     cta.sync();
     sub_lap(kPhSecApply);

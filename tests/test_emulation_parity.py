@@ -258,24 +258,3 @@ def test_barriers_outside_the_interval_are_dead_but_draw(mode):
         # counter-based draws are keyed by barrier index: the leading dead barrier renumbers them
         assert results_equal(a, b) != []
 
-
-def test_window_rank_repair_variant_of_the_deterministic_mode_matches_oracle():
-    """sim_core.hpp's experiment switch MODLE_B200_WINDOW_RANK_REPAIR=1 (the throughput mode's
-    window repair of rank_lefs in the deterministic kernels) must not change a single
-    rank: the same parity cases, the rank fuzz and the reference's ranking goldens, in a child
-    process whose emulation library is built with the switch."""
-    import os
-    import subprocess
-    import sys
-
-    if os.environ.get("MODLE_B200_EMU_DEFINES"):
-        pytest.skip("already inside a variant run")
-    env = dict(os.environ, MODLE_B200_EMU_DEFINES="MODLE_B200_WINDOW_RANK_REPAIR=1")
-    here = os.path.dirname(os.path.abspath(__file__))
-    r = subprocess.run(
-        [sys.executable, "-m", "pytest", "-x", "-q", "-p", "no:cacheprovider",
-         os.path.join(here, "test_emulation_parity.py"), "-k",
-         "emulation_matches_oracle or rank_lefs or per_epoch_state or reference_goldens"],
-        env=env, capture_output=True, text=True, timeout=900)
-    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
-    assert " passed" in r.stdout and "no tests ran" not in r.stdout

@@ -295,3 +295,21 @@ def test_internal_state_statistics_match_the_oracle(throughput):
         se = np.sqrt(a.var(ddof=1) / len(a) + b.var(ddof=1) / len(b))
         assert abs(a.mean() - b.mean()) <= 4 * se + 1e-9, (f, a.mean(), b.mean(), se)
         assert b.mean() > 0 or f == "lefs_stalled_both", f
+
+
+@pytest.mark.parametrize("virtual_threads", [64, 33, 256])
+def test_results_are_pinned_by_the_golden_digests(throughput, virtual_threads):
+    """The throughput mode's outputs are a pure function of the task; the digests committed in
+    tests/golden/throughput_mode_digests.json (written by make_throughput_mode_digests.py) pin
+    that function, so a kernel change that alters any throughput-mode result is seen."""
+    import json
+    import os
+    import sys
+
+    gold_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, gold_dir)
+    import make_throughput_mode_digests as mk
+
+    with open(os.path.join(gold_dir, "throughput_mode_digests.json")) as f:
+        gold = json.load(f)
+    assert mk.compute(virtual_threads) == gold
