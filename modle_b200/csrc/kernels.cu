@@ -432,8 +432,7 @@ int modle_b200_launch_geometry(uint64_t num_lefs, uint64_t num_barriers, uint32_
       pick_staging(static_cast<u32>(num_lefs), static_cast<u32>(num_barriers));
   if (cta_threads) *cta_threads = sc.cta_threads;
   if (cells_per_sm)
-    *cells_per_sm = sc.cta_threads == 256 ? MODLE_B200_SMALL_MIN_BLOCKS
-                                          : (sc.cta_threads == 512 ? 2u : 1u);
+    *cells_per_sm = sc.cells_per_sm == 3 ? MODLE_B200_SMALL_MIN_BLOCKS : sc.cells_per_sm;
   if (shared_bytes_per_cell)
     *shared_bytes_per_cell =
         ((sizeof(CellShared) + 15) / 16) * 16 +
@@ -488,8 +487,13 @@ namespace {
 // adds ~2 G words/s and the genome-wide run brings 370 M words back per step.
 void add_into_u32(u32* dst, const u32* src, size_t n) {
   const size_t kMinPerThread = size_t(1) << 22;
+  static const unsigned max_threads = [] {  // MODLE_B200_HOST_ADD_THREADS: measurement knob
+    const char* e = std::getenv("MODLE_B200_HOST_ADD_THREADS");
+    const int v = e ? std::atoi(e) : 4;
+    return static_cast<unsigned>(std::max(1, std::min(64, v)));
+  }();
   unsigned nt = std::thread::hardware_concurrency();
-  nt = std::max(1u, std::min(8u, nt));
+  nt = std::max(1u, std::min(max_threads, nt));
   nt = static_cast<unsigned>(std::min<size_t>(nt, std::max<size_t>(1, n / kMinPerThread)));
   auto work = [=](size_t lo, size_t hi) {
     for (size_t i = lo; i < hi; ++i) dst[i] += src[i];
@@ -575,10 +579,10 @@ int launch_simulate(modle_b200_context* ctx, const modle_b200_sim_params* params
   // grid: persistent CTAs, as many as fit
   const bool ctr = ctx->rng_mode == MODLE_B200_RNG_COUNTER;
   void (*kernel)(const LaunchArgs) =
-      sc.cta_threads == 256
+      sc.cells_per_sm == 3
           ? (ctr ? k_simulate_cells<256, MODLE_B200_SMALL_MIN_BLOCKS, true>
                  : k_simulate_cells<256, MODLE_B200_SMALL_MIN_BLOCKS>)
-      : sc.cta_threads == 512
+      : sc.cells_per_sm == 2
           ? (ctr ? k_simulate_cells<512, 2, true> : k_simulate_cells<512, 2>)
           : (ctr ? k_simulate_cells<MODLE_B200_LARGE_THREADS, 1, true>
                  : k_simulate_cells<MODLE_B200_LARGE_THREADS, 1>);

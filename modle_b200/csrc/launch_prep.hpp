@@ -40,6 +40,7 @@ struct ZigguratTables {
 // RNG staging configurations: (CTA threads, generator threads G, draws per generator per window l).
 struct StagingConfig {
   u32 cta_threads, gen_threads, per_thread, window, jump_slot;
+  u32 cells_per_sm;  // launch class: 3 (small), 2 (mid) or 1 (large) CTAs per SM
 };
 #ifndef MODLE_B200_LARGE_THREADS
 #define MODLE_B200_LARGE_THREADS 1024
@@ -58,7 +59,8 @@ inline u32 staging_per_thread() {
 inline StagingConfig staging_with_window(u32 cta_threads, u32 window) {
   const u32 l = staging_per_thread();
   const u32 jump_slot = window == 32768 ? 0u : (window == 8192 ? 1u : 2u);
-  return StagingConfig{cta_threads, window / l, l, window, jump_slot};
+  const u32 per_sm = cta_threads == 256 ? 3u : (cta_threads == 512 && window == 16384 ? 2u : 1u);
+  return StagingConfig{cta_threads, window / l, l, window, jump_slot, per_sm};
 }
 inline StagingConfig staging_large() {
   // 16384 draws per window: the rings of all resident CTAs (2 windows each) then stay L2
@@ -71,10 +73,14 @@ inline StagingConfig staging_large() {
     const int v = e ? std::atoi(e) : 16384;
     return v == 32768 ? 32768u : 16384u;
   }();
-  return staging_with_window(MODLE_B200_LARGE_THREADS, w);
+  StagingConfig c = staging_with_window(MODLE_B200_LARGE_THREADS, w);
+  c.cells_per_sm = 1;
+  return c;
 }
 inline StagingConfig staging_large_wide() {
-  return staging_with_window(MODLE_B200_LARGE_THREADS, 32768);
+  StagingConfig c = staging_with_window(MODLE_B200_LARGE_THREADS, 32768);
+  c.cells_per_sm = 1;
+  return c;
 }
 inline StagingConfig staging_small() { return staging_with_window(256, 8192); }
 inline StagingConfig staging_mid() { return staging_with_window(512, 16384); }

@@ -35,6 +35,16 @@ constexpr size_t kJumpTableWords = size_t(32) * 256 * 4;
 #endif
 #endif
 
+// Profiling builds (-DMODLE_B200_PROBE=1, throughput mode only: it borrows the nested phase slots
+// that mode leaves unused) split the rank and LEF-BAR phases further; see scripts/gpu_probe.sh.
+#ifdef MODLE_B200_PROBE
+#define MB_PROBE_BEGIN() sub_begin()
+#define MB_PROBE(slot) sub_lap(slot)
+#else
+#define MB_PROBE_BEGIN() ((void)0)
+#define MB_PROBE(slot) ((void)0)
+#endif
+
 constexpr double kTwo64 = 18446744073709551616.0;
 #if !MB_DEVICE_BUILD
 using std::isfinite;
@@ -943,21 +953,6 @@ struct CellSimT {
 #endif
   }
 
-  // number of elements of the sorted list `lst` (length m) that order before LEF `x`
-  template <bool kRev>
-  MB_FN u32 count_less(const u16* lst, u32 m, u32 x, const u16* prev_slot) const {
-    u32 a = 0, b = m;
-    while (a < b) {
-      const u32 mid = (a + b) >> 1;
-      if (rank_less<kRev>(lst[mid], x, prev_slot)) {
-        a = mid + 1;
-      } else {
-        b = mid;
-      }
-    }
-    return a;
-  }
-
   // rank_lefs (simulation.cpp:410-496). extrude() keeps the relative order of the LEFs that were
   // not (re)bound this epoch, so the new permutation is the old one minus the changed LEFs,
   // merged with the few changed ones: compact the unchanged LEFs, rank the changed ones among
@@ -976,9 +971,10 @@ struct CellSimT {
     u32* dirty_r = A.bits;  // bit k: the pair of rank slots (k, k + 1) has to be looked at
     u32* dirty_f = A.bits + nwords;
     const u32 cur = static_cast<u32>(S.epoch);
-    u32 max_changed = static_cast<u32>(cell_scratch_words(P.n_lefs, P.n_bar) / 4);
+    u32 max_changed = static_cast<u32>(cell_scratch_words(P.n_lefs, P.n_bar) / 6);  // see the merge
     if (max_changed > 512) max_changed = 512;
     PerThread<u64> cnt(cta.nt());
+    MB_PROBE_BEGIN();
     MB_REGION(cta, tid) {
       u32 lo, hi;
       chunk(tid, n, &lo, &hi);
@@ -1000,7 +996,9 @@ struct CellSimT {
       rank_lefs_full(prev_r, prev_f);
       return;
     }
+    MB_PROBE(kPhRngGenerate);
     if (nc != 0) rank_lefs_merge(cnt, nc, prev_r, prev_f);
+    MB_PROBE(kPhMvEnsure);
     // Verify / repair. Units can legitimately cross during extrude() (a unit is not tested
     // against the unit behind an avoided secondary collision) and new ties need their epoch
     // order: typically a handful of adjacent pairs of a few thousand are out of order, each a
@@ -1027,6 +1025,7 @@ struct CellSimT {
       if (any) MB_SHARED_STORE_U32(&S.tmp_u32[4], 1u);
     }
     cta.sync();
+    MB_PROBE(kPhMvScan);
     constexpr u32 kMaxRounds = 64;
     for (u32 round = 0; round < kMaxRounds; ++round) {
       // Three flags take turns: round r reads tmp_u32[4 + r % 3] ("marks were left for this
@@ -1083,7 +1082,9 @@ struct CellSimT {
     const u32 nu = n - nc;
     u32* rank_r = A.scratch;            // [nc] rank of each changed LEF among the changed ones
     u32* rank_f = A.scratch + nc;
-    u16* pos_r = reinterpret_cast<u16*>(A.scratch + 2 * nc);  // [nc] unchanged LEFs before it
+    u32* kp_r = A.scratch + 2 * nc;     // [nc] position of each changed LEF (rev == fwd == where
+    u32* kp_f = A.scratch + 3 * nc;     //      it was just bound), in the order of ch_r / ch_f
+    u16* pos_r = reinterpret_cast<u16*>(A.scratch + 4 * nc);  // [nc] unchanged LEFs before it
     u16* pos_f = pos_r + nc;
     u16* ts_r = pos_f + nc;  // [nc] pos_* ordered by rank_*
     u16* ts_f = ts_r + nc;
@@ -1094,11 +1095,13 @@ struct CellSimT {
       for (u32 k = lo; k < hi; ++k) {
         const u16 r = A.rr[k], f = A.fr[k];
         if (A.ep[r] == cur) {
+          kp_r[cr] = A.rev[r];
           ch_r[cr++] = r;
         } else {
           un_r[k - cr] = r;
         }
         if (A.ep[f] == cur) {
+          kp_f[cf] = A.fwd[f];
           ch_f[cf++] = f;
         } else {
           un_f[k - cf] = f;
@@ -1107,8 +1110,15 @@ struct CellSimT {
       for (u32 j = tid; j < 2 * nc; j += cta.nt()) A.scratch[j] = 0;
     }
     cta.sync();
-    // work items: (changed LEF j, segment s of the changed list) -> partial rank; then one
-    // binary search over the unchanged list per changed LEF; rev order first, then fwd
+    // Work items: (changed LEF j, segment s of the changed list) -> partial rank among the
+    // changed ones; then one binary search over the unchanged list per changed LEF; rev order
+    // first, then fwd. A changed LEF was bound this epoch: both its units sit at one position and
+    // carry the current epoch, so among changed LEFs the order is (position, previous slot) --
+    // and the previous slots ascend along ch_r / ch_f, i.e. ties go by list index -- while
+    // against an unchanged LEF (older epoch) a tie on the position is decided by the epoch rule
+    // alone: older first in the rev order, newer first in the fwd order. (The unchanged lists
+    // may still hold the few out-of-order pairs the repair below removes; the search then picks
+    // some slot nearby and the repair settles it, as it does for every other pair.)
     u32 nseg = static_cast<u32>(cta.nt()) / (2 * nc);
     if (nseg < 1) nseg = 1;
     if (nseg > nc) nseg = nc;
@@ -1117,24 +1127,41 @@ struct CellSimT {
       for (u32 w = tid; w < 2 * per_dir; w += cta.nt()) {
         const bool is_rev = w < per_dir;
         const u32 v = is_rev ? w : w - per_dir;
-        const u16* ch = is_rev ? ch_r : ch_f;
+        const u32* kp = is_rev ? kp_r : kp_f;
         if (v < nc * nseg) {
           const u32 j = v / nseg, s = v % nseg;
           const u32 a = s * nc / nseg, b = (s + 1) * nc / nseg;
-          const u32 x = ch[j];
+          const u32 x = kp[j];
           u32 c = 0;
-          if (is_rev) {
-            for (u32 q = a; q < b; ++q) c += rank_less<true>(ch[q], x, prev_r);
-          } else {
-            for (u32 q = a; q < b; ++q) c += rank_less<false>(ch[q], x, prev_f);
+          for (u32 q = a; q < b; ++q) {
+            const u32 y = kp[q];
+            c += (y < x) || (y == x && q < j);
           }
           if (c) MB_ATOMIC_ADD_U32(is_rev ? &rank_r[j] : &rank_f[j], c);
         } else {
           const u32 j = v - nc * nseg;
-          if (is_rev) {
-            pos_r[j] = static_cast<u16>(count_less<true>(un_r, nu, ch[j], prev_r));
-          } else {
-            pos_f[j] = static_cast<u16>(count_less<false>(un_f, nu, ch[j], prev_f));
+          const u32 x = kp[j];
+          u32 a = 0, b = nu;
+          if (is_rev) {  // unchanged LEFs with rev pos <= x order before it
+            while (a < b) {
+              const u32 mid = (a + b) >> 1;
+              if (A.rev[un_r[mid]] <= x) {
+                a = mid + 1;
+              } else {
+                b = mid;
+              }
+            }
+            pos_r[j] = static_cast<u16>(a);
+          } else {  // unchanged LEFs with fwd pos < x order before it
+            while (a < b) {
+              const u32 mid = (a + b) >> 1;
+              if (A.fwd[un_f[mid]] < x) {
+                a = mid + 1;
+              } else {
+                b = mid;
+              }
+            }
+            pos_f[j] = static_cast<u16>(a);
           }
         }
       }
@@ -2396,23 +2423,21 @@ struct CellSimT {
   MB_FN u32 sec_idx(u32 first, u32 m) const {
     return kRevPass ? A.rr[first + m] : A.fr[first - m];
   }
+  // (32-bit signed: positions are below 2^28 and moves below 2^24)
   template <bool kRevPass>
-  MB_FN i64 sec_pos(u32 idx) const {
-    return kRevPass ? i64(A.rev[idx]) : -i64(A.fwd[idx]);
+  MB_FN i32 sec_pos(u32 idx) const {
+    return kRevPass ? static_cast<i32>(A.rev[idx]) : -static_cast<i32>(A.fwd[idx]);
   }
   template <bool kRevPass>
-  MB_FN i64 sec_q(u32 idx) const {  // position after the unit's current move
-    return kRevPass ? i64(A.rev[idx]) - i64(A.rm[idx]) : -(i64(A.fwd[idx]) + i64(A.fm[idx]));
+  MB_FN i32 sec_q(u32 idx) const {  // position after the unit's current move
+    return kRevPass ? static_cast<i32>(A.rev[idx]) - static_cast<i32>(A.rm[idx])
+                    : -(static_cast<i32>(A.fwd[idx]) + static_cast<i32>(A.fm[idx]));
   }
 
-  // State of the walk after scan position m: `alive` = the unit at m ends the epoch stalled
-  // (collided before this pass, or stalled by this pass assuming its trial succeeds), v = its
-  // final position. A free unit at m is a candidate when alive(m-1) and q[m] <= v(m-1).
-  // One scan over SecOp elements gives every thread the state at the start of its chunk. The
-  // rev pass (5'->3' over rev ranks) and the fwd pass (3'->5' over fwd ranks) touch disjoint
-  // arrays, so both run through the same steps together; only the draws couple them (the fwd
-  // pass draws after the rev pass), and those are resolved in one walk over the concatenated
-  // candidate list.
+  // The rev pass (5'->3' over rev ranks) and the fwd pass (3'->5' over fwd ranks) touch disjoint
+  // arrays, so both run through the same steps together; only the draws couple them in the
+  // deterministic mode (the fwd pass draws after the rev pass), and those are resolved in one
+  // walk over the concatenated candidate list.
   struct SecDir {
     u32 first, M;
     u32* cand;   // by scan position: the unit is a candidate
@@ -2440,25 +2465,46 @@ struct CellSimT {
       // (a neighbouring walk may be parking a move in the index bits of this word; the event
       // bits read here do not change in this region)
       if (!coll_occurred(MB_SHARED_LOAD_U32(&coll[idx]))) continue;
-      i64 v = sec_q<kRevPass>(idx);
-      for (u32 k = m + 1; k < d.M; ++k) {
-        const u32 ik = sec_idx<kRevPass>(d.first, k);
-        if (coll_occurred(MB_SHARED_LOAD_U32(&coll[ik]))) break;
-        if (sec_q<kRevPass>(ik) > v) break;
-        const i64 p = sec_pos<kRevPass>(ik);
-        const i64 mv = p - v;  // distance to the blocker's site
-        MB_SHARED_STORE_U32(&coll[ik], static_cast<u32>(mv > 0 ? mv - 1 : 0));  // event bits stay 0
-        MB_ATOMIC_OR_U32(&d.cand[k >> 5], 1u << (k & 31));
-        if (k == m + 1) MB_ATOMIC_OR_U32(&d.head1[k >> 5], 1u << (k & 31));
-        if constexpr (kCtr) {
-          if (never) break;
-          if (draws && !bernoulli_raw(raw(ctr_pack(S.epoch, kDrSecondary,
-                                                   ((kRevPass ? 0u : 1u) << 24) | k)),
-                                      1.0 - P.p_bypass))
-            break;
-          MB_ATOMIC_OR_U32(&ok[k >> 5], 1u << (k & 31));
+      i32 v = sec_q<kRevPass>(idx);
+      // The only value carried from one unit of the run to the next is v, so the loads of the
+      // next four units are issued together before they are looked at (a queue behind a barrier
+      // can be dozens of units long, and the longest one sets the pace of this region).
+      bool open_run = true;
+      for (u32 k0 = m + 1; open_run && k0 < d.M; k0 += 4) {
+        u32 ik[4], cw[4];
+        i32 pp[4], qq[4];
+#pragma unroll
+        for (u32 j = 0; j < 4; ++j) ik[j] = k0 + j < d.M ? sec_idx<kRevPass>(d.first, k0 + j) : idx;
+#pragma unroll
+        for (u32 j = 0; j < 4; ++j) {
+          cw[j] = MB_SHARED_LOAD_U32(&coll[ik[j]]);
+          pp[j] = sec_pos<kRevPass>(ik[j]);
+          qq[j] = sec_q<kRevPass>(ik[j]);
         }
-        v = p < v + 1 ? p : v + 1;
+#pragma unroll
+        for (u32 j = 0; j < 4; ++j) {
+          const u32 k = k0 + j;
+          if (k >= d.M || coll_occurred(cw[j]) || qq[j] > v) {
+            open_run = false;
+            break;
+          }
+          const i32 p = pp[j];
+          const i32 mv = p - v;  // distance to the blocker's site
+          MB_SHARED_STORE_U32(&coll[ik[j]], static_cast<u32>(mv > 0 ? mv - 1 : 0));  // event bits stay 0
+          MB_ATOMIC_OR_U32(&d.cand[k >> 5], 1u << (k & 31));
+          if (k == m + 1) MB_ATOMIC_OR_U32(&d.head1[k >> 5], 1u << (k & 31));
+          if constexpr (kCtr) {
+            if (never ||
+                (draws && !bernoulli_raw(raw(ctr_pack(S.epoch, kDrSecondary,
+                                                      ((kRevPass ? 0u : 1u) << 24) | k)),
+                                         1.0 - P.p_bypass))) {
+              open_run = false;
+              break;
+            }
+            MB_ATOMIC_OR_U32(&ok[k >> 5], 1u << (k & 31));
+          }
+          v = p < v + 1 ? p : v + 1;
+        }
       }
     }
   }
@@ -2771,6 +2817,7 @@ struct CellSimT {
   // Simulation::process_collisions (simulation.cpp:763-793)
   MB_FN void process_collisions(bool with_fix) {
     const u32 n = S.num_active;
+    MB_PROBE_BEGIN();
     MB_REGION(cta, tid) {
       for (u32 i = tid; i < n; i += cta.nt()) {
         A.rc[i] = 0;
@@ -2778,11 +2825,14 @@ struct CellSimT {
       }
     }
     cta.sync();
+    MB_PROBE(kPhMvExceptions);
     MB_REGION(cta, tid) {
       if (cta.leader(tid)) detect_boundaries_leader();
     }
     cta.sync();
+    MB_PROBE(kPhSecScan);
     detect_lef_bar_collisions();
+    MB_PROBE(kPhSecDraws);
     lap(kPhLefBar);
     detect_primary_lef_lef_collisions();
     lap(kPhPrimary);
