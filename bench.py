@@ -245,7 +245,7 @@ class DeviceJob:
     (kernels + band memsets + the reduce of every interval whose cells are split over ranks)."""
 
     def __init__(self, torch, dist, engine, cfg, genome, rank, world, local_rank, rng_mode,
-                 slice_all=False):
+                 slice_all=None, tolerance=1.10, pre_split=1):
         from modle_b200 import abi, distributed, host
         from modle_b200.simulation import Simulation
 
@@ -259,7 +259,8 @@ class DeviceJob:
         self.barrier_dt = abi.np_dtypes()[0]
         ivs = self.sim.intervals
         self.shards = distributed.plan_shards(distributed.interval_weights(ivs),
-                                              int(self.p.num_cells), world, slice_all=slice_all)
+                                              int(self.p.num_cells), world, tolerance=tolerance,
+                                              slice_all=slice_all, pre_split=pre_split)
         self.roots = distributed.interval_roots(self.shards)
         self.split = [i for i, (_, ranks) in self.roots.items() if len(ranks) > 1]
         order = sorted(self.shards, key=lambda s: (-s.weight, s.interval, s.cell_lo))
@@ -557,7 +558,9 @@ def run_ours(args, rank, world, local_rank):
     engine = distributed.DeviceEngine(local_rank, num_streams=args.streams, rng_mode=rng_mode)
     ctx = engine.ctx
     job = DeviceJob(torch, dist, engine, cfg, genome, rank, world, local_rank, rng_mode,
-                    slice_all=args.plan == "slices")
+                    slice_all={"auto": None, "slices": True, "whole": False}[args.plan],
+                    tolerance=args.tolerance,
+                    pre_split=args.pre_split)
     sim = job.sim
     main_stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(main_stream)
@@ -574,6 +577,14 @@ def run_ours(args, rank, world, local_rank):
         t = torch.tensor([x], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM)
         return float(t.item())
+
+    def all_gather(x):
+        if world == 1:
+            return [x]
+        t = torch.zeros(world, dtype=torch.float64, device=dev)
+        t[rank] = x
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(v) for v in t.tolist()]
 
     def timed_steps(steps, warmup, events=None):
         for _ in range(warmup):
@@ -609,7 +620,13 @@ def run_ours(args, rank, world, local_rank):
     total_lu = all_reduce(float(lef_updates), "sum")
     total_contacts = all_reduce(float(contacts), "sum")
     value = total_lu * args.steps / (elapsed_ms * 1e-3)
+    rank_ms = all_gather(my_ms / args.steps)       # each rank's own device time per step
+    rank_lu = all_gather(float(lef_updates))       # ... and its share of the work
     launch_ms = [ev0.elapsed_time(ev1) for _, ev0, ev1 in events]
+    per_interval = {}
+    for e, ev0, ev1 in events:
+        key = f"{e['iv'].chrom_name}[{e['cells'][0]}:{e['cells'][1]}]"
+        per_interval.setdefault(key, []).append(ev0.elapsed_time(ev1))
     peak, peak_src = measured_peaks()
     # launches overlap (several streams), so the kernel's rate is taken over the timed region
     achieved = (alg_bytes * args.steps / 1e9) / (my_ms * 1e-3) if my_ms > 0 else 0.0
@@ -625,7 +642,7 @@ def run_ours(args, rank, world, local_rank):
         sum(e["ntasks"] * stats_dt.itemsize for e in job.mine)
 
     def step_e2e():
-        sim.run_simulate(num_workers=args.streams)
+        sim.run_simulate(num_workers=args.e2e_workers)
 
     e2e_steps = max(1, min(args.steps, 2))
     step_e2e()  # warm-up (contexts, staging buffers, page faults)
@@ -684,6 +701,10 @@ def run_ours(args, rank, world, local_rank):
                        "l2_policy": "band matrices + RNG staging of a step exceed the 126 MB L2 "
                                     "for the genome-wide workload; bands are re-zeroed every step",
                        "streams": args.streams,
+                       "rank_ms_per_step": [round(x, 1) for x in rank_ms],
+                       "rank0_launch_ms": {k: round(sum(v) / len(v), 1)
+                                           for k, v in per_interval.items()},
+                       "rank_lef_updates_per_step": rank_lu,
                        "rng_mode": "deterministic (reference draw order, bit-exact)"
                                    if rng_mode == 0 else
                                    "throughput (counter-based draws, statistically equivalent)",
@@ -744,9 +765,16 @@ def main():
     ap.add_argument("--write-c3-golden", action="store_true",
                     help="(1 GPU) run the extra C3 step and write its checksums to "
                          "tests/golden/c3_chr1_8192cells_checksums.json")
-    ap.add_argument("--plan", default="whole", choices=["whole", "slices"],
-                    help="whole: whole intervals per rank, cells split only to balance (default); "
-                         "slices: every interval cut into one cell slice per rank + one reduce each")
+    ap.add_argument("--plan", default="auto", choices=["auto", "whole", "slices"],
+                    help="whole: whole intervals per rank, cells split only to balance; slices: "
+                         "every interval cut into one cell slice per rank + one reduce each; auto "
+                         "(default): slices when a slice still holds >= 222 cells (1.5 waves)")
+    ap.add_argument("--e2e-workers", type=int, default=4,
+                    help="host worker threads (one context each) of the end-to-end run at 1 GPU")
+    ap.add_argument("--tolerance", type=float, default=1.10,
+                    help="planner: split cells while the heaviest rank exceeds this x the mean")
+    ap.add_argument("--pre-split", type=int, default=1,
+                    help="planner: cut every interval into this many cell ranges before dealing")
     ap.add_argument("--streams", type=int, default=3,
                     help="concurrent launches per GPU (streams / host worker threads)")
     args = ap.parse_args()

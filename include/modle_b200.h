@@ -409,8 +409,9 @@ double modle_b200_cell_weight(uint64_t num_lefs, uint64_t num_barriers);
 /* Deals the cells of `num_intervals` intervals (`num_cells` cells each; cell_weights[i] from
  * modle_b200_cell_weight, 0 = interval skipped, e.g. no barriers) to `world_size` ranks: whole
  * intervals heaviest-first; while the heaviest rank carries more than `tolerance` (<= 0: 1.10) x
- * the mean, the heaviest piece of that rank is halved by cells. slice_all != 0: every interval is
- * cut into one cell range per rank instead (one reduce per interval). Shards come out sorted by
+ * the mean, the heaviest piece of that rank is halved by cells. slice_all > 0: every interval is
+ * cut into one cell range per rank instead (one reduce per interval); slice_all < 0: the library
+ * decides (slices when a slice still holds >= 222 cells, i.e. 1.5 waves over the SMs). Shards come out sorted by
  * (interval, cell_lo); the root of an interval is the rank of its first shard. Deterministic:
  * every rank computes the same plan. shards_out == NULL with capacity 0 is a size query. */
 int modle_b200_plan_shards(const double* cell_weights, size_t num_intervals, uint64_t num_cells,

@@ -80,6 +80,11 @@ struct modle_b200_context {
   DevBuf d_phase;  // kNumPhases cycle accumulators
   LaunchSlot slots[kLaunchSlots];
   int next_slot = 0;
+  // High-water sizes of the slot buffers. A slot that has to (re)allocate takes the largest size
+  // any launch of this context has asked for so far, and idle slots are grown along: cudaFree /
+  // cudaMalloc synchronise the device, so after the first (largest-first) launches no launch
+  // should have to allocate again.
+  size_t hw_rings = 0, hw_states = 0, hw_barriers = 0;
   DevBuf d_tasks, d_band, d_occ1d, d_stats, d_missed, d_snap_u64, d_snap_bar, d_log;
   PinnedBuf h_stage;  // band | occ1d | stats | missed of the host-buffer entry point
   DevBuf d_binned, d_tiles;  // binned contact register: pixel indices by tile, counts + cursors

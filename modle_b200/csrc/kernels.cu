@@ -558,11 +558,20 @@ int launch_simulate(modle_b200_context* ctx, const modle_b200_sim_params* params
   cudaGetLastError();  // cudaEventQuery's cudaErrorNotReady is not an error
   // per-interval arrays (pageable host -> device; small)
   const size_t nb = num_barriers;
-  CUDA_TRY(sl->d_bar_pos.reserve(sizeof(u32) * (nb + 1)));
-  CUDA_TRY(sl->d_bar_dir.reserve(sizeof(u32) * hd.bar_dir_rev.size()));
-  CUDA_TRY(sl->d_stp_a.reserve(sizeof(double) * (nb + 1)));
-  CUDA_TRY(sl->d_stp_i.reserve(sizeof(double) * (nb + 1)));
-  CUDA_TRY(sl->d_occ.reserve(sizeof(double) * (nb + 1)));
+  auto reserve_barriers = [&](LaunchSlot& x, size_t n1) -> cudaError_t {
+    cudaError_t e = x.d_bar_pos.reserve(sizeof(u32) * n1);
+    if (e == cudaSuccess) e = x.d_bar_dir.reserve(sizeof(u32) * (n1 / 32 + 2));
+    if (e == cudaSuccess) e = x.d_stp_a.reserve(sizeof(double) * n1);
+    if (e == cudaSuccess) e = x.d_stp_i.reserve(sizeof(double) * n1);
+    if (e == cudaSuccess) e = x.d_occ.reserve(sizeof(double) * n1);
+    return e;
+  };
+  if (nb + 1 > ctx->hw_barriers) {
+    ctx->hw_barriers = nb + 1;
+    for (auto& x : ctx->slots)
+      if (!x.in_flight && &x != sl) CUDA_TRY(reserve_barriers(x, ctx->hw_barriers));
+  }
+  CUDA_TRY(reserve_barriers(*sl, ctx->hw_barriers));
   if (nb) {
     CUDA_TRY(cudaMemcpyAsync(sl->d_bar_pos.p, hd.bar_pos.data(), sizeof(u32) * nb,
                              cudaMemcpyHostToDevice, stream));
@@ -593,10 +602,22 @@ int launch_simulate(modle_b200_context* ctx, const modle_b200_sim_params* params
   const u32 grid = static_cast<u32>(
       std::min<size_t>(num_cells, size_t(per_sm) * static_cast<size_t>(ctx->num_sms)));
   if (!ctr) {  // the throughput mode stages no draws
-    CUDA_TRY(sl->d_rings.reserve(sizeof(u64) * 2 * size_t(sc.window) * grid));
-    CUDA_TRY(sl->d_states.reserve(sizeof(u64) * 4 * size_t(sc.gen_threads) * grid));
+    const size_t rings = sizeof(u64) * 2 * size_t(sc.window) * grid;
+    const size_t states = sizeof(u64) * 4 * size_t(sc.gen_threads) * grid;
+    if (rings > ctx->hw_rings || states > ctx->hw_states) {
+      ctx->hw_rings = std::max(ctx->hw_rings, rings);
+      ctx->hw_states = std::max(ctx->hw_states, states);
+      for (auto& x : ctx->slots) {
+        if (x.in_flight || &x == sl) continue;
+        CUDA_TRY(x.d_rings.reserve(ctx->hw_rings));
+        CUDA_TRY(x.d_states.reserve(ctx->hw_states));
+      }
+    }
+    CUDA_TRY(sl->d_rings.reserve(ctx->hw_rings));
+    CUDA_TRY(sl->d_states.reserve(ctx->hw_states));
   }
-  CUDA_TRY(sl->d_queue.reserve(sizeof(u32) * 4));
+  if (!sl->d_queue.p)
+    for (auto& x : ctx->slots) CUDA_TRY(x.d_queue.reserve(sizeof(u32) * 4));
   CUDA_TRY(cudaMemsetAsync(sl->d_queue.p, 0, sizeof(u32) * 4, stream));
 
   LaunchArgs a;

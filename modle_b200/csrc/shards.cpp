@@ -102,6 +102,14 @@ int modle_b200_plan_shards(const double* cell_weights, size_t num_intervals, uin
   if (!cell_weights || !num_shards_out || world_size < 1)
     return fail(MODLE_B200_ERR_INVALID_ARGUMENT, "NULL argument or world_size < 1");
   if (tolerance <= 0.0) tolerance = 1.10;
+  if (slice_all < 0) {
+    // Automatic: one cell slice of EVERY interval per rank pays when a slice still is a launch of
+    // its own right -- at least ~1.5 waves of cells over the 148 SMs -- because every rank then
+    // runs the same mix and twice as many launches fill each other's tails (measured on B200s,
+    // C2 with 512 cells: 2 ranks 2.13 s per step sliced vs 2.85 s whole; 8 ranks 1.24 s sliced --
+    // 64-cell launches are nothing but tail -- vs 0.72 s whole).
+    slice_all = (world_size > 1 && num_cells / static_cast<uint64_t>(world_size) >= 222) ? 1 : 0;
+  }
   std::vector<Piece> pieces;
   if (slice_all && world_size > 1) {
     for (size_t i = 0; i < num_intervals; ++i) {

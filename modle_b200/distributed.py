@@ -57,7 +57,8 @@ def interval_weights(intervals):
             for iv in intervals]
 
 
-def plan_shards(num_lefs, num_cells, world, tolerance=1.10, slice_all=False):
+def plan_shards(num_lefs, num_cells, world, tolerance=1.10, slice_all=False, pre_split=1):
+    # slice_all: False (whole intervals), True (one slice per rank) or None (the library decides)
     """Deals (interval, cell range) shards to `world` ranks (modle_b200_plan_shards).
 
     num_lefs[i] is the weight of one cell of interval i (0 = interval skipped, e.g. no
@@ -73,13 +74,38 @@ def plan_shards(num_lefs, num_cells, world, tolerance=1.10, slice_all=False):
     same mix of work, which removes both the imbalance between ranks and most of the tail of a
     rank's last launches, at the price of one reduce per interval.
     """
+    if pre_split > 1 and world > 1 and slice_all is False and num_cells >= pre_split:
+        # every interval is first cut into `pre_split` equal cell ranges, which are then dealt out
+        # like intervals of their own (finer grain for the balance, more launches per rank)
+        k = int(pre_split)
+        bounds = [num_cells * j // k for j in range(k + 1)]
+        out = []
+        for j in range(k):
+            sub = plan_shards(num_lefs, bounds[j + 1] - bounds[j], 1, tolerance)
+            out += [Shard(s.interval, s.cell_lo + bounds[j], s.cell_hi + bounds[j], -1, s.weight)
+                    for s in sub]
+        load = [0.0] * world
+        for s in sorted(out, key=lambda s: (-s.weight, s.interval, s.cell_lo)):
+            s.rank = min(range(world), key=lambda r: (load[r], r))
+            load[s.rank] += s.weight
+        out.sort(key=lambda s: (s.interval, s.cell_lo))
+        merged = []  # neighbouring ranges of one interval on one rank run as one launch
+        for s in out:
+            if merged and merged[-1].interval == s.interval and merged[-1].rank == s.rank and \
+                    merged[-1].cell_hi == s.cell_lo:
+                merged[-1].cell_hi = s.cell_hi
+                merged[-1].weight += s.weight
+            else:
+                merged.append(s)
+        return merged
     L = host.lib()
     L.modle_b200_plan_shards.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64, C.c_int, C.c_int,
                                          C.c_double, C.c_void_p, C.c_size_t,
                                          C.POINTER(C.c_size_t)]
     w = np.ascontiguousarray(num_lefs, dtype=np.float64)
     n = C.c_size_t(0)
-    args = (w.ctypes.data, len(w), int(num_cells), int(world), int(bool(slice_all)), float(tolerance))
+    args = (w.ctypes.data, len(w), int(num_cells), int(world),
+            -1 if slice_all is None else int(bool(slice_all)), float(tolerance))
     host.check(L.modle_b200_plan_shards(*args, None, 0, C.byref(n)))
     out = np.zeros(n.value, dtype=abi.shard_dtype())
     if n.value:
@@ -231,7 +257,8 @@ def run_sharded(engine, params, intervals, rank=0, world=1, dist=None, shards=No
     launches, its device->host copy behind its reduce (or launches), both on their own streams.
     """
     if shards is None:
-        shards = plan_shards(interval_weights(intervals), int(params.num_cells), world)
+        shards = plan_shards(interval_weights(intervals), int(params.num_cells), world,
+                             slice_all=None)
     roots = interval_roots(shards)
     _, _, stats_dt = abi.np_dtypes()
     out = {}

@@ -274,7 +274,8 @@ class Simulation:
     rank: int = 0
     world_size: int = 1
     rng_mode: int = RNG_REFERENCE_ORDER  # RNG_COUNTER selects the throughput mode
-    slice_all: bool = False  # multi-GPU plan: one cell slice of EVERY interval per rank
+    slice_all: object = None  # multi-GPU plan: True = one cell slice of EVERY interval per rank,
+    #                           False = whole intervals, None = the library decides
     intervals: list = field(default_factory=list)
     _ctxs: list = field(default_factory=list, repr=False)
     _engine: object = field(default=None, repr=False)
