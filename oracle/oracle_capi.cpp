@@ -391,6 +391,16 @@ int oracle_simulate_genome(const modle_b200_sim_params* params, std::size_t num_
   return 0;
 }
 
+// Counters of burnin_margin_note (oracle_sim.hpp): out = {comparisons, within 64 ulp, smallest
+// relative gap as double bits}; reset != 0 clears them afterwards.
+void oracle_burnin_margin(u64* out, int reset) {
+  BurninMargin& m = burnin_margin();
+  out[0] = __atomic_load_n(&m.comparisons, __ATOMIC_RELAXED);
+  out[1] = __atomic_load_n(&m.within_64_ulp, __ATOMIC_RELAXED);
+  out[2] = __atomic_load_n(&m.min_gap_bits, __ATOMIC_RELAXED);
+  if (reset) m = BurninMargin{};
+}
+
 // Runs one cell for params->debug_max_epochs epochs and dumps its state.
 int oracle_snapshot_cell(const modle_b200_sim_params* params, const modle_b200_interval* interval,
                          const modle_b200_barrier* barriers, std::size_t num_barriers,

@@ -6,6 +6,7 @@
 #pragma once
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <cstdint>
 #include <deque>
 #include <limits>
@@ -540,6 +541,35 @@ inline std::pair<u64, u64> process_collisions(CollisionCtx& c, bool with_fix = t
 // Contact sink: banded u32 matrix + missed updates + 1D occupancy
 // (contact_matrix_dense_safe_impl.hpp:54-68; register_contacts.cpp:199-232)
 // ------------------------------------------------------------------------------------------
+// Measurement aid for ONE question (tests/test_burnin_margin.py): how close do the window-mean
+// comparisons of evaluate_burnin come to a tie? The CUDA kernel sums the squared deviations behind
+// the coefficient of variation in a tree order, the reference (and this oracle) left to right, so
+// a comparison can only come out differently when the two means are within a few ulp of each
+// other. Counters are process-wide relaxed atomics: comparisons seen, comparisons within 64 ulp,
+// and the smallest relative gap (as the bit pattern of a double).
+struct BurninMargin {
+  u64 comparisons = 0, within_64_ulp = 0, min_gap_bits = 0x7FF0000000000000ull;
+};
+inline BurninMargin& burnin_margin() {
+  static BurninMargin m;
+  return m;
+}
+inline void burnin_margin_note(double n1, double n2) {
+  BurninMargin& m = burnin_margin();
+  __atomic_fetch_add(&m.comparisons, u64(1), __ATOMIC_RELAXED);
+  const double big = std::fabs(n1) > std::fabs(n2) ? std::fabs(n1) : std::fabs(n2);
+  if (!(big > 0.0)) return;
+  const double gap = std::fabs(n1 - n2) / big;
+  if (gap <= 64 * 2.220446049250313e-16) __atomic_fetch_add(&m.within_64_ulp, u64(1), __ATOMIC_RELAXED);
+  u64 bits;
+  std::memcpy(&bits, &gap, 8);
+  u64 cur = __atomic_load_n(&m.min_gap_bits, __ATOMIC_RELAXED);
+  while (bits < cur &&
+         !__atomic_compare_exchange_n(&m.min_gap_bits, &cur, bits, true, __ATOMIC_RELAXED,
+                                      __ATOMIC_RELAXED)) {
+  }
+}
+
 struct ContactSink {
   u32* band = nullptr;  // nrows*ncols (+1 slack in the reference layout)
   u64* occ1d = nullptr;
@@ -760,6 +790,7 @@ class CellSim {
         const double n1 = a1 / static_cast<double>(w);
         const double n2 = a2 / static_cast<double>(w);
         n += static_cast<std::size_t>(n1 > n2);
+        if (&b == &s.cv_buff) burnin_margin_note(n1, n2);
       }
       const double r = static_cast<double>(n) / static_cast<double>(cap - w - n);
       return r >= 0.95 && r <= 1.05;

@@ -280,6 +280,19 @@ def simulate_genome(params, jobs, nthreads=1):
     return [(bands[i], occs[i], stats[i], int(missed[i])) for i in range(n)]
 
 
+def burnin_margin(reset=True):
+    """Counters of the oracle's burn-in comparisons since the last reset: (comparisons of two
+    window means of the coefficient of variation, those within 64 ulp of a tie, the smallest
+    relative gap). See oracle_sim.hpp burnin_margin_note."""
+    out = (C.c_uint64 * 3)()
+    L = lib()
+    L.oracle_burnin_margin.argtypes = [C.POINTER(C.c_uint64), C.c_int]
+    L.oracle_burnin_margin.restype = None
+    L.oracle_burnin_margin(out, 1 if reset else 0)
+    gap = np.array([out[2]], dtype=np.uint64).view(np.float64)[0]
+    return int(out[0]), int(out[1]), float(gap)
+
+
 def band_to_pixels(band, nrows, ncols, bin_offset=0):
     """CPU counterpart of modle_b200_band_to_pixels (the reference's .cool pixel loop)."""
     band = np.ascontiguousarray(band, dtype=np.uint32)

@@ -313,3 +313,27 @@ def test_results_are_pinned_by_the_golden_digests(throughput, virtual_threads):
     with open(os.path.join(gold_dir, "throughput_mode_digests.json")) as f:
         gold = json.load(f)
     assert mk.compute(virtual_threads) == gold
+
+
+def test_c1_scale_statistical_gate_on_the_emulation(throughput):
+    """The throughput mode at the size of BASELINE C1 (512 cells, 7.73 M contacts) through the
+    emulation of the kernel source -- what the device produces bit for bit
+    (tests/test_zz_gpu_throughput_mode.py) -- against the oracle under three other seeds."""
+    from stats_eval import c1_inputs, c1_scale_gate
+
+    runs, (nrows, ncols) = c1_inputs()
+    p, iv, bars, tasks = runs[1]
+
+    def chunk(lo):
+        emu_lib.set_rng_mode(1)  # (the mode is per thread)
+        return emu_lib.simulate_interval(p, iv, bars, tasks[lo:lo + 32], virtual_threads=64)
+
+    with ThreadPoolExecutor(8) as ex:
+        parts = list(ex.map(chunk, range(0, 512, 32)))
+    band = sum(x[0].astype(np.uint64) for x in parts).astype(np.uint32)
+    occ = sum(x[1] for x in parts)
+    stats = np.concatenate([x[2] for x in parts])
+    assert stats["device_fault"].max() == 0
+    assert int(band.astype(np.uint64).sum()) + sum(x[3] for x in parts) == 600 * 12889
+    ora = {s: pyoracle.simulate_interval(*runs[s], nthreads=8) for s in (2, 3, 4)}
+    c1_scale_gate((band, occ, stats), ora, nrows, ncols)

@@ -123,3 +123,16 @@ def test_c1_size_properties(thr_ctx):
     assert np.array_equal(band, a[0]) and np.array_equal(occ, a[1]) and m1 + m2 == a[3]
     assert np.array_equal(np.concatenate([s1, s2])["num_epochs"], a[2]["num_epochs"])
     sim.close()
+
+
+def test_c1_scale_statistical_gate(thr_ctx):
+    """Throughput mode on the device vs the oracle with other seeds at the size of BASELINE C1;
+    tolerances and their calibration: stats_eval.c1_scale_gate."""
+    from stats_eval import c1_inputs, c1_scale_gate
+
+    runs, (nrows, ncols) = c1_inputs()
+    gpu = thr_ctx.simulate_interval(*runs[1])
+    assert gpu[2]["device_fault"].max() == 0
+    assert int(gpu[0].astype(np.uint64).sum()) + gpu[3] == 600 * 12889
+    ora = {s: pyoracle.simulate_interval(*runs[s], nthreads=16) for s in (2, 3, 4)}
+    c1_scale_gate((gpu[0], gpu[1], gpu[2]), ora, nrows, ncols)
