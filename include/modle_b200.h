@@ -255,6 +255,13 @@ int modle_b200_simulate_interval(modle_b200_context* ctx, const modle_b200_sim_p
                                  uint32_t* band_out, uint64_t* occ1d_out,
                                  modle_b200_cell_stats* stats_out, uint64_t* missed_updates_out);
 
+/* Optional: sizes the context's device and pinned staging buffers once for the largest interval
+ * the caller will pass to the host-buffer entry points (band of max_nrows x max_ncols, max_cells
+ * cells) -- what Simulation::State::resize_buffers (simulation.cpp:603-627) does for a reference
+ * worker. Without it the buffers grow on demand, at the price of device-wide synchronisations. */
+int modle_b200_reserve(modle_b200_context* ctx, uint64_t max_nrows, uint64_t max_ncols,
+                       size_t max_cells);
+
 /* Same, with every buffer already resident in device memory (d_* are device pointers in the
  * context's device; cuda_stream is a cudaStream_t or NULL for the context's own stream). The call
  * is asynchronous; d_missed_updates (1 uint64) and d_stats accumulate on the device.            */

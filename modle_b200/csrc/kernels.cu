@@ -766,6 +766,29 @@ static int simulate_interval_host(modle_b200_context* ctx, const modle_b200_sim_
   return MODLE_B200_OK;
 }
 
+// Sizes the buffers behind the host-buffer entry points once, for the largest interval the caller
+// is going to pass (the reference sizes each worker's State the same way, up front:
+// Simulation::State::resize_buffers, src/libmodle/cpu/simulation.cpp:603-627). Optional -- the
+// buffers also grow on demand -- but growing means cudaFree / cudaFreeHost, which synchronise the
+// whole device and stall the launches of the other worker contexts.
+int modle_b200_reserve(modle_b200_context* ctx, uint64_t max_nrows, uint64_t max_ncols,
+                       size_t max_cells) {
+  if (!ctx) return fail(MODLE_B200_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  const size_t npx = max_nrows * max_ncols + 1;
+  const size_t cells = std::max<size_t>(max_cells, 1);
+  CUDA_TRY(ctx->d_tasks.reserve(sizeof(modle_b200_cell_task) * cells));
+  CUDA_TRY(ctx->d_band.reserve(sizeof(u32) * npx));
+  CUDA_TRY(ctx->d_occ1d.reserve(sizeof(u64) * std::max<u64>(max_ncols, 1)));
+  CUDA_TRY(ctx->d_stats.reserve(sizeof(modle_b200_cell_stats) * cells));
+  CUDA_TRY(ctx->d_missed.reserve(sizeof(u64)));
+  const size_t off_occ = ((sizeof(u32) * npx + 63) / 64) * 64;
+  const size_t off_stats = off_occ + ((sizeof(u64) * max_ncols + 63) / 64) * 64;
+  const size_t off_missed = off_stats + ((sizeof(modle_b200_cell_stats) * cells + 63) / 64) * 64;
+  CUDA_TRY(ctx->h_stage.reserve(off_missed + 64));
+  return MODLE_B200_OK;
+}
+
 int modle_b200_simulate_interval(modle_b200_context* ctx, const modle_b200_sim_params* params,
                                  const modle_b200_interval* interval,
                                  const modle_b200_barrier* barriers, size_t num_barriers,

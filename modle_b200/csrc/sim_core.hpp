@@ -249,6 +249,37 @@ struct CellSimT {
     return Cursor{this, c, c + kCtrDrawsPerItem, false};
   }
 
+  // Generator sub-stream gi writes its l draws of the window that starts at stream offset wbase
+  // and hops to its block of the next window.
+  MB_FN void rng_generate_block(u32 gi, u64 wbase) const {
+    const u32 G = P.rng_gen_threads;
+    Xs g{A.rng_state[gi], A.rng_state[G + gi], A.rng_state[2 * G + gi], A.rng_state[3 * G + gi]};
+    const Xs nxt = xs_jump(g, D.jump_tbl);
+    const u64 mask = 2 * u64(P.rng_window) - 1;
+    const u64 o0 = wbase + u64(gi) * P.rng_per_thread;
+    for (u32 i = 0; i < P.rng_per_thread; i += 4) {  // one full 32-byte sector per store
+      const u64 a = xs_next(g);
+      const u64 b = xs_next(g);
+      const u64 c = xs_next(g);
+      const u64 e = xs_next(g);
+      u64* dst = A.rng_ring + ((o0 + i) & mask);
+#if MB_DEVICE_BUILD
+      asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "l"(a), "l"(b), "l"(c),
+                   "l"(e)
+                   : "memory");
+#else
+      dst[0] = a;
+      dst[1] = b;
+      dst[2] = c;
+      dst[3] = e;
+#endif
+    }
+    A.rng_state[gi] = nxt.s0;
+    A.rng_state[G + gi] = nxt.s1;
+    A.rng_state[2 * G + gi] = nxt.s2;
+    A.rng_state[3 * G + gi] = nxt.s3;
+  }
+
   // ------------------------------------------------------------------------------ RNG staging
   // Makes raw(o) valid for every o in [S.rng_pos, need_end). The stream is produced window by
   // window (W draws): generator thread g owns the l consecutive draws [g*l, (g+1)*l) of each
@@ -274,34 +305,8 @@ struct CellSimT {
       cta.sync();
       MB_REGION(cta, tid) {
         const u32 G = P.rng_gen_threads;
-        for (u32 gi = static_cast<u32>(tid); gi < G; gi += static_cast<u32>(cta.nt())) {
-          Xs g{A.rng_state[gi], A.rng_state[G + gi], A.rng_state[2 * G + gi],
-               A.rng_state[3 * G + gi]};
-          const Xs nxt = xs_jump(g, D.jump_tbl);
-          const u64 mask = 2 * u64(P.rng_window) - 1;
-          const u64 o0 = wbase + u64(gi) * P.rng_per_thread;
-          for (u32 i = 0; i < P.rng_per_thread; i += 4) {  // one full 32-byte sector per store
-            const u64 a = xs_next(g);
-            const u64 b = xs_next(g);
-            const u64 c = xs_next(g);
-            const u64 e = xs_next(g);
-            u64* dst = A.rng_ring + ((o0 + i) & mask);
-#if MB_DEVICE_BUILD
-            asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "l"(a), "l"(b),
-                         "l"(c), "l"(e)
-                         : "memory");
-#else
-            dst[0] = a;
-            dst[1] = b;
-            dst[2] = c;
-            dst[3] = e;
-#endif
-          }
-          A.rng_state[gi] = nxt.s0;
-          A.rng_state[G + gi] = nxt.s1;
-          A.rng_state[2 * G + gi] = nxt.s2;
-          A.rng_state[3 * G + gi] = nxt.s3;
-        }
+        for (u32 gi = static_cast<u32>(tid); gi < G; gi += static_cast<u32>(cta.nt()))
+          rng_generate_block(gi, wbase);
         if (cta.leader(tid)) S.rng_generated = wbase + P.rng_window;
       }
       cta.sync();
@@ -2644,6 +2649,8 @@ struct CellSimT {
     const u32 npot = npot_r + static_cast<u32>(tot >> 32);
     sub_lap(kPhSecClassify);
     if (npot == 0) return;
+    u64 pregen_base = 0;
+    bool pregen = false;
     if (draws) {
       rng_ensure(S.rng_pos + npot);
       MB_REGION(cta, tid) {
@@ -2656,6 +2663,13 @@ struct CellSimT {
       }
       cta.sync();
       sub_lap(kPhSecDraws);
+      // While warp 0 walks the candidates below, the generator threads would idle at the barrier:
+      // they stage the NEXT window of the cell's stream instead, whenever the ring has room for
+      // it (the window it overwrites lies wholly behind the stream position; the draws of this
+      // pass have been read already). The stream is sequential, so a window staged early is never
+      // wasted; S.rng_generated moves in the region after the next barrier.
+      pregen_base = S.rng_generated;
+      pregen = pregen_base <= S.rng_pos + P.rng_window;
       // Walk the candidates in order (all rev candidates, then all fwd candidates; the first
       // fwd candidate always starts a run). A candidate is reached when it is the first of its
       // run or the previous one was reached and its trial succeeded; only reached candidates
@@ -2696,9 +2710,17 @@ struct CellSimT {
           alive_in = ((Rm & ~bad) >> 31) & 1u;
         }
         if (lane == 0) S.tmp_u32[4] = d;
+      } else if (pregen) {
+        for (u32 gi = threadIdx.x - 32; gi < P.rng_gen_threads; gi += blockDim.x - 32)
+          rng_generate_block(gi, pregen_base);
       }
 #else
       MB_REGION(cta, tid) {
+        if (pregen) {
+          for (u32 gi = static_cast<u32>(tid); gi < P.rng_gen_threads;
+               gi += static_cast<u32>(cta.nt()))
+            rng_generate_block(gi, pregen_base);
+        }
         if (!cta.leader(tid)) continue;
         u32 d = 0, alive = 0;
         for (u32 w = 0; w < ncw; ++w) {
@@ -2726,7 +2748,10 @@ struct CellSimT {
       sec_apply<true>(R, tid, static_cast<u32>(cnt[tid] & 0xFFFFFFFFu), mode, bits_reached, bits_ok);
       sec_apply<false>(F, tid, npot_r + static_cast<u32>(cnt[tid] >> 32), mode, bits_reached,
                        bits_ok);
-      if (draws && cta.leader(tid)) S.rng_pos += S.tmp_u32[4];
+      if (draws && cta.leader(tid)) {
+        S.rng_pos += S.tmp_u32[4];
+        if (pregen) S.rng_generated = pregen_base + P.rng_window;
+      }
     }
     cta.sync();
     sub_lap(kPhSecApply);

@@ -126,6 +126,11 @@ class Context:
     def synchronize(self):
         host.check(host.lib().modle_b200_synchronize(self._h))
 
+    def reserve(self, max_nrows, max_ncols, max_cells):
+        """Sizes the buffers of the host-buffer calls once for the largest interval to come."""
+        host.check(host.lib().modle_b200_reserve(self._h, int(max_nrows), int(max_ncols),
+                                                 int(max_cells)))
+
     def phase_cycles(self, reset=True):
         """{phase name: SM-clock cycles} summed over the cells simulated since the last reset."""
         out = (C.c_uint64 * len(host.PHASE_NAMES))()
@@ -320,13 +325,16 @@ class Simulation:
             iv.contacts, iv.lef_1d_occupancy, iv.stats, iv.missed_updates = \
                 c.simulate_interval(p, iv.abi_interval(), iv.barriers, tasks)
 
-        if ctx is not None:
+        if ctx is not None or not todo:
             for idx in todo:
                 one(ctx, idx)
             return self.intervals
         nw = max(1, min(num_workers, len(todo)))
         while len(self._ctxs) < nw:  # contexts (streams, device buffers) persist across calls
-            self._ctxs.append(Context(self.device, self.rng_mode))
+            c = Context(self.device, self.rng_mode)
+            big = max((self.intervals[i] for i in todo), key=lambda iv: iv.nrows * iv.ncols)
+            c.reserve(big.nrows, big.ncols, int(p.num_cells))  # any worker may get the largest
+            self._ctxs.append(c)
         if nw == 1:
             for idx in todo:
                 one(self._ctxs[0], idx)
