@@ -769,7 +769,7 @@ def main():
                     help="whole: whole intervals per rank, cells split only to balance; slices: "
                          "every interval cut into one cell slice per rank + one reduce each; auto "
                          "(default): slices when a slice still holds >= 222 cells (1.5 waves)")
-    ap.add_argument("--e2e-workers", type=int, default=4,
+    ap.add_argument("--e2e-workers", type=int, default=6,
                     help="host worker threads (one context each) of the end-to-end run at 1 GPU")
     ap.add_argument("--tolerance", type=float, default=1.10,
                     help="planner: split cells while the heaviest rank exceeds this x the mean")

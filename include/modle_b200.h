@@ -255,6 +255,19 @@ int modle_b200_simulate_interval(modle_b200_context* ctx, const modle_b200_sim_p
                                  uint32_t* band_out, uint64_t* occ1d_out,
                                  modle_b200_cell_stats* stats_out, uint64_t* missed_updates_out);
 
+/* Same call, but band_out / occ1d_out / *missed_updates_out are OVERWRITTEN with this call's
+ * results instead of added to: for the usual case of one call per interval (all its cells at
+ * once) the caller then neither has to zero 4 x nrows x ncols bytes nor pay a read-modify-write
+ * pass over them. */
+int modle_b200_simulate_interval_overwrite(modle_b200_context* ctx,
+                                           const modle_b200_sim_params* params,
+                                           const modle_b200_interval* interval,
+                                           const modle_b200_barrier* barriers, size_t num_barriers,
+                                           const modle_b200_cell_task* tasks, size_t num_cells,
+                                           uint32_t* band_out, uint64_t* occ1d_out,
+                                           modle_b200_cell_stats* stats_out,
+                                           uint64_t* missed_updates_out);
+
 /* Optional: sizes the context's device and pinned staging buffers once for the largest interval
  * the caller will pass to the host-buffer entry points (band of max_nrows x max_ncols, max_cells
  * cells) -- what Simulation::State::resize_buffers (simulation.cpp:603-627) does for a reference

@@ -508,6 +508,21 @@ void add_into_u32(u32* dst, const u32* src, size_t n) {
   for (auto& th : pool) th.join();
 }
 
+void copy_into_u32(u32* dst, const u32* src, size_t n) {
+  const size_t kMinPerThread = size_t(1) << 22;
+  unsigned nt = std::max(1u, std::min(4u, std::thread::hardware_concurrency()));
+  nt = static_cast<unsigned>(std::min<size_t>(nt, std::max<size_t>(1, n / kMinPerThread)));
+  auto work = [=](size_t lo, size_t hi) { std::memcpy(dst + lo, src + lo, sizeof(u32) * (hi - lo)); };
+  if (nt <= 1) {
+    work(0, n);
+    return;
+  }
+  std::vector<std::thread> pool;
+  for (unsigned t = 1; t < nt; ++t) pool.emplace_back(work, n * t / nt, n * (t + 1) / nt);
+  work(0, n / nt);
+  for (auto& th : pool) th.join();
+}
+
 // Shared implementation of the two simulate entry points. All pointers are device pointers.
 int launch_simulate(modle_b200_context* ctx, const modle_b200_sim_params* params,
                     const modle_b200_interval* interval, const modle_b200_barrier* h_barriers,
@@ -694,7 +709,8 @@ static int simulate_interval_host(modle_b200_context* ctx, const modle_b200_sim_
                                   const modle_b200_cell_task* tasks, size_t num_cells,
                                   uint32_t* band_out, uint64_t* occ1d_out,
                                   modle_b200_cell_stats* stats_out, uint64_t* missed_updates_out,
-                                  modle_b200_epoch_record* log_out, size_t log_cap) {
+                                  modle_b200_epoch_record* log_out, size_t log_cap,
+                                  bool overwrite = false) {
   if (!ctx || !params || !interval || !tasks || !band_out)
     return fail(MODLE_B200_ERR_INVALID_ARGUMENT, "NULL argument");
   if (log_cap != 0 && !log_out) return fail(MODLE_B200_ERR_INVALID_ARGUMENT, "log_out is NULL");
@@ -751,10 +767,16 @@ static int simulate_interval_host(modle_b200_context* ctx, const modle_b200_sim_
                            sizeof(modle_b200_cell_stats) * num_cells, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaMemcpyAsync(hs + off_missed, ctx->d_missed.p, sizeof(u64), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
-  add_into_u32(band_out, h_band, npx);
-  if (occ1d_out)
-    for (size_t i = 0; i < ncols; ++i) occ1d_out[i] += h_occ[i];
-  if (missed_updates_out) *missed_updates_out += *h_missed;
+  if (overwrite) {  // the caller's buffers need not be zeroed (or even touched) beforehand
+    copy_into_u32(band_out, h_band, npx);
+    if (occ1d_out) std::memcpy(occ1d_out, h_occ, sizeof(u64) * ncols);
+    if (missed_updates_out) *missed_updates_out = *h_missed;
+  } else {
+    add_into_u32(band_out, h_band, npx);
+    if (occ1d_out)
+      for (size_t i = 0; i < ncols; ++i) occ1d_out[i] += h_occ[i];
+    if (missed_updates_out) *missed_updates_out += *h_missed;
+  }
   u64 first_fault = 0;
   for (size_t i = 0; i < num_cells; ++i) {
     if (stats_out) stats_out[i] = h_stats[i];
@@ -797,6 +819,19 @@ int modle_b200_simulate_interval(modle_b200_context* ctx, const modle_b200_sim_p
                                  modle_b200_cell_stats* stats_out, uint64_t* missed_updates_out) {
   return simulate_interval_host(ctx, params, interval, barriers, num_barriers, tasks, num_cells,
                                 band_out, occ1d_out, stats_out, missed_updates_out, nullptr, 0);
+}
+
+int modle_b200_simulate_interval_overwrite(modle_b200_context* ctx,
+                                           const modle_b200_sim_params* params,
+                                           const modle_b200_interval* interval,
+                                           const modle_b200_barrier* barriers, size_t num_barriers,
+                                           const modle_b200_cell_task* tasks, size_t num_cells,
+                                           uint32_t* band_out, uint64_t* occ1d_out,
+                                           modle_b200_cell_stats* stats_out,
+                                           uint64_t* missed_updates_out) {
+  return simulate_interval_host(ctx, params, interval, barriers, num_barriers, tasks, num_cells,
+                                band_out, occ1d_out, stats_out, missed_updates_out, nullptr, 0,
+                                /*overwrite=*/true);
 }
 
 int modle_b200_simulate_interval_logged(modle_b200_context* ctx,

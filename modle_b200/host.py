@@ -69,6 +69,7 @@ def lib():
         L.modle_b200_simulate_interval.argtypes = [
             C.c_void_p, P, C.POINTER(abi.Interval), C.c_void_p, C.c_size_t, C.c_void_p,
             C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, u64p]
+        L.modle_b200_simulate_interval_overwrite.argtypes = L.modle_b200_simulate_interval.argtypes
         L.modle_b200_simulate_interval_logged.argtypes = [
             C.c_void_p, P, C.POINTER(abi.Interval), C.c_void_p, C.c_size_t, C.c_void_p,
             C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, u64p, C.c_void_p, C.c_size_t]
@@ -120,7 +121,8 @@ EXPORTED_SYMBOLS = [
     "modle_b200_stp_active_from_occupancy", "modle_b200_occupancy_from_stp",
     "modle_b200_make_cell_tasks", "modle_b200_init", "modle_b200_destroy",
     "modle_b200_set_rng_mode", "modle_b200_get_rng_mode", "modle_b200_launch_geometry",
-    "modle_b200_reserve", "modle_b200_simulate_interval", "modle_b200_simulate_interval_logged",
+    "modle_b200_reserve", "modle_b200_simulate_interval", "modle_b200_simulate_interval_overwrite",
+    "modle_b200_simulate_interval_logged",
     "modle_b200_simulate_interval_device",
     "modle_b200_synchronize", "modle_b200_snapshot_cell", "modle_b200_register_contacts_device",
     "modle_b200_kernel_launches", "modle_b200_phase_cycles", "modle_b200_calibrate_red_device",

@@ -148,10 +148,13 @@ class Context:
         simulation.cpp:995-1056) is returned as a fifth element: records[cell][epoch]."""
         _, _, stats_dt = abi.np_dtypes()
         nrows, ncols = host.band_shape(params, int(interval.end - interval.start))
+        # no buffers given: the results are written into fresh ones (overwrite entry point, no
+        # zeroing and no add pass); buffers given: the results are ADDED to them
+        fresh = band is None and occ1d is None and not log_capacity_per_cell
         if band is None:
-            band = np.zeros(nrows * ncols + 1, dtype=np.uint32)
+            band = (np.empty if fresh else np.zeros)(nrows * ncols + 1, dtype=np.uint32)
         if occ1d is None:
-            occ1d = np.zeros(ncols, dtype=np.uint64)
+            occ1d = (np.empty if fresh else np.zeros)(ncols, dtype=np.uint64)
         stats = np.zeros(len(tasks), dtype=stats_dt)
         missed = C.c_uint64(0)
         barriers = np.ascontiguousarray(barriers)
@@ -165,10 +168,11 @@ class Context:
                 C.byref(missed), log.ctypes.data, int(log_capacity_per_cell))
             host.check(rc)
             return band, occ1d, stats, int(missed.value), log
-        rc = host.lib().modle_b200_simulate_interval(
-            self._h, C.byref(params), C.byref(interval),
-            barriers.ctypes.data if len(barriers) else None, len(barriers), tasks.ctypes.data,
-            len(tasks), band.ctypes.data, occ1d.ctypes.data, stats.ctypes.data, C.byref(missed))
+        fn = host.lib().modle_b200_simulate_interval_overwrite if fresh else \
+            host.lib().modle_b200_simulate_interval
+        rc = fn(self._h, C.byref(params), C.byref(interval),
+                barriers.ctypes.data if len(barriers) else None, len(barriers), tasks.ctypes.data,
+                len(tasks), band.ctypes.data, occ1d.ctypes.data, stats.ctypes.data, C.byref(missed))
         host.check(rc)
         return band, occ1d, stats, int(missed.value)
 

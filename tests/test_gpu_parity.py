@@ -117,6 +117,28 @@ def test_results_accumulate_into_caller_buffers(gpu_ctx):
     assert np.array_equal(band2, 2 * band) and np.array_equal(occ2, 2 * occ)
 
 
+def test_overwrite_entry_point_ignores_what_the_buffers_held(gpu_ctx):
+    """modle_b200_simulate_interval_overwrite: same results as the accumulating call into zeroed
+    buffers, whatever the caller's buffers held before."""
+    from modle_b200 import abi, host
+
+    p, iv, bars, tasks = make_case(size=3_000_000, ncells=4, target_contact_density=0.01)
+    nrows, ncols = host.band_shape(p, 3_000_000)
+    band0 = np.zeros(nrows * ncols + 1, dtype=np.uint32)
+    occ0 = np.zeros(ncols, dtype=np.uint64)
+    ref = gpu_ctx.simulate_interval(p, iv, bars, tasks, band=band0, occ1d=occ0)  # accumulating call
+    band = np.full(nrows * ncols + 1, 0xDEADBEEF, dtype=np.uint32)
+    occ = np.full(ncols, 12345678901234, dtype=np.uint64)
+    _, _, stats_dt = abi.np_dtypes()
+    stats = np.zeros(len(tasks), dtype=stats_dt)
+    missed = C.c_uint64(777)
+    host.check(host.lib().modle_b200_simulate_interval_overwrite(
+        gpu_ctx.handle, C.byref(p), C.byref(iv), bars.ctypes.data, len(bars), tasks.ctypes.data,
+        len(tasks), band.ctypes.data, occ.ctypes.data, stats.ctypes.data, C.byref(missed)))
+    assert results_equal(ref, (band, occ, stats, int(missed.value))) == []
+    assert results_equal(ref, gpu_ctx.simulate_interval(p, iv, bars, tasks)) == []  # fresh buffers
+
+
 def test_register_contacts_kernel(gpu_ctx):
     import torch
 
