@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks)
   extern __shared__ __align__(16) unsigned char smem[];
   CellShared& S = *reinterpret_cast<CellShared*>(smem);
   CellArrays A = carve_cell_arrays(smem + ((sizeof(CellShared) + 15) / 16) * 16, a.kp.n_lefs,
-                                   a.kp.n_bar);
+                                   a.kp.n_bar, a.kp.lut_entries);
   A.rng_ring = a.ring_pool + size_t(blockIdx.x) * 2 * a.kp.rng_window;
   A.rng_state = a.state_pool + size_t(blockIdx.x) * 4 * a.kp.rng_gen_threads;
   __shared__ u32 s_cell;
@@ -534,11 +534,15 @@ int launch_simulate(modle_b200_context* ctx, const modle_b200_sim_params* params
       pick_staging(static_cast<u32>(interval->num_lefs), static_cast<u32>(num_barriers));
   KernelParams kp;
   IntervalHostData hd;
-  const std::string err =
-      prepare_interval(*params, *interval, h_barriers, num_barriers, sc, &kp, &hd);
+  // shared memory a CTA of this launch class may use: what leaves room for 3 / 2 CTAs per SM,
+  // or everything the device offers
+  const size_t class_limit = sc.cells_per_sm == 3 ? size_t(75) * 1024
+                             : sc.cells_per_sm == 2 ? size_t(113) * 1024 : ctx->max_smem_optin;
+  const std::string err = prepare_interval(*params, *interval, h_barriers, num_barriers, sc, &kp,
+                                           &hd, std::min(class_limit, ctx->max_smem_optin));
   if (!err.empty()) return fail(MODLE_B200_ERR_UNSUPPORTED, err);
-  const size_t smem =
-      ((sizeof(CellShared) + 15) / 16) * 16 + cell_array_bytes(kp.n_lefs, kp.n_bar);
+  const size_t smem = ((sizeof(CellShared) + 15) / 16) * 16 +
+                      cell_array_bytes(kp.n_lefs, kp.n_bar, kp.lut_entries);
   if (smem > ctx->max_smem_optin)
     return fail(MODLE_B200_ERR_UNSUPPORTED,
                 "interval needs " + std::to_string(smem) +
@@ -767,7 +771,13 @@ static int simulate_interval_host(modle_b200_context* ctx, const modle_b200_sim_
                            sizeof(modle_b200_cell_stats) * num_cells, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaMemcpyAsync(hs + off_missed, ctx->d_missed.p, sizeof(u64), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
-  if (overwrite) {  // the caller's buffers need not be zeroed (or even touched) beforehand
+  static const bool skip_copy_out = [] {  // MODLE_B200_E2E_SKIP_COPY=1: measurement knob only
+    const char* e = std::getenv("MODLE_B200_E2E_SKIP_COPY");
+    return e && e[0] == '1';
+  }();
+  if (skip_copy_out) {
+    // (diagnostic: how much of an end-to-end step is the host-side copy into the caller's arrays)
+  } else if (overwrite) {  // the caller's buffers need not be zeroed (or even touched) beforehand
     copy_into_u32(band_out, h_band, npx);
     if (occ1d_out) std::memcpy(occ1d_out, h_occ, sizeof(u64) * ncols);
     if (missed_updates_out) *missed_updates_out = *h_missed;

@@ -112,7 +112,7 @@ struct IntervalHostData {
 inline std::string prepare_interval(const modle_b200_sim_params& p, const modle_b200_interval& iv,
                                     const modle_b200_barrier* bars, size_t nb,
                                     const StagingConfig& sc, KernelParams* kp,
-                                    IntervalHostData* hd) {
+                                    IntervalHostData* hd, size_t smem_limit = 0) {
   if (iv.end <= iv.start) return "empty interval";
   if (iv.end >= 0xFFFFFFF0ull) return "interval end does not fit 32-bit device coordinates";
   if (iv.num_lefs == 0 || iv.num_lefs >= 65535) return "num_lefs must be in [1, 65534]";
@@ -180,6 +180,25 @@ inline std::string prepare_interval(const modle_b200_sim_params& p, const modle_
   k.rng_per_thread = sc.per_thread;
   k.rng_window = sc.window;
   k.rng_jump_slot = sc.jump_slot;
+  // Barrier look-up table: the finest bucket (>= 4 kb) whose table still fits next to the cell's
+  // arrays under `smem_limit` (what the launch class allows per CTA); dropped when there is no
+  // room for buckets of at most 16 average barrier spacings (the walk then keeps its cursor).
+  k.lut_shift = 0;
+  k.lut_entries = 0;
+  if (smem_limit != 0 && nb != 0 && nb < 65535) {
+    const size_t base = ((sizeof(CellShared) + 15) / 16) * 16 +
+                        cell_array_bytes(static_cast<u32>(iv.num_lefs), static_cast<u32>(nb));
+    const u64 span = iv.end - iv.start;
+    for (u32 shift = 12; shift <= 24; ++shift) {
+      const u64 entries = (span >> shift) + 2;
+      if (entries > 60000) continue;
+      if (base + ((entries + 1) / 2) * 4 + 32 > smem_limit) continue;
+      if ((u64(1) << shift) > 16 * (span / nb + 1)) break;  // too coarse to be worth it
+      k.lut_shift = shift;
+      k.lut_entries = static_cast<u32>(entries);
+      break;
+    }
+  }
   // every phase must fit one staging window (largest consumer: the normal draws of both move
   // arrays, 2n items + n/4 + 64 slack + 192), and a thread's chunk of them one 32-bit mask
   const u64 worst = worst_phase_draws(static_cast<u32>(iv.num_lefs));

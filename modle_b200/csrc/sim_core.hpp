@@ -597,6 +597,21 @@ struct CellSimT {
       }
       for (u32 i = tid; i < P.n_bar; i += cta.nt()) A.bar_pos[i] = D.bar_pos[i];
       for (u32 i = tid; i < 129; i += cta.nt()) A.zig_nx[i] = D.zig_nx[i];
+      // barrier look-up table of the LEF-BAR walk: entry e = number of barriers below the first
+      // position of bucket e (binary search over the interval's own copy of the positions)
+      for (u32 e = tid; e < P.lut_entries; e += cta.nt()) {
+        const u64 first = u64(P.start) + (u64(e) << P.lut_shift);
+        u32 a = 0, z = P.n_bar;
+        while (a < z) {
+          const u32 mid = (a + z) >> 1;
+          if (u64(D.bar_pos[mid]) < first) {
+            a = mid + 1;
+          } else {
+            z = mid;
+          }
+        }
+        A.bar_lut[e] = static_cast<u16>(a);
+      }
       if (cta.leader(tid)) {
         S.epoch = 0;
         S.num_burnin_epochs = 0;
@@ -2076,12 +2091,14 @@ struct CellSimT {
       // No trial needs a draw, so the search can be turned around: instead of two binary
       // searches over the (doubly indirect) rank orders per barrier, every thread walks its
       // contiguous share of the rev ranks and of the fwd ranks together with the sorted barrier
-      // positions -- one binary search over bar_pos for the first unit of the share, then the
-      // barrier cursor only moves forward. The barriers that test rev rank k are those with
+      // positions -- the number of barriers below a unit comes from a look-up table over
+      // position buckets plus a step or two (or, when the table found no room in shared memory,
+      // from one binary search for the first unit of the share and a forward-only cursor). The barriers that test rev rank k are those with
       // pos[k-1] <= bp < pos[k] (all below pos[k] for k == j0); the closest one that is active,
       // blocks this direction with certainty and lies within the unit's move wins, exactly what
       // the per-barrier atomicMax selected. A hit overrides a boundary mark, as before.
       const bool rev_hit_maj = pmaj == 1.0, rev_hit_min = pmin == 1.0;
+      const bool use_lut = P.lut_entries != 0;
       MB_REGION(cta, tid) {
         u32 lo, hi;
         if (j0 < n && (rev_hit_maj || rev_hit_min)) {
@@ -2091,7 +2108,10 @@ struct CellSimT {
           for (u32 k = j0 + lo; k < j0 + hi; ++k) {
             const u32 idx = A.rr[k];
             const u32 pos = A.rev[idx];
-            if (first) {
+            if (use_lut) {  // a bucket holds a barrier or two: no cursor, no search
+              b = A.bar_lut[(pos - P.start) >> P.lut_shift];
+              while (b < nb && A.bar_pos[b] < pos) ++b;
+            } else if (first) {
               u32 a = 0, z = nb;
               while (a < z) {
                 const u32 mid = (a + z) >> 1;
@@ -2127,7 +2147,10 @@ struct CellSimT {
           for (u32 k = lo; k < hi; ++k) {
             const u32 idx = A.fr[k];
             const u32 pos = A.fwd[idx];
-            if (first) {
+            if (use_lut) {
+              b = A.bar_lut[(pos - P.start) >> P.lut_shift];
+              while (b < nb && A.bar_pos[b] <= pos) ++b;
+            } else if (first) {
               u32 a = 0, z = nb;
               while (a < z) {
                 const u32 mid = (a + z) >> 1;

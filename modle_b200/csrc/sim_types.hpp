@@ -102,6 +102,9 @@ struct KernelParams {
   u32 rng_per_thread;   // l: consecutive draws per generator thread per window
   u32 rng_window;       // W = G * l
   u32 rng_jump_slot;    // which precomputed T^W matrix to use
+  // barrier look-up table of the LEF-BAR walk: bar_lut[(pos - start) >> lut_shift] = number of
+  // barriers below the bucket's first position; lut_entries == 0: no table (not enough room)
+  u32 lut_shift, lut_entries;
 };
 
 // Per-interval read-only device arrays.
@@ -169,6 +172,7 @@ struct CellArrays {
   u32* bits;            // 12 * (n_lefs/32 + 3) words: bitmaps of the secondary-collision pass
   u32* bar_pos;         // n_bar (copy of IntervalData::bar_pos)
   u8* bar_active;       // n_bar bytes (0/1)
+  u16* bar_lut;         // KernelParams::lut_entries entries, or null
   double* zig_nx;       // 129 (copy)
   // per-CTA global scratch
   u64* rng_ring;   // 2 * rng_window entries
@@ -180,7 +184,7 @@ MB_HD size_t cell_scratch_words(u32 n_lefs, u32 n_bar) {
   return size_t(n_lefs > n_bar ? n_lefs : n_bar) + 64;
 }
 MB_HD size_t cell_bits_words(u32 n_lefs) { return size_t(12) * (n_lefs / 32 + 3); }
-MB_HD size_t cell_array_bytes(u32 n_lefs, u32 n_bar) {
+MB_HD size_t cell_array_bytes(u32 n_lefs, u32 n_bar, u32 lut_entries = 0) {
   size_t w = 0;
   w += 260;                                // zig_nx: 129 doubles (+ pad)
   w += size_t(7) * n_lefs;                 // rev, fwd, ep, rm, fm, rc, fc
@@ -189,9 +193,10 @@ MB_HD size_t cell_array_bytes(u32 n_lefs, u32 n_bar) {
   w += n_bar;                              // bar_pos
   w += n_lefs + 2;                         // rr, fr (u16 each)
   w += (n_bar + 3) / 4 + 1;                // bar_active (bytes)
+  w += (lut_entries + 1) / 2;              // bar_lut (u16 each)
   return ((w * 4 + 15) / 16) * 16;
 }
-MB_HD CellArrays carve_cell_arrays(void* base, u32 n_lefs, u32 n_bar) {
+MB_HD CellArrays carve_cell_arrays(void* base, u32 n_lefs, u32 n_bar, u32 lut_entries = 0) {
   CellArrays a;
   u32* p = static_cast<u32*>(base);
   a.zig_nx = reinterpret_cast<double*>(p);
@@ -220,6 +225,8 @@ MB_HD CellArrays carve_cell_arrays(void* base, u32 n_lefs, u32 n_bar) {
   a.fr = a.rr + n_lefs + (n_lefs & 1);
   p += n_lefs + 2;
   a.bar_active = reinterpret_cast<u8*>(p);
+  p += (n_bar + 3) / 4 + 1;
+  a.bar_lut = lut_entries ? reinterpret_cast<u16*>(p) : nullptr;
   a.rng_ring = nullptr;
   a.rng_state = nullptr;
   return a;

@@ -14,6 +14,7 @@
 using namespace modle_b200;
 namespace {
 std::vector<u64> g_emu_jump[kJumpSlots];
+static thread_local int g_emu_barrier_lut = 1;  // emu_set_barrier_lut
 }
 
 namespace {
@@ -37,7 +38,9 @@ struct EmuCell {
                        : staging == 4 ? staging_large_wide()
                                       : pick_staging(static_cast<u32>(iv.num_lefs),
                                                      static_cast<u32>(nb));
-    const std::string err = prepare_interval(p, iv, bars, nb, sc, &kp, &hd);
+    // (with the barrier look-up table unless emu_set_barrier_lut(0): both forms of the LEF-BAR walk)
+    const std::string err = prepare_interval(p, iv, bars, nb, sc, &kp, &hd,
+                                             g_emu_barrier_lut ? size_t(227) * 1024 : 0);
     if (!err.empty()) return err;
     if (g_emu_jump[sc.jump_slot].empty()) {
       g_emu_jump[sc.jump_slot].resize(kJumpTableWords);
@@ -53,8 +56,8 @@ struct EmuCell {
     D.zig_ny = zig.ny;
     D.zig_ex = zig.ex;
     D.zig_ey = zig.ey;
-    arrays.assign(cell_array_bytes(kp.n_lefs, kp.n_bar) / 8 + 2, 0);
-    A = carve_cell_arrays(arrays.data(), kp.n_lefs, kp.n_bar);
+    arrays.assign(cell_array_bytes(kp.n_lefs, kp.n_bar, kp.lut_entries) / 8 + 2, 0);
+    A = carve_cell_arrays(arrays.data(), kp.n_lefs, kp.n_bar, kp.lut_entries);
     ring.assign(2 * size_t(kp.rng_window), 0);
     gstate.assign(4 * size_t(kp.rng_gen_threads), 0);
     A.rng_ring = ring.data();
@@ -109,6 +112,7 @@ void emu_phase_barriers_get(u64* out, int n, int reset) {
   }
 }
 // MODLE_B200_RNG_* of the calling thread's later emu_simulate_* / emu_snapshot_cell calls
+void emu_set_barrier_lut(int on) { g_emu_barrier_lut = on; }
 void emu_set_rng_mode(int mode) { g_emu_rng_mode = mode; }
 
 int emu_simulate_interval_logged(const modle_b200_sim_params* params,

@@ -258,3 +258,21 @@ def test_barriers_outside_the_interval_are_dead_but_draw(mode):
         # counter-based draws are keyed by barrier index: the leading dead barrier renumbers them
         assert results_equal(a, b) != []
 
+
+
+@pytest.mark.parametrize("name", ["defaults_small", "more_barriers", "lef_density_x4", "sub_interval"])
+def test_lef_bar_walk_without_the_barrier_lookup_table(name):
+    """The LEF-BAR walk finds the barriers below a unit through a position-bucket table when the
+    table fits in shared memory and through a per-thread cursor otherwise: both forms against the
+    oracle (the default emulation run uses the table)."""
+    kw = dict(CASES[name])
+    vt = kw.pop("_vt", 64)
+    kw.pop("_staging", 0)
+    p, iv, bars, tasks = make_case(**kw)
+    a = pyoracle.simulate_interval(p, iv, bars, tasks, nthreads=4)
+    emu_lib.lib().emu_set_barrier_lut(0)
+    try:
+        b = emu_lib.simulate_interval(p, iv, bars, tasks, virtual_threads=vt)
+    finally:
+        emu_lib.lib().emu_set_barrier_lut(1)
+    assert results_equal(a, b) == []
