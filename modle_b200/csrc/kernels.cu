@@ -558,15 +558,14 @@ int launch_simulate(modle_b200_context* ctx, const modle_b200_sim_params* params
     CUDA_TRY(cudaMemcpy(ctx->d_jump[sc.jump_slot].p, table.data(), sizeof(u64) * kJumpTableWords,
                         cudaMemcpyHostToDevice));
   }
-  // pick a launch slot: the first idle one, else wait for the oldest
+  // pick a launch slot: the idle one with the lowest index (a caller that waits for every launch
+  // keeps reusing slot 0 and its buffers; overlapping launches take as many slots as are in
+  // flight at once), else wait for the oldest
   LaunchSlot* sl = nullptr;
   for (int k = 0; k < kLaunchSlots && !sl; ++k) {
-    LaunchSlot& c = ctx->slots[(ctx->next_slot + k) % kLaunchSlots];
+    LaunchSlot& c = ctx->slots[k];
     if (c.in_flight && cudaEventQuery(c.done) == cudaSuccess) c.in_flight = false;
-    if (!c.in_flight) {
-      sl = &c;
-      ctx->next_slot = (ctx->next_slot + k + 1) % kLaunchSlots;
-    }
+    if (!c.in_flight) sl = &c;
   }
   if (!sl) {
     sl = &ctx->slots[ctx->next_slot];
@@ -587,8 +586,8 @@ int launch_simulate(modle_b200_context* ctx, const modle_b200_sim_params* params
   };
   if (nb + 1 > ctx->hw_barriers) {
     ctx->hw_barriers = nb + 1;
-    for (auto& x : ctx->slots)
-      if (!x.in_flight && &x != sl) CUDA_TRY(reserve_barriers(x, ctx->hw_barriers));
+    for (auto& x : ctx->slots)  // (slots that never ran a launch allocate when they first do)
+      if (!x.in_flight && &x != sl && x.d_bar_pos.p) CUDA_TRY(reserve_barriers(x, ctx->hw_barriers));
   }
   CUDA_TRY(reserve_barriers(*sl, ctx->hw_barriers));
   if (nb) {
@@ -627,7 +626,7 @@ int launch_simulate(modle_b200_context* ctx, const modle_b200_sim_params* params
       ctx->hw_rings = std::max(ctx->hw_rings, rings);
       ctx->hw_states = std::max(ctx->hw_states, states);
       for (auto& x : ctx->slots) {
-        if (x.in_flight || &x == sl) continue;
+        if (x.in_flight || &x == sl || !x.d_rings.p) continue;
         CUDA_TRY(x.d_rings.reserve(ctx->hw_rings));
         CUDA_TRY(x.d_states.reserve(ctx->hw_states));
       }
@@ -818,6 +817,20 @@ int modle_b200_reserve(modle_b200_context* ctx, uint64_t max_nrows, uint64_t max
   const size_t off_stats = off_occ + ((sizeof(u64) * max_ncols + 63) / 64) * 64;
   const size_t off_missed = off_stats + ((sizeof(modle_b200_cell_stats) * cells + 63) / 64) * 64;
   CUDA_TRY(ctx->h_stage.reserve(off_missed + 64));
+  // the launch scratch of the slot a waiting caller keeps reusing, for the largest of the three
+  // launch classes (RNG rings: 2 windows per resident CTA)
+  if (ctx->rng_mode != MODLE_B200_RNG_COUNTER) {
+    size_t rings = 0, states = 0;
+    for (const StagingConfig& sc : {staging_small(), staging_mid(), staging_large()}) {
+      const size_t grid = std::min<size_t>(cells, size_t(sc.cells_per_sm) * size_t(ctx->num_sms));
+      rings = std::max(rings, sizeof(u64) * 2 * size_t(sc.window) * grid);
+      states = std::max(states, sizeof(u64) * 4 * size_t(sc.gen_threads) * grid);
+    }
+    ctx->hw_rings = std::max(ctx->hw_rings, rings);
+    ctx->hw_states = std::max(ctx->hw_states, states);
+    CUDA_TRY(ctx->slots[0].d_rings.reserve(ctx->hw_rings));
+    CUDA_TRY(ctx->slots[0].d_states.reserve(ctx->hw_states));
+  }
   return MODLE_B200_OK;
 }
 
