@@ -2108,13 +2108,8 @@ struct CellSimT {
           for (u32 k = j0 + lo; k < j0 + hi; ++k) {
             const u32 idx = A.rr[k];
             const u32 pos = A.rev[idx];
-            if (use_lut) {
-              // most units have no barrier within their move at all: two table entries say so
-              const u32 off = pos - P.start, mvq = A.rm[idx];
-              const u32 e1 = off >> P.lut_shift;
-              const u32 e0 = (off > mvq ? off - mvq : 0u) >> P.lut_shift;
-              if (A.bar_lut[e1 + 1] == A.bar_lut[e0]) continue;
-              b = A.bar_lut[e1];  // a bucket holds a barrier or two: no cursor, no search
+            if (use_lut) {  // a bucket holds a barrier or two: no cursor, no search
+              b = A.bar_lut[(pos - P.start) >> P.lut_shift];
               while (b < nb && A.bar_pos[b] < pos) ++b;
             } else if (first) {
               u32 a = 0, z = nb;
@@ -2153,13 +2148,8 @@ struct CellSimT {
             const u32 idx = A.fr[k];
             const u32 pos = A.fwd[idx];
             if (use_lut) {
-              const u32 off = pos - P.start, mvq = A.fm[idx], span1 = P.end - 1 - P.start;
-              const u32 e0 = off >> P.lut_shift;
-              const u32 e1 = (mvq > span1 - off ? span1 : off + mvq) >> P.lut_shift;
-              if (A.bar_lut[e1 + 1] == A.bar_lut[e0]) continue;
-              b = A.bar_lut[e0];
+              b = A.bar_lut[(pos - P.start) >> P.lut_shift];
               while (b < nb && A.bar_pos[b] <= pos) ++b;
-              if (b == nb) continue;
             } else if (first) {
               u32 a = 0, z = nb;
               while (a < z) {
@@ -2428,6 +2418,10 @@ struct CellSimT {
       }
     }
     cta.sync();
+    // One region for both primary cases: a rev unit whose partner also carries the primary mark
+    // rewrites both moves; a unit whose partner is stalled by a barrier rewrites only its own and
+    // reads the partner's (set in the region above, not touched here) -- the two loops write
+    // disjoint words.
     MB_REGION(cta, tid) {
       for (u32 r = tid; r < n; r += cta.nt()) {
         if (!coll_is(A.rc[r], kEvPrimary)) continue;
@@ -2441,9 +2435,6 @@ struct CellSimT {
           A.rm[r] = A.rev[r] - (A.fwd[f] + A.fm[f]) - 1;
         }
       }
-    }
-    cta.sync();
-    MB_REGION(cta, tid) {
       for (u32 f = tid; f < n; f += cta.nt()) {
         if (!coll_is(A.fc[f], kEvPrimary)) continue;
         const u32 r = coll_index(A.fc[f]);
