@@ -33,11 +33,10 @@ def gpu_ctx(product_lib):
 
 # `-m gpu` tests that have not met a device yet go last and under a timeout (the driver runs the
 # GPU suite with `-x`: a surprise in a new test must not hide the parity tests that already
-# passed on a B200). Everything written in round 1 has run on a device since (GPUTEST_r01, r02a);
+# passed on a B200). Everything written in rounds 1 and 2 has run on a device (GPUTEST_r01, the
+# r02 calls listed in profiles/README.md);
 # add the file or test name of a NEW gpu test here until it has passed once on a B200.
-_NOT_YET_RUN_ON_A_DEVICE = (
-    "test_overwrite_entry_point_ignores_what_the_buffers_held",
-)
+_NOT_YET_RUN_ON_A_DEVICE = ()
 
 
 def pytest_collection_modifyitems(config, items):
