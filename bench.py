@@ -1,28 +1,36 @@
 #!/usr/bin/env python3
-"""Benchmark of the loop-extrusion hot path (see BASELINE.md / SURVEY.md 8d).
+"""Benchmark of the loop-extrusion hot path (see BASELINE.md / SURVEY.md 8d, DESIGN.md 6).
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c2|c1|c3]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c2|c1|c3|c4|c5]
 
 One "step" = one whole simulation of the workload (default: BASELINE config C2, genome-wide
 GRCh38 shape, 24 chromosomes x 512 cells, default parameters, synthetic barriers). Metric:
 LEF-updates/s (1 LEF-update = one active LEF carried through one epoch, burn-in included).
 
   value  device-resident: cell tasks / band matrices live in HBM, kernels only (+ band memset)
-  e2e    the reference-facing call modle_b200_simulate_interval with HOST buffers
-         (H2D of tasks and barriers, D2H of band / 1D occupancy / stats inside the timed region)
+  e2e    the reference-facing call with HOST buffers (modle_b200_simulate_interval_overwrite
+         through Simulation.run_simulate: H2D of tasks and barriers, D2H of band / 1D occupancy /
+         stats inside the timed region); N > 1: device shards + NCCL reduce + D2H on the roots
+  extra  (default C2 line only) throughput_mode: the same workload with counter-based draws;
+         c3: BASELINE C3 (chr1 x 8192 cells) timed AND verified -- cells split over the ranks, one
+         NCCL reduce, checksums against the committed single-GPU golden, sampled cells against the
+         CPU oracle; a mismatch ends the bench with a non-zero exit code;
+         register: the contact-register kernel in isolation with its rooflines and an independent
+         calibration of the atomic ceilings
   roofline, cpu_baseline, clocks, gpu_launches: see DESIGN.md "Measurement"
 
---rng-mode throughput runs the same workload with counter-based draws ("Throughput
+--rng-mode throughput runs the main workload with counter-based draws ("Throughput
 mode"); the default and the headline is the deterministic mode.
 
-N > 1 (launched by torch.distributed.run, one rank per GPU): whole chromosomes are dealt to
-ranks heaviest-first (no data-path collective is needed for C2; a chromosome whose cells are
-split over ranks -- workload c3 -- is summed with one NCCL reduce). Total work is fixed, so
-"scaling" is "strong".
+N > 1 (launched by torch.distributed.run, one rank per GPU): modle_b200_plan_shards deals whole
+chromosomes to ranks heaviest-first, or one cell slice of every chromosome per rank when a slice
+still fills a GPU (--plan auto|whole|slices); a chromosome whose cells are split over ranks is
+summed with one NCCL reduce. Total work is fixed, so "scaling" is "strong".
 
 --impl reference: the reference's CPU implementation of the path cannot be built offline
 (no Boost/xoshiro-cpp/...), so this arm times the oracle restatement
-(oracle/liboracle.so) on the host cores over a bounded sample of the same workload.
+(oracle/liboracle.so) on all host cores over a bounded sample of the same workload, scheduled the
+way the reference schedules its run: one queue over all (interval, cell) tasks.
 """
 import argparse
 import json
