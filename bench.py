@@ -652,8 +652,9 @@ def run_ours(args, rank, world, local_rank):
     def step_e2e():
         sim.run_simulate(num_workers=args.e2e_workers)
 
-    e2e_steps = max(1, min(args.steps, 2))
-    step_e2e()  # warm-up (contexts, staging buffers, page faults)
+    e2e_steps = max(1, min(args.steps, 3))
+    for _ in range(2 if args.steps > 1 else 1):  # warm-up (contexts, staging buffers, page faults)
+        step_e2e()
     sync_all()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
