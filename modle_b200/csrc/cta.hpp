@@ -505,6 +505,7 @@ struct Cta {
 #define MB_ATOMIC_ADD_U64(ptr, val) \
   atomicAdd(reinterpret_cast<unsigned long long*>(ptr), static_cast<unsigned long long>(val))
 #define MB_U64_TO_F64(x) __ull2double_rn(x)
+#define MB_UMULHI64(a, b) __umul64hi((a), (b))
 #define MB_POPC(x) __popc(x)
 #define MB_FFS(x) __ffs(static_cast<int>(x))
 
@@ -674,6 +675,8 @@ inline u32 emu_atomic_min_u32(u32* p, u32 v) {
 #define MB_ATOMIC_ADD_U32(ptr, val) __atomic_fetch_add((ptr), (val), __ATOMIC_RELAXED)
 #define MB_ATOMIC_ADD_U64(ptr, val) __atomic_fetch_add((ptr), (val), __ATOMIC_RELAXED)
 #define MB_U64_TO_F64(x) static_cast<double>(x)
+#define MB_UMULHI64(a, b) \
+  static_cast<unsigned long long>((static_cast<unsigned __int128>(a) * static_cast<unsigned __int128>(b)) >> 64)
 #define MB_POPC(x) __builtin_popcount(x)
 #define MB_FFS(x) __builtin_ffs(static_cast<int>(x))
 
@@ -800,6 +803,8 @@ struct Cta {
 #define MB_ATOMIC_ADD_U32(ptr, val) (*(ptr) += (val))
 #define MB_ATOMIC_ADD_U64(ptr, val) (*(ptr) += (val))
 #define MB_U64_TO_F64(x) static_cast<double>(x)
+#define MB_UMULHI64(a, b) \
+  static_cast<unsigned long long>((static_cast<unsigned __int128>(a) * static_cast<unsigned __int128>(b)) >> 64)
 #define MB_POPC(x) __builtin_popcount(x)
 #define MB_FFS(x) __builtin_ffs(static_cast<int>(x))
 

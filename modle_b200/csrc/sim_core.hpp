@@ -105,6 +105,22 @@ MB_FN u64 uniform_int_bucket(u64 range) {
   if (brange % (range + 1) == range) ++bucket;
   return bucket;
 }
+// floor(x / d) for a divisor that is used many times: m = floor((2^64 - 1) / d) never exceeds
+// 2^64 / d, so the high half of x * m is at most x / d and short of it by two at the very most;
+// the remainder settles the rest exactly. (A 64-bit division is ~100 instructions on the device.)
+struct InvU64 {
+  u64 d, m;
+};
+MB_FN InvU64 inv_u64(u64 d) { return InvU64{d, ~u64(0) / d}; }
+MB_FN u64 div_u64(u64 x, const InvU64& v) {
+  u64 q = MB_UMULHI64(x, v.m);
+  u64 r = x - q * v.d;
+  while (r >= v.d) {
+    r -= v.d;
+    ++q;
+  }
+  return q;
+}
 // detail::generate_int_float_pair<double, 8>
 MB_FN double int_float_pair8(u64 u, int* bucket) {
   *bucket = static_cast<int>(u & 0xFF);
@@ -803,22 +819,32 @@ struct CellSimT {
   MB_FN void bind_lefs() {
     const u32 n = S.num_active;
     const u64 range = u64(P.end - 1) - u64(P.start);
-    const u64 bucket = range ? uniform_int_bucket(range) : 1;
+    const InvU64 bucket = inv_u64(range ? uniform_int_bucket(range) : 1);
+    const u32 cur = static_cast<u32>(S.epoch);
     if constexpr (kCtr) {
-      // every unbound LEF draws its position from its own sequence: one pass, no repair
+      // Every unbound LEF draws its position from its own sequence: one pass, no repair. Few
+      // LEFs are unbound in an epoch (a lane or two of a warp per trip), so a thread first notes
+      // which of its LEFs are and then handles those back to back: the lanes of a warp that have
+      // any then go through the draw together instead of a lane or two per trip.
       MB_REGION(cta, tid) {
-        for (u32 i = tid; i < n; i += cta.nt()) {
-          if (A.ep[i] != kUnbound) continue;
-          u64 r = 0;
-          if (range != 0) {
-            Cursor c = ctr_cursor(S.epoch, kDrBind, i);
-            do {
-              r = c.next() / bucket;
-            } while (r > range && !c.overrun);
-            if (c.overrun) fault(kFaultSerialDraws);
+        for (u32 i0 = tid; i0 < n; i0 += 32u * cta.nt()) {
+          u32 todo = 0, k = 0;
+          for (u32 i = i0; k < 32 && i < n; i += cta.nt(), ++k) todo |= u32(A.ep[i] == kUnbound) << k;
+          while (todo) {
+            k = static_cast<u32>(MB_FFS(todo)) - 1;
+            todo &= todo - 1;
+            const u32 i = i0 + k * cta.nt();
+            u64 r = 0;
+            if (range != 0) {
+              Cursor c = ctr_cursor(S.epoch, kDrBind, i);
+              do {
+                r = div_u64(c.next(), bucket);
+              } while (r > range && !c.overrun);
+              if (c.overrun) fault(kFaultSerialDraws);
+            }
+            A.rev[i] = A.fwd[i] = static_cast<u32>(u64(P.start) + r);
+            A.ep[i] = cur;
           }
-          A.rev[i] = A.fwd[i] = static_cast<u32>(u64(P.start) + r);
-          A.ep[i] = static_cast<u32>(S.epoch);
         }
       }
       cta.sync();
@@ -831,6 +857,7 @@ struct CellSimT {
       u64 c = 0;
       for (u32 i = lo; i < hi; ++i) c += A.ep[i] == kUnbound;
       cnt[tid] = c;
+      if (cta.leader(tid)) S.tmp_u32[0] = 0;
     }
     const u64 total = cta.exscan_sum(cnt);
     if (total == 0) return;
@@ -839,7 +866,7 @@ struct CellSimT {
         for (u32 i = tid; i < n; i += cta.nt()) {
           if (A.ep[i] == kUnbound) {
             A.rev[i] = A.fwd[i] = P.start;
-            A.ep[i] = static_cast<u32>(S.epoch);
+            A.ep[i] = cur;
           }
         }
       }
@@ -847,10 +874,10 @@ struct CellSimT {
       return;
     }
     rng_ensure(S.rng_pos + total + 64);
-    MB_REGION(cta, tid) {
-      if (cta.leader(tid)) S.tmp_u32[0] = 0;
-    }
-    cta.sync();
+    // The k-th unbound LEF takes the k-th draw unless a uniform_int rejection (about one draw in
+    // 2^36 for a human chromosome) shifts the later ones: bind with the draws at their default
+    // offsets and note a rejection. LEFs bound here are the only ones that carry the current
+    // epoch, which is how the sequential redo below finds them again.
     MB_REGION(cta, tid) {
       u32 lo, hi;
       chunk(tid, n, &lo, &hi);
@@ -858,46 +885,32 @@ struct CellSimT {
       bool rejected = false;
       for (u32 i = lo; i < hi; ++i) {
         if (A.ep[i] != kUnbound) continue;
-        const u64 r = raw(o++) / bucket;
+        const u64 r = div_u64(raw(o++), bucket);
         if (r > range) rejected = true;
-        A.scratch[i] = static_cast<u32>(u64(P.start) + r);
+        A.rev[i] = A.fwd[i] = static_cast<u32>(u64(P.start) + r);
+        A.ep[i] = cur;
       }
       if (rejected) S.tmp_u32[0] = 1;
     }
     cta.sync();
-    if (S.tmp_u32[0] != 0) {
-      // a uniform_int rejection shifts every later draw: redo the phase sequentially
-      cta.sync();
-      MB_REGION(cta, tid) {
-        if (cta.leader(tid)) {
-          Cursor c = cursor(S.rng_pos, S.rng_pos + total + 64);
-          for (u32 i = 0; i < n; ++i) {
-            if (A.ep[i] != kUnbound) continue;
-            u64 r;
-            do {
-              r = c.next() / bucket;
-            } while (r > range && !c.overrun);
-            A.scratch[i] = static_cast<u32>(u64(P.start) + r);
-          }
-          if (c.overrun) fault(kFaultSerialDraws);
-          S.tmp_u64[0] = c.pos;
-        }
-      }
-      cta.sync();
-    } else {
-      MB_REGION(cta, tid) {
-        if (cta.leader(tid)) S.tmp_u64[0] = S.rng_pos + total;
-      }
-      cta.sync();
-    }
+    const bool redo = S.tmp_u32[0] != 0;
     MB_REGION(cta, tid) {
-      for (u32 i = tid; i < n; i += cta.nt()) {
-        if (A.ep[i] == kUnbound) {
-          A.rev[i] = A.fwd[i] = A.scratch[i];
-          A.ep[i] = static_cast<u32>(S.epoch);
-        }
+      if (!cta.leader(tid)) continue;
+      if (!redo) {
+        S.rng_pos += total;
+        continue;
       }
-      if (cta.leader(tid)) S.rng_pos = S.tmp_u64[0];
+      Cursor c = cursor(S.rng_pos, S.rng_pos + total + 64);
+      for (u32 i = 0; i < n; ++i) {
+        if (A.ep[i] != cur) continue;
+        u64 r;
+        do {
+          r = div_u64(c.next(), bucket);
+        } while (r > range && !c.overrun);
+        A.rev[i] = A.fwd[i] = static_cast<u32>(u64(P.start) + r);
+      }
+      if (c.overrun) fault(kFaultSerialDraws);
+      S.rng_pos = c.pos;
     }
     cta.sync();
   }
@@ -1258,10 +1271,11 @@ struct CellSimT {
     const u32 n = S.num_active;
     u64 i = 0;
     if (n > 1) {
+      // bucket * (range + 1) <= 2^64 - 1: range + 1 serves as the reciprocal of the bucket
       const u64 range = n - 1;
-      const u64 bucket = uniform_int_bucket(range);
+      const InvU64 bucket{uniform_int_bucket(range), range + 1};
       do {
-        i = c.next() / bucket;
+        i = div_u64(c.next(), bucket);
       } while (i > range && !c.overrun);
     }
     if (c.overrun) {
@@ -1288,14 +1302,14 @@ struct CellSimT {
           const u64 range = x2 - x1;
           u64 y1 = x1, y2 = x1;
           if (range != 0) {
-            const u64 bucket = uniform_int_bucket(range);
+            const InvU64 bucket{uniform_int_bucket(range), range + 1};
             u64 r;
             do {
-              r = c.next() / bucket;
+              r = div_u64(c.next(), bucket);
             } while (r > range && !c.overrun);
             y1 = x1 + r;
             do {
-              r = c.next() / bucket;
+              r = div_u64(c.next(), bucket);
             } while (r > range && !c.overrun);
             y2 = x1 + r;
           }
@@ -1310,46 +1324,57 @@ struct CellSimT {
     return static_cast<u32>(c.pos - o);
   }
 
-  // Runs `n_events` events of one kind. Events are evaluated speculatively at their default
-  // stride; the first event that consumes a different number of draws re-bases the rest.
-  MB_FN void sampling_events(u32 n_events, int kind) {
-    if (n_events == 0) return;
-    const u32 n_act = S.num_active;
-    const u32 base_draws = n_act > 1 ? 1u : 0u;
-    const u32 stride = base_draws + (P.noisify ? 2u : 0u) + (kind == 1 ? 2u : 0u);
-    const u32 cap = ((P.n_lefs > P.n_bar ? P.n_lefs : P.n_bar) + 64) / 2;
-    u32 e0 = 0;
-    while (e0 < n_events) {
-      u32 batch = n_events - e0;
+  // Deterministic mode: the events of an epoch in the reference's order -- nloop loop contacts,
+  // ntad TAD contacts, n1d 1D-occupancy events -- as one pool. Every event is evaluated at the
+  // stream offset it has when all events before it consume their usual number of draws; the
+  // first event that consumes a different number ends the round (events up to and including it
+  // are final) and the rest is re-based in the next round. Two flag words take turns (a round's
+  // flag is reset in the NEXT round's register region, after every thread has read it); the
+  // caller sets S.tmp_u32[0] to all-ones before the barrier that precedes this call.
+  MB_FN void sampling_pool(u32 nloop, u32 ntad, u32 n1d) {
+    const u32 total = nloop + ntad + n1d;
+    if (total == 0) return;
+    const u32 sl = (S.num_active > 1 ? 1u : 0u) + (P.noisify ? 2u : 0u);  // loop / 1D event
+    const u32 st = sl + 2;                                                  // TAD event
+    // default draws of the events before pool index w
+    auto draws_before = [&](u32 w) -> u64 {
+      if (w <= nloop) return u64(w) * sl;
+      if (w <= nloop + ntad) return u64(nloop) * sl + u64(w - nloop) * st;
+      return u64(nloop) * sl + u64(ntad) * st + u64(w - nloop - ntad) * sl;
+    };
+    const u32 cap = ((P.n_lefs > P.n_bar ? P.n_lefs : P.n_bar) + 64) / 2;  // scratch: 2 words each
+    const u32 max_by_window = (P.rng_window - 64) / (st + 1);
+    u32 w0 = 0;
+    for (u32 round = 0; w0 < total; ++round) {
+      u32 batch = total - w0;
       if (batch > cap) batch = cap;
-      const u32 max_by_window = (P.rng_window - 64) / (stride + 1);
       if (batch > max_by_window) batch = max_by_window;
+      const u64 d0 = draws_before(w0);
       const u64 base = S.rng_pos;
-      const u64 limit = base + u64(batch) * stride + 48;
+      const u64 limit = base + (draws_before(w0 + batch) - d0) + 48;
       rng_ensure(limit);
-      MB_REGION(cta, tid) {
-        if (cta.leader(tid)) S.tmp_u32[0] = 0xFFFFFFFFu;
-      }
-      cta.sync();
+      u32* flag = &S.tmp_u32[(round & 1u) ? 2 : 0];
+      u32* next_flag = &S.tmp_u32[(round & 1u) ? 0 : 2];
       MB_REGION(cta, tid) {
         for (u32 e = tid; e < batch; e += cta.nt()) {
+          const u32 w = w0 + e;
+          const int kind = w < nloop ? 0 : (w < nloop + ntad ? 1 : 2);
           u32 b1, b2;
-          const u32 c = sampling_event(base + u64(e) * stride, kind, limit, &b1, &b2);
+          const u32 c = sampling_event(base + (draws_before(w) - d0), kind, limit, &b1, &b2);
           A.scratch[2 * e] = b1;
           A.scratch[2 * e + 1] = b2;
-          if (c != stride) MB_ATOMIC_MIN_U32(&S.tmp_u32[0], (e << 8) | (c > 255 ? 255u : c));
+          if (c != (kind == 1 ? st : sl)) MB_ATOMIC_MIN_U32(flag, (e << 8) | (c > 255 ? 255u : c));
         }
       }
       cta.sync();
-      const u32 exc = S.tmp_u32[0];
+      const u32 exc = MB_SHARED_LOAD_U32(flag);
       const u32 valid = exc == 0xFFFFFFFFu ? batch : (exc >> 8) + 1;  // events final this round
-      cta.sync();
       MB_REGION(cta, tid) {
         u32 registered = 0;
         for (u32 e = tid; e < valid; e += cta.nt()) {
           const u32 b1 = A.scratch[2 * e], b2 = A.scratch[2 * e + 1];
           if (b1 == kUnbound) continue;
-          if (kind == 2) {
+          if (w0 + e >= nloop + ntad) {
             if (K.occ1d) {
               MB_ATOMIC_ADD_U64(K.occ1d + b1, u64(1));
               MB_ATOMIC_ADD_U64(K.occ1d + b2, u64(1));
@@ -1363,16 +1388,17 @@ struct CellSimT {
         // compare-and-swap loop that 1,024 threads would fight over)
         if (registered) MB_ATOMIC_ADD_U32(&S.tmp_u32[7], registered);
         if (cta.leader(tid)) {
-          u64 consumed = u64(valid) * stride;
+          u64 consumed = draws_before(w0 + valid) - d0;
           if (exc != 0xFFFFFFFFu) {
             if ((exc & 0xFF) == 255) fault(kFaultSerialDraws);
-            consumed = u64(valid - 1) * stride + (exc & 0xFF);
+            consumed = (draws_before(w0 + valid - 1) - d0) + (exc & 0xFF);
           }
           S.rng_pos = base + consumed;
+          MB_SHARED_STORE_U32(next_flag, 0xFFFFFFFFu);
         }
       }
       cta.sync();
-      e0 += valid;
+      w0 += valid;
     }
   }
 
@@ -1403,6 +1429,7 @@ struct CellSimT {
         }
         S.tmp_u32[1] = static_cast<u32>(nloop);
         S.tmp_u32[7] = 0;  // contacts registered this epoch
+        S.tmp_u32[0] = 0xFFFFFFFFu;  // sampling_pool: no event off its usual draw count so far
       }
     }
     cta.sync();
@@ -1438,9 +1465,7 @@ struct CellSimT {
       }
       cta.sync();
     } else {
-      sampling_events(nloop, 0);
-      sampling_events(ntad, 1);
-      if (P.track_1d) sampling_events(static_cast<u32>(nev), 2);
+      sampling_pool(nloop, ntad, P.track_1d ? static_cast<u32>(nev) : 0u);
     }
     MB_REGION(cta, tid) {
       if (cta.leader(tid)) S.num_contacts += S.tmp_u32[7];
@@ -1473,22 +1498,42 @@ struct CellSimT {
   // the rare slow paths are evaluated speculatively and stitched into the stream by the leader.
   MB_FN void draw_normal_moves(u32 items, u32 n_rev, double rev_speed, double fwd_speed) {
     if constexpr (kCtr) {
-      // one full ziggurat sampler per item on the item's own sequence (fast and slow paths alike)
+      // One ziggurat sampler per item on the item's own sequence. Some 98 % of the items are
+      // settled by their first draw; the others (rejection loops, exp()) are noted per thread and
+      // finished after the thread's fast items, so that the lanes of a warp that have any go
+      // through the slow code together instead of one or two at a time on every trip.
       sub_begin();
       const double rsd = P.rev_std, fsd = P.fwd_std;
       MB_REGION(cta, tid) {
         bool over = false;
-        for (u32 i = tid; i < items; i += cta.nt()) {
-          Cursor c = ctr_cursor(S.epoch, kDrMoves, i);
-          const double z = unit_normal_serial(c);
-          if (c.overrun) fault(kFaultSerialDraws);
+        auto store = [&](u32 item, double z) {
           u32 mv;
-          if (i < n_rev) {
-            A.rm[i] = mv = move_from_z(z, rev_speed, rsd);
+          if (item < n_rev) {
+            A.rm[item] = mv = move_from_z(z, rev_speed, rsd);
           } else {
-            A.fm[i - n_rev] = mv = move_from_z(z, fwd_speed, fsd);
+            A.fm[item - n_rev] = mv = move_from_z(z, fwd_speed, fsd);
           }
           over |= mv > P.move_bound;
+        };
+        for (u32 i0 = tid; i0 < items; i0 += 32u * cta.nt()) {
+          u32 later = 0, k = 0;
+          for (u32 i = i0; k < 32 && i < items; i += cta.nt(), ++k) {
+            double z;
+            if (unit_normal_fast(raw(ctr_pack(S.epoch, kDrMoves, i)), &z)) {
+              store(i, z);
+            } else {
+              later |= 1u << k;
+            }
+          }
+          while (later) {
+            k = static_cast<u32>(MB_FFS(later)) - 1;
+            later &= later - 1;
+            const u32 i = i0 + k * cta.nt();
+            Cursor c = ctr_cursor(S.epoch, kDrMoves, i);
+            const double z = unit_normal_serial(c);
+            if (c.overrun) fault(kFaultSerialDraws);
+            store(i, z);
+          }
         }
         if (over) S.move_bound_hit = 1;
       }
@@ -1684,9 +1729,17 @@ struct CellSimT {
     const u32 kept = S.tmp_u32[2];
     sub_lap(kPhMvExceptions);
     const double rev_sd = P.rev_std, fwd_sd = P.fwd_std;
+    // Item i reads the draw at offset i + (extra draws of the kept exceptions before it). Groups
+    // of 32 consecutive threads (a warp) own consecutive ranges of items and go through them 32
+    // items at a time, lane by lane: neighbouring lanes read neighbouring draws of the ring, and
+    // every lane of a group walks the (short, shared) list of exceptions of the 32 items in
+    // step, so the trip count is the same for all lanes whatever the exceptions are.
     MB_REGION(cta, tid) {
-      u32 lo, hi;
-      chunk(tid, items, &lo, &hi);
+      const u32 nt = static_cast<u32>(cta.nt());
+      const u32 G = (nt & 31u) == 0 ? 32u : 1u;  // (odd widths exist only in the emulation)
+      const u32 ng = nt / G, g = static_cast<u32>(tid) / G, lane = static_cast<u32>(tid) % G;
+      const u32 lo = static_cast<u32>(u64(items) * g / ng);
+      const u32 hi = static_cast<u32>(u64(items) * (g + 1) / ng);
       // first kept exception with item >= lo
       u32 a = 0, b = kept;
       while (a < b) {
@@ -1709,21 +1762,26 @@ struct CellSimT {
         }
         over |= mv > P.move_bound;
       };
-      u32 i = lo;
-      while (i < hi) {
-        const u32 next_exc = e < kept ? ex[4 * e] : 0xFFFFFFFFu;
-        const u32 run_end = hi < next_exc ? hi : next_exc;  // [i, run_end): fast items
-        const u64 o = base + shift;
-        for (; i + 4 <= run_end; i += 4) {
-          const u64 r0 = raw(o + i), r1 = raw(o + i + 1), r2 = raw(o + i + 2), r3 = raw(o + i + 3);
-          store(i, unit_normal_fast_value(r0));
-          store(i + 1, unit_normal_fast_value(r1));
-          store(i + 2, unit_normal_fast_value(r2));
-          store(i + 3, unit_normal_fast_value(r3));
+      // the draw an item reads when no exception lies between the start of its 32 items and it
+      // -- nearly always -- is requested one trip ahead
+      u64 r_ahead = lo < hi ? raw(base + shift + lo + lane) : 0;
+      for (u32 i0 = lo; i0 < hi; i0 += G) {
+        const u32 i = i0 + lane;
+        const u32 end = i0 + G < hi ? i0 + G : hi;
+        const u64 r_spec = r_ahead;
+        const u32 shift_spec = shift;
+        u32 my_shift = shift, my_exc = 0xFFFFFFFFu;
+        while (e < kept && ex[4 * e] < end) {  // same trips for every lane of the group
+          const u32 xi = ex[4 * e];
+          if (xi < i) my_shift = ex[4 * e + 1];
+          if (xi == i) my_exc = e;
+          shift = ex[4 * e + 1];  // later items start after this item's extra draws
+          ++e;
         }
-        for (; i < run_end; ++i) store(i, unit_normal_fast_value(raw(o + i)));
-        if (i < hi && i == next_exc) {
-          const u64 zb = u64(ex[4 * e + 2]) | (u64(ex[4 * e + 3]) << 32);
+        if (end < hi) r_ahead = raw(base + shift + end + lane);
+        if (i >= end) continue;
+        if (my_exc != 0xFFFFFFFFu) {
+          const u64 zb = u64(ex[4 * my_exc + 2]) | (u64(ex[4 * my_exc + 3]) << 32);
           double z;
 #if MB_DEVICE_BUILD
           z = __longlong_as_double(static_cast<long long>(zb));
@@ -1731,9 +1789,8 @@ struct CellSimT {
           std::memcpy(&z, &zb, 8);
 #endif
           store(i, z);
-          shift = ex[4 * e + 1];  // later items start after this item's extra draws
-          ++e;
-          ++i;
+        } else {
+          store(i, unit_normal_fast_value(my_shift == shift_spec ? r_spec : raw(base + my_shift + i)));
         }
       }
       if (over) S.move_bound_hit = 1;
