@@ -613,6 +613,7 @@ struct CellSimT {
       }
       for (u32 i = tid; i < P.n_bar; i += cta.nt()) A.bar_pos[i] = D.bar_pos[i];
       for (u32 i = tid; i < 129; i += cta.nt()) A.zig_nx[i] = D.zig_nx[i];
+      mv_clear_slow_bits(tid);
       // barrier look-up table of the LEF-BAR walk: entry e = number of barriers below the first
       // position of bucket e (binary search over the interval's own copy of the positions)
       for (u32 e = tid; e < P.lut_entries; e += cta.nt()) {
@@ -895,22 +896,23 @@ struct CellSimT {
     cta.sync();
     const bool redo = S.tmp_u32[0] != 0;
     MB_REGION(cta, tid) {
-      if (!cta.leader(tid)) continue;
-      if (!redo) {
-        S.rng_pos += total;
-        continue;
+      if (cta.leader(tid)) {
+        if (!redo) {
+          S.rng_pos += total;
+        } else {
+          Cursor c = cursor(S.rng_pos, S.rng_pos + total + 64);
+          for (u32 i = 0; i < n; ++i) {
+            if (A.ep[i] != cur) continue;
+            u64 r;
+            do {
+              r = div_u64(c.next(), bucket);
+            } while (r > range && !c.overrun);
+            A.rev[i] = A.fwd[i] = static_cast<u32>(u64(P.start) + r);
+          }
+          if (c.overrun) fault(kFaultSerialDraws);
+          S.rng_pos = c.pos;
+        }
       }
-      Cursor c = cursor(S.rng_pos, S.rng_pos + total + 64);
-      for (u32 i = 0; i < n; ++i) {
-        if (A.ep[i] != cur) continue;
-        u64 r;
-        do {
-          r = div_u64(c.next(), bucket);
-        } while (r > range && !c.overrun);
-        A.rev[i] = A.fwd[i] = static_cast<u32>(u64(P.start) + r);
-      }
-      if (c.overrun) fault(kFaultSerialDraws);
-      S.rng_pos = c.pos;
     }
     cta.sync();
   }
@@ -1492,6 +1494,24 @@ struct CellSimT {
     return (bits & 1) ? x : -x;
   }
 
+  // Bitmap of the draws that leave the fast ziggurat path (deterministic mode; one bit per
+  // examined stream offset, at most 2.25 n_lefs + 64 of them). It borrows words [4, 12) * (n_lefs
+  // / 32 + 3) of A.bits, which only the secondary pass uses otherwise: init_cell and -- after the
+  // secondary pass of every epoch -- extrude_and_release clear it, so draw_normal_moves finds it
+  // zero (bind, rank and the contact sampling in between leave those words alone).
+  MB_FN u32* mv_slow_bits() const { return A.bits + 4 * (P.n_lefs / 32 + 3); }
+  MB_FN u32 mv_slow_words() const {
+    const u32 items = 2 * P.n_lefs;
+    return (items + items / 8 + 64 + 31) / 32;
+  }
+  MB_FN void mv_clear_slow_bits(int tid) const {
+    if constexpr (!kCtr) {
+      u32* w = mv_slow_bits();
+      const u32 nw = mv_slow_words();
+      for (u32 k = static_cast<u32>(tid); k < nw; k += static_cast<u32>(cta.nt())) w[k] = 0;
+    }
+  }
+
   // One Normal(speed, sd) per item, items in stream order: the first n_rev items are the rev
   // moves of LEFs 0..n_rev-1, the others the fwd moves (generate_moves, simulation.cpp:299-330,
   // draws all rev moves and then all fwd moves). The fast ziggurat path uses exactly one draw;
@@ -1551,26 +1571,34 @@ struct CellSimT {
     // exception records live in scratch: 4 words each {offset, draws consumed, z lo, z hi}
     u32* ex = A.scratch;
     const u32 ex_cap = ((P.n_lefs > P.n_bar ? P.n_lefs : P.n_bar) + 64) / 4;
+    // Which offsets leave the fast path: consecutive threads test consecutive draws (a warp reads
+    // whole lines of the ring) and set a bit per slow offset; the bitmap -- zero on entry, see
+    // mv_slow_bits() -- is then turned into the ordered list by word.
+    u32* slowbits = mv_slow_bits();
+    const u32 slow_words = (span + 31) / 32;
+    MB_REGION(cta, tid) {
+      const u32 nt = static_cast<u32>(cta.nt());
+      for (u32 o = static_cast<u32>(tid); o < span; o += 4 * nt) {
+        // (offsets past span are read but not used: inside the staged range)
+        const u64 r0 = raw(base + o), r1 = raw(base + o + nt), r2 = raw(base + o + 2 * nt),
+                  r3 = raw(base + o + 3 * nt);
+        double z;
+        if (!unit_normal_fast(r0, &z)) MB_ATOMIC_OR_U32(&slowbits[o >> 5], 1u << (o & 31));
+        u32 q = o + nt;
+        if (q < span && !unit_normal_fast(r1, &z)) MB_ATOMIC_OR_U32(&slowbits[q >> 5], 1u << (q & 31));
+        q += nt;
+        if (q < span && !unit_normal_fast(r2, &z)) MB_ATOMIC_OR_U32(&slowbits[q >> 5], 1u << (q & 31));
+        q += nt;
+        if (q < span && !unit_normal_fast(r3, &z)) MB_ATOMIC_OR_U32(&slowbits[q >> 5], 1u << (q & 31));
+      }
+    }
+    cta.sync();
     PerThread<u64> cnt(cta.nt());
-    PerThread<u32> slow(cta.nt());  // bit k: offset lo + k of this thread's chunk is not fast
     MB_REGION(cta, tid) {
       u32 lo, hi;
-      chunk(tid, span, &lo, &hi);
-      u32 m = 0, c = 0;
-      for (u32 o = lo; o < hi; o += 4) {  // (reads up to 3 draws past hi: inside the staged range)
-        const u64 r0 = raw(base + o), r1 = raw(base + o + 1), r2 = raw(base + o + 2),
-                  r3 = raw(base + o + 3);
-        double z;
-        const u32 k = (o - lo) & 31u;
-        u32 q = 0;
-        if (!unit_normal_fast(r0, &z)) q |= 1u;
-        if (o + 1 < hi && !unit_normal_fast(r1, &z)) q |= 2u;
-        if (o + 2 < hi && !unit_normal_fast(r2, &z)) q |= 4u;
-        if (o + 3 < hi && !unit_normal_fast(r3, &z)) q |= 8u;
-        m |= q << k;
-        c += static_cast<u32>(MB_POPC(q));
-      }
-      slow[tid] = m;
+      chunk(tid, slow_words, &lo, &hi);
+      u32 c = 0;
+      for (u32 w = lo; w < hi; ++w) c += static_cast<u32>(MB_POPC(slowbits[w]));
       cnt[tid] = c;
     }
     const u64 n_exc = cta.exscan_sum(cnt);
@@ -1584,19 +1612,14 @@ struct CellSimT {
     }
     MB_REGION(cta, tid) {
       u32 lo, hi;
-      chunk(tid, span, &lo, &hi);
+      chunk(tid, slow_words, &lo, &hi);
       u32 j = static_cast<u32>(cnt[tid]);
-      if (hi - lo <= 32) {
-        u32 m = slow[tid];
+      for (u32 w = lo; w < hi; ++w) {
+        u32 m = slowbits[w];
         while (m) {
           const u32 k = static_cast<u32>(MB_FFS(m)) - 1;
           m &= m - 1;
-          ex[4 * j++] = lo + k;
-        }
-      } else {  // chunk wider than the mask (never with the CTA widths the launcher uses)
-        for (u32 o = lo; o < hi; ++o) {
-          double z;
-          if (!unit_normal_fast(raw(base + o), &z)) ex[4 * j++] = o;
+          ex[4 * j++] = 32 * w + k;
         }
       }
     }
@@ -2367,24 +2390,24 @@ struct CellSimT {
   }
 
   MB_FN void primary_apply(u32 r, u32 f) const {
-    u32 cp_rev, cp_fwd;
-    lef_lef_collision_pos(A.rev[r], A.fwd[f], A.rm[r], A.fm[f], &cp_rev, &cp_fwd);
     const u32 rcol = A.rc[r], fcol = A.fc[f];
     const u32 hit_r = coll_make(f, kEvCollision | kEvPrimary);
     const u32 hit_f = coll_make(r, kEvCollision | kEvPrimary);
-    if (!coll_occurred(rcol) && !coll_occurred(fcol)) {
+    if (!coll_occurred(rcol) && !coll_occurred(fcol)) {  // (most pairs: no division needed)
       A.rc[r] = hit_r;
       A.fc[f] = hit_f;
-    } else if (coll_occurred(rcol) && !coll_occurred(fcol)) {
+      return;
+    }
+    if (coll_occurred(rcol) && coll_occurred(fcol)) return;
+    // one unit is stalled by a barrier already: where the two would meet decides
+    u32 cp_rev, cp_fwd;
+    lef_lef_collision_pos(A.rev[r], A.fwd[f], A.rm[r], A.fm[f], &cp_rev, &cp_fwd);
+    if (coll_occurred(rcol)) {
       // the reference asserts LEF_BAR here; a boundary mark has index 5/3 and is read the same way
       const u32 barrier_pos = A.bar_pos[coll_index(rcol)];
-      if (cp_fwd > barrier_pos) {
-        A.rc[r] = hit_r;
-        A.fc[f] = hit_f;
-      } else {
-        A.fc[f] = hit_f;
-      }
-    } else if (!coll_occurred(rcol) && coll_occurred(fcol)) {
+      if (cp_fwd > barrier_pos) A.rc[r] = hit_r;
+      A.fc[f] = hit_f;
+    } else {
       const u32 barrier_pos = A.bar_pos[coll_index(fcol)];
       A.rc[r] = hit_r;
       if (cp_rev < barrier_pos) A.fc[f] = hit_f;
@@ -2479,17 +2502,30 @@ struct CellSimT {
     // rewrites both moves; a unit whose partner is stalled by a barrier rewrites only its own and
     // reads the partner's (set in the region above, not touched here) -- the two loops write
     // disjoint words.
+    // (a thread first notes which of its rev units meet a fwd unit half-way and then works those
+    // off back to back: the division sits in that part, and a warp goes through it as often as
+    // its busiest lane has pairs rather than once per trip with a few lanes each)
     MB_REGION(cta, tid) {
-      for (u32 r = tid; r < n; r += cta.nt()) {
-        if (!coll_is(A.rc[r], kEvPrimary)) continue;
-        const u32 f = coll_index(A.rc[r]);
-        if (coll_is(A.fc[f], kEvPrimary)) {
+      for (u32 r0 = tid; r0 < n; r0 += 32u * cta.nt()) {
+        u32 both = 0, k = 0;
+        for (u32 r = r0; k < 32 && r < n; r += cta.nt(), ++k) {
+          if (!coll_is(A.rc[r], kEvPrimary)) continue;
+          const u32 f = coll_index(A.rc[r]);
+          if (coll_is(A.fc[f], kEvPrimary)) {
+            both |= 1u << k;
+          } else if (coll_is(A.fc[f], kEvLefBar)) {
+            A.rm[r] = A.rev[r] - (A.fwd[f] + A.fm[f]) - 1;
+          }
+        }
+        while (both) {
+          k = static_cast<u32>(MB_FFS(both)) - 1;
+          both &= both - 1;
+          const u32 r = r0 + k * cta.nt();
+          const u32 f = coll_index(A.rc[r]);
           u32 p1, p2;
           lef_lef_collision_pos(A.rev[r], A.fwd[f], A.rm[r], A.fm[f], &p1, &p2);
           A.rm[r] = A.rev[r] - p1;
           A.fm[f] = p2 - A.fwd[f];
-        } else if (coll_is(A.fc[f], kEvLefBar)) {
-          A.rm[r] = A.rev[r] - (A.fwd[f] + A.fm[f]) - 1;
         }
       }
       for (u32 f = tid; f < n; f += cta.nt()) {
@@ -2552,11 +2588,38 @@ struct CellSimT {
       // bits read here do not change in this region)
       if (!coll_occurred(MB_SHARED_LOAD_U32(&coll[idx]))) continue;
       i32 v = sec_q<kRevPass>(idx);
-      // The only value carried from one unit of the run to the next is v, so the loads of the
-      // next four units are issued together before they are looked at (a queue behind a barrier
-      // can be dozens of units long, and the longest one sets the pace of this region).
+      // One unit of a run: false when the run ends at scan position k (unit ik with collision
+      // word cw, position p and target q).
+      auto step = [&](u32 k, u32 ik, u32 cw, i32 p, i32 q) -> bool {
+        if (coll_occurred(cw) || q > v) return false;
+        const i32 mv = p - v;  // distance to the blocker's site
+        MB_SHARED_STORE_U32(&coll[ik], static_cast<u32>(mv > 0 ? mv - 1 : 0));  // event bits stay 0
+        MB_ATOMIC_OR_U32(&d.cand[k >> 5], 1u << (k & 31));
+        if (k == m + 1) MB_ATOMIC_OR_U32(&d.head1[k >> 5], 1u << (k & 31));
+        if constexpr (kCtr) {
+          if (never ||
+              (draws && !bernoulli_raw(raw(ctr_pack(S.epoch, kDrSecondary,
+                                                    ((kRevPass ? 0u : 1u) << 24) | k)),
+                                       1.0 - P.p_bypass)))
+            return false;
+          MB_ATOMIC_OR_U32(&ok[k >> 5], 1u << (k & 31));
+        }
+        v = p < v + 1 ? p : v + 1;
+        return true;
+      };
+      // Most stalled units have nobody within reach behind them: the first follower is looked at
+      // on its own. For the runs that do go on, the only value carried from one unit to the next
+      // is v, so the loads of the next four units are issued together before they are looked at
+      // (a queue behind a barrier can be dozens of units long, and the longest one sets the pace
+      // of this region).
+      if (m + 1 >= d.M) continue;
+      {
+        const u32 i1 = sec_idx<kRevPass>(d.first, m + 1);
+        if (!step(m + 1, i1, MB_SHARED_LOAD_U32(&coll[i1]), sec_pos<kRevPass>(i1), sec_q<kRevPass>(i1)))
+          continue;
+      }
       bool open_run = true;
-      for (u32 k0 = m + 1; open_run && k0 < d.M; k0 += 4) {
+      for (u32 k0 = m + 2; open_run && k0 < d.M; k0 += 4) {
         u32 ik[4], cw[4];
         i32 pp[4], qq[4];
 #pragma unroll
@@ -2569,27 +2632,10 @@ struct CellSimT {
         }
 #pragma unroll
         for (u32 j = 0; j < 4; ++j) {
-          const u32 k = k0 + j;
-          if (k >= d.M || coll_occurred(cw[j]) || qq[j] > v) {
+          if (k0 + j >= d.M || !step(k0 + j, ik[j], cw[j], pp[j], qq[j])) {
             open_run = false;
             break;
           }
-          const i32 p = pp[j];
-          const i32 mv = p - v;  // distance to the blocker's site
-          MB_SHARED_STORE_U32(&coll[ik[j]], static_cast<u32>(mv > 0 ? mv - 1 : 0));  // event bits stay 0
-          MB_ATOMIC_OR_U32(&d.cand[k >> 5], 1u << (k & 31));
-          if (k == m + 1) MB_ATOMIC_OR_U32(&d.head1[k >> 5], 1u << (k & 31));
-          if constexpr (kCtr) {
-            if (never ||
-                (draws && !bernoulli_raw(raw(ctr_pack(S.epoch, kDrSecondary,
-                                                      ((kRevPass ? 0u : 1u) << 24) | k)),
-                                         1.0 - P.p_bypass))) {
-              open_run = false;
-              break;
-            }
-            MB_ATOMIC_OR_U32(&ok[k >> 5], 1u << (k & 31));
-          }
-          v = p < v + 1 ? p : v + 1;
         }
       }
     }
@@ -2979,6 +3025,7 @@ struct CellSimT {
         A.fwd[i] = fwd;
         A.ep[i] = ep;
       }
+      mv_clear_slow_bits(tid);  // the secondary pass is done with A.bits
     }
     cta.sync();  // every thread has read `base` before the leader moves the stream position
     if (!kCtr && draws) {
