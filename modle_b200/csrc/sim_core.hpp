@@ -1866,6 +1866,30 @@ struct CellSimT {
     }
     return a;
   }
+  // The same count for a caller whose previous answer `from` is close: doubling steps bracket the
+  // answer and a binary search finishes inside the bracket, so the trip count follows the
+  // distance (a warp runs as many trips as its farthest lane needs), not the array length.
+  MB_FN u32 count_fwd_lt_near(u64 thr, u32 from, u32 limit) const {
+    u32 a = from;
+    if (a >= limit || u64(A.fwd[A.fr[a]]) >= thr) return a;
+    // invariant: rank a is below thr
+    u32 step = 1;
+    while (a + step < limit && u64(A.fwd[A.fr[a + step]]) < thr) {
+      a += step;
+      step <<= 1;
+    }
+    u32 b = a + step < limit ? a + step : limit;  // rank b is not below thr (or b == limit)
+    ++a;
+    while (a < b) {
+      const u32 m = (a + b) >> 1;
+      if (u64(A.fwd[A.fr[m]]) < thr) {
+        a = m + 1;
+      } else {
+        b = m;
+      }
+    }
+    return a;
+  }
   MB_FN u32 count_fwd_lt_from_top(u64 thr) const {  // number of fwd ranks with pos < thr
     u32 c = S.num_active;
     for (int step = 0; step < 4; ++step) {
@@ -2185,9 +2209,13 @@ struct CellSimT {
           chunk(tid, n - j0, &lo, &hi);
           u32 b = 0;  // number of barriers with bar_pos < pos of the current unit
           bool first = true;
+          // position of the unit one rank down: carried along instead of re-read through rr
+          u32 below = (lo < hi && lo > 0) ? A.rev[A.rr[j0 + lo - 1]] : 0u;
           for (u32 k = j0 + lo; k < j0 + hi; ++k) {
             const u32 idx = A.rr[k];
             const u32 pos = A.rev[idx];
+            const u32 lower = below;
+            below = pos;
             if (use_lut) {  // a bucket holds a barrier or two: no cursor, no search
               b = A.bar_lut[(pos - P.start) >> P.lut_shift];
               while (b < nb && A.bar_pos[b] < pos) ++b;
@@ -2207,7 +2235,6 @@ struct CellSimT {
               while (b < nb && A.bar_pos[b] < pos) ++b;
             }
             if (b == 0) continue;
-            const u32 lower = k > j0 ? A.rev[A.rr[k - 1]] : 0u;
             const u32 mv = A.rm[idx];
             for (u32 t = b; t-- > 0;) {
               const u32 bp = A.bar_pos[t];
@@ -2224,9 +2251,17 @@ struct CellSimT {
           chunk(tid, jend + 1, &lo, &hi);
           u32 b = 0;  // number of barriers with bar_pos <= pos of the current unit
           bool first = true;
+          // the unit one rank up is read one trip ahead (its position bounds this unit's search)
+          u32 idx_up = lo < hi ? A.fr[lo] : 0u;
+          u32 pos_up = lo < hi ? A.fwd[idx_up] : 0u;
           for (u32 k = lo; k < hi; ++k) {
-            const u32 idx = A.fr[k];
-            const u32 pos = A.fwd[idx];
+            const u32 idx = idx_up;
+            const u32 pos = pos_up;
+            if (k < jend) {
+              idx_up = A.fr[k + 1];
+              pos_up = A.fwd[idx_up];
+            }
+            const u32 upper = k < jend ? pos_up : 0xFFFFFFFFu;
             if (use_lut) {
               b = A.bar_lut[(pos - P.start) >> P.lut_shift];
               while (b < nb && A.bar_pos[b] <= pos) ++b;
@@ -2246,7 +2281,6 @@ struct CellSimT {
               while (b < nb && A.bar_pos[b] <= pos) ++b;
             }
             if (b == nb) break;  // no barrier downstream of this or any later unit
-            const u32 upper = k < jend ? A.fwd[A.fr[k + 1]] : 0xFFFFFFFFu;
             const u32 mv = A.fm[idx];
             for (u32 t = b; t < nb; ++t) {
               const u32 bp = A.bar_pos[t];
@@ -2377,7 +2411,21 @@ struct CellSimT {
     const u32 r = A.rr[j];
     const u32 rp = A.rev[r];
     // first fwd rank in [0, i2) with pos >= rp
-    const u32 a = count_fwd_lt_from(rp, *hint == 0xFFFFFFFFu ? 0u : *hint, i2);
+    u32 a;
+    if (*hint == 0xFFFFFFFFu) {  // first rev rank of this thread: binary search over [0, i2)
+      u32 lo = 0, hi = i2;
+      while (lo < hi) {
+        const u32 m = (lo + hi) >> 1;
+        if (A.fwd[A.fr[m]] < rp) {
+          lo = m + 1;
+        } else {
+          hi = m;
+        }
+      }
+      a = lo;
+    } else {
+      a = count_fwd_lt_near(rp, *hint, i2);
+    }
     *hint = a;
     if (a == i2 || a == 0) return false;
     const u32 f = A.fr[a - 1];
@@ -2820,10 +2868,11 @@ struct CellSimT {
           const bool can = lane < nvalid && (Fle != 0 || alive_in != 0);
           u32 Rm = __ballot_sync(0xffffffffu, can);
           u32 bad = 0;
+          // outcomes of the draws d .. d + 31 (all this word can use), read once per word
+          const u32 fw = __funnelshift_r(bits_fail[d >> 5], bits_fail[(d >> 5) + 1], d & 31u);
           for (int it = 0; it < 34; ++it) {
             // the d-th draw belongs to the d-th REACHED candidate
-            const u32 dd = d + static_cast<u32>(__popc(Rm & lt));
-            const u32 fbit = (bits_fail[dd >> 5] >> (dd & 31)) & 1u;
+            const u32 fbit = (fw >> __popc(Rm & lt)) & 1u;
             bad = __ballot_sync(0xffffffffu, ((Rm >> lane) & 1u) && fbit);
             const u32 Rn = __ballot_sync(0xffffffffu, can && (bad & range) == 0);
             if (Rn == Rm) break;
