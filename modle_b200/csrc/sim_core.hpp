@@ -1047,15 +1047,25 @@ struct CellSimT {
       u32 lo, hi;
       chunk(tid, n, &lo, &hi);
       bool any = false;
+      // (the unit in slot k + 1 of one trip is the unit in slot k of the next: read once; only a
+      // tie on the position needs the full comparison)
+      u32 ar = lo < hi ? A.rr[lo] : 0u, af = lo < hi ? A.fr[lo] : 0u;
+      u32 par = lo < hi ? A.rev[ar] : 0u, paf = lo < hi ? A.fwd[af] : 0u;
       for (u32 k = lo; k < hi && k + 1 < n; ++k) {
-        if (rank_less<true>(A.rr[k + 1], A.rr[k], prev_r)) {
+        const u32 br = A.rr[k + 1], bf = A.fr[k + 1];
+        const u32 pbr = A.rev[br], pbf = A.fwd[bf];
+        if (pbr < par || (pbr == par && rank_less<true>(br, ar, prev_r))) {
           MB_ATOMIC_OR_U32(&dirty_r[k >> 5], 1u << (k & 31));
           any = true;
         }
-        if (rank_less<false>(A.fr[k + 1], A.fr[k], prev_f)) {
+        if (pbf < paf || (pbf == paf && rank_less<false>(bf, af, prev_f))) {
           MB_ATOMIC_OR_U32(&dirty_f[k >> 5], 1u << (k & 31));
           any = true;
         }
+        ar = br;
+        af = bf;
+        par = pbr;
+        paf = pbf;
       }
       if (any) MB_SHARED_STORE_U32(&S.tmp_u32[4], 1u);
     }
@@ -1582,14 +1592,15 @@ struct CellSimT {
         // (offsets past span are read but not used: inside the staged range)
         const u64 r0 = raw(base + o), r1 = raw(base + o + nt), r2 = raw(base + o + 2 * nt),
                   r3 = raw(base + o + 3 * nt);
-        double z;
-        if (!unit_normal_fast(r0, &z)) MB_ATOMIC_OR_U32(&slowbits[o >> 5], 1u << (o & 31));
-        u32 q = o + nt;
-        if (q < span && !unit_normal_fast(r1, &z)) MB_ATOMIC_OR_U32(&slowbits[q >> 5], 1u << (q & 31));
-        q += nt;
-        if (q < span && !unit_normal_fast(r2, &z)) MB_ATOMIC_OR_U32(&slowbits[q >> 5], 1u << (q & 31));
-        q += nt;
-        if (q < span && !unit_normal_fast(r3, &z)) MB_ATOMIC_OR_U32(&slowbits[q >> 5], 1u << (q & 31));
+        auto test = [&](u32 q, u64 r) {
+          double z;
+          if (q < span && !unit_normal_fast(r, &z))
+            MB_ATOMIC_OR_U32(&slowbits[q >> 5], 1u << (q & 31));
+        };
+        test(o, r0);
+        test(o + nt, r1);
+        test(o + 2 * nt, r2);
+        test(o + 3 * nt, r3);
       }
     }
     cta.sync();
@@ -1813,7 +1824,8 @@ struct CellSimT {
 #endif
           store(i, z);
         } else {
-          store(i, unit_normal_fast_value(my_shift == shift_spec ? r_spec : raw(base + my_shift + i)));
+          const u64 r = my_shift == shift_spec ? r_spec : raw(base + my_shift + i);
+          store(i, unit_normal_fast_value(r));
         }
       }
       if (over) S.move_bound_hit = 1;
@@ -2197,7 +2209,8 @@ struct CellSimT {
       // contiguous share of the rev ranks and of the fwd ranks together with the sorted barrier
       // positions -- the number of barriers below a unit comes from a look-up table over
       // position buckets plus a step or two (or, when the table found no room in shared memory,
-      // from one binary search for the first unit of the share and a forward-only cursor). The barriers that test rev rank k are those with
+      // from one binary search for the first unit of the share and a forward-only cursor). The
+      // barriers that test rev rank k are those with
       // pos[k-1] <= bp < pos[k] (all below pos[k] for k == j0); the closest one that is active,
       // blocks this direction with certainty and lies within the unit's move wins, exactly what
       // the per-barrier atomicMax selected. A hit overrides a boundary mark, as before.
@@ -2630,59 +2643,74 @@ struct CellSimT {
     u32* coll = kRevPass ? A.rc : A.fc;
     u32 lo, hi;
     chunk(tid, d.M, &lo, &hi);
-    for (u32 m = lo; m < hi; ++m) {
-      const u32 idx = sec_idx<kRevPass>(d.first, m);
-      // (a neighbouring walk may be parking a move in the index bits of this word; the event
-      // bits read here do not change in this region)
-      if (!coll_occurred(MB_SHARED_LOAD_U32(&coll[idx]))) continue;
-      i32 v = sec_q<kRevPass>(idx);
-      // One unit of a run: false when the run ends at scan position k (unit ik with collision
-      // word cw, position p and target q).
-      auto step = [&](u32 k, u32 ik, u32 cw, i32 p, i32 q) -> bool {
-        if (coll_occurred(cw) || q > v) return false;
-        const i32 mv = p - v;  // distance to the blocker's site
-        MB_SHARED_STORE_U32(&coll[ik], static_cast<u32>(mv > 0 ? mv - 1 : 0));  // event bits stay 0
-        MB_ATOMIC_OR_U32(&d.cand[k >> 5], 1u << (k & 31));
-        if (k == m + 1) MB_ATOMIC_OR_U32(&d.head1[k >> 5], 1u << (k & 31));
-        if constexpr (kCtr) {
-          if (never ||
-              (draws && !bernoulli_raw(raw(ctr_pack(S.epoch, kDrSecondary,
-                                                    ((kRevPass ? 0u : 1u) << 24) | k)),
-                                       1.0 - P.p_bypass)))
-            return false;
-          MB_ATOMIC_OR_U32(&ok[k >> 5], 1u << (k & 31));
-        }
-        v = p < v + 1 ? p : v + 1;
-        return true;
-      };
-      // Most stalled units have nobody within reach behind them: the first follower is looked at
-      // on its own. For the runs that do go on, the only value carried from one unit to the next
-      // is v, so the loads of the next four units are issued together before they are looked at
-      // (a queue behind a barrier can be dozens of units long, and the longest one sets the pace
-      // of this region).
-      if (m + 1 >= d.M) continue;
-      {
-        const u32 i1 = sec_idx<kRevPass>(d.first, m + 1);
-        if (!step(m + 1, i1, MB_SHARED_LOAD_U32(&coll[i1]), sec_pos<kRevPass>(i1), sec_q<kRevPass>(i1)))
-          continue;
+    // A thread first notes which of its scan positions hold a stalled unit (one in four or so) and
+    // then walks from those back to back: a warp goes through the walk as often as its busiest
+    // lane has heads, not once per scan position with a few lanes each.
+    for (u32 m0 = lo; m0 < hi; m0 += 32) {
+      u32 heads = 0;
+      const u32 m1 = m0 + 32 < hi ? m0 + 32 : hi;
+      for (u32 m = m0; m < m1; ++m) {
+        // (a neighbouring walk may be parking a move in the index bits of this word; the event
+        // bits read here do not change in this region)
+        const u32 cw = MB_SHARED_LOAD_U32(&coll[sec_idx<kRevPass>(d.first, m)]);
+        heads |= u32(coll_occurred(cw)) << (m - m0);
       }
-      bool open_run = true;
-      for (u32 k0 = m + 2; open_run && k0 < d.M; k0 += 4) {
-        u32 ik[4], cw[4];
-        i32 pp[4], qq[4];
-#pragma unroll
-        for (u32 j = 0; j < 4; ++j) ik[j] = k0 + j < d.M ? sec_idx<kRevPass>(d.first, k0 + j) : idx;
-#pragma unroll
-        for (u32 j = 0; j < 4; ++j) {
-          cw[j] = MB_SHARED_LOAD_U32(&coll[ik[j]]);
-          pp[j] = sec_pos<kRevPass>(ik[j]);
-          qq[j] = sec_q<kRevPass>(ik[j]);
+      while (heads) {
+        const u32 m = m0 + static_cast<u32>(MB_FFS(heads)) - 1;
+        heads &= heads - 1;
+        const u32 idx = sec_idx<kRevPass>(d.first, m);
+        i32 v = sec_q<kRevPass>(idx);
+        // One unit of a run: false when the run ends at scan position k (unit ik with collision
+        // word cw, position p and target q).
+        auto step = [&](u32 k, u32 ik, u32 cw, i32 p, i32 q) -> bool {
+          if (coll_occurred(cw) || q > v) return false;
+          const i32 mv = p - v;  // distance to the blocker's site
+          // (event bits stay 0)
+          MB_SHARED_STORE_U32(&coll[ik], static_cast<u32>(mv > 0 ? mv - 1 : 0));
+          MB_ATOMIC_OR_U32(&d.cand[k >> 5], 1u << (k & 31));
+          if (k == m + 1) MB_ATOMIC_OR_U32(&d.head1[k >> 5], 1u << (k & 31));
+          if constexpr (kCtr) {
+            if (never ||
+                (draws && !bernoulli_raw(raw(ctr_pack(S.epoch, kDrSecondary,
+                                                      ((kRevPass ? 0u : 1u) << 24) | k)),
+                                         1.0 - P.p_bypass)))
+              return false;
+            MB_ATOMIC_OR_U32(&ok[k >> 5], 1u << (k & 31));
+          }
+          v = p < v + 1 ? p : v + 1;
+          return true;
+        };
+        // Most stalled units have nobody within reach behind them: the first follower is looked at
+        // on its own. For the runs that do go on, the only value carried from one unit to the next
+        // is v, so the loads of the next four units are issued together before they are looked at
+        // (a queue behind a barrier can be dozens of units long, and the longest one sets the pace
+        // of this region).
+        if (m + 1 >= d.M) continue;
+        {
+          const u32 i1 = sec_idx<kRevPass>(d.first, m + 1);
+          if (!step(m + 1, i1, MB_SHARED_LOAD_U32(&coll[i1]), sec_pos<kRevPass>(i1),
+                    sec_q<kRevPass>(i1)))
+            continue;
         }
+        bool open_run = true;
+        for (u32 k0 = m + 2; open_run && k0 < d.M; k0 += 4) {
+          u32 ik[4], cw[4];
+          i32 pp[4], qq[4];
 #pragma unroll
-        for (u32 j = 0; j < 4; ++j) {
-          if (k0 + j >= d.M || !step(k0 + j, ik[j], cw[j], pp[j], qq[j])) {
-            open_run = false;
-            break;
+          for (u32 j = 0; j < 4; ++j)
+            ik[j] = k0 + j < d.M ? sec_idx<kRevPass>(d.first, k0 + j) : idx;
+#pragma unroll
+          for (u32 j = 0; j < 4; ++j) {
+            cw[j] = MB_SHARED_LOAD_U32(&coll[ik[j]]);
+            pp[j] = sec_pos<kRevPass>(ik[j]);
+            qq[j] = sec_q<kRevPass>(ik[j]);
+          }
+#pragma unroll
+          for (u32 j = 0; j < 4; ++j) {
+            if (k0 + j >= d.M || !step(k0 + j, ik[j], cw[j], pp[j], qq[j])) {
+              open_run = false;
+              break;
+            }
           }
         }
       }
