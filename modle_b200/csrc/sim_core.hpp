@@ -240,32 +240,16 @@ struct CellSimT {
   }
 
   // A serial reader of the raw stream used by the few inherently sequential samplers.
-  // Deterministic mode: the draws come from the ring in global memory (L2), and a sampler asks
-  // for them one after the other with arithmetic in between; the cursor keeps the next four
-  // requested ahead (q0 = draw `pos`), so a sampler waits for the memory once, not once per draw.
-  // (Entries past the staged part of the ring may be read ahead; they are never handed out: the
-  // callers' limits lie inside the staged part.)
   struct Cursor {
     const CellSimT* sim;
     u64 pos, limit;
     bool overrun;
-    u64 q0, q1, q2, q3;
     MB_FN u64 next() {
       if (pos >= limit) {
         overrun = true;
         return 0;
       }
-      if constexpr (kCtr) {
-        return sim->raw(pos++);
-      } else {
-        const u64 v = q0;
-        q0 = q1;
-        q1 = q2;
-        q2 = q3;
-        q3 = sim->raw(pos + 4);
-        ++pos;
-        return v;
-      }
+      return sim->raw(pos++);
     }
     MB_FN double uniform01() {  // boost::random::uniform_01<double>
       for (;;) {
@@ -274,17 +258,11 @@ struct CellSimT {
       }
     }
   };
-  MB_FN Cursor cursor(u64 pos, u64 limit) const {
-    if constexpr (kCtr) {
-      return Cursor{this, pos, limit, false, 0, 0, 0, 0};
-    } else {
-      return Cursor{this, pos, limit, false, raw(pos), raw(pos + 1), raw(pos + 2), raw(pos + 3)};
-    }
-  }
+  MB_FN Cursor cursor(u64 pos, u64 limit) const { return Cursor{this, pos, limit, false}; }
   // throughput mode: the private draw sequence of (epoch, phase, item)
   MB_FN Cursor ctr_cursor(u64 epoch, u32 phase, u32 item) const {
     const u64 c = ctr_pack(epoch, phase, item);
-    return Cursor{this, c, c + kCtrDrawsPerItem, false, 0, 0, 0, 0};
+    return Cursor{this, c, c + kCtrDrawsPerItem, false};
   }
 
   // Generator sub-stream gi writes its l draws of the window that starts at stream offset wbase
@@ -1818,36 +1796,26 @@ struct CellSimT {
         }
         over |= mv > P.move_bound;
       };
-      // The walk over the exceptions runs two trips ahead of the stores, so that every draw is
-      // requested from the ring (L2) two trips before it is used.
-      struct Ahead {
-        u64 r;
-        u32 exc;  // this lane's item is exception record `exc` (0xFFFFFFFF: a fast item, draw r)
-      };
-      auto request = [&](u32 i0) -> Ahead {
+      // the draw an item reads when no exception lies between the start of its 32 items and it
+      // -- nearly always -- is requested one trip ahead
+      u64 r_ahead = lo < hi ? raw(base + shift + lo + lane) : 0;
+      for (u32 i0 = lo; i0 < hi; i0 += G) {
         const u32 i = i0 + lane;
         const u32 end = i0 + G < hi ? i0 + G : hi;
-        u32 my_shift = shift;
-        Ahead t{0, 0xFFFFFFFFu};
+        const u64 r_spec = r_ahead;
+        const u32 shift_spec = shift;
+        u32 my_shift = shift, my_exc = 0xFFFFFFFFu;
         while (e < kept && ex[4 * e] < end) {  // same trips for every lane of the group
           const u32 xi = ex[4 * e];
           if (xi < i) my_shift = ex[4 * e + 1];
-          if (xi == i) t.exc = e;
+          if (xi == i) my_exc = e;
           shift = ex[4 * e + 1];  // later items start after this item's extra draws
           ++e;
         }
-        if (i < end && t.exc == 0xFFFFFFFFu) t.r = raw(base + my_shift + i);
-        return t;
-      };
-      Ahead t0 = request(lo), t1 = request(lo + G);
-      for (u32 i0 = lo; i0 < hi; i0 += G) {
-        const Ahead cur = t0;
-        t0 = t1;
-        t1 = request(i0 + 2 * G);
-        const u32 i = i0 + lane;
-        if (i >= hi) continue;
-        if (cur.exc != 0xFFFFFFFFu) {
-          const u64 zb = u64(ex[4 * cur.exc + 2]) | (u64(ex[4 * cur.exc + 3]) << 32);
+        if (end < hi) r_ahead = raw(base + shift + end + lane);
+        if (i >= end) continue;
+        if (my_exc != 0xFFFFFFFFu) {
+          const u64 zb = u64(ex[4 * my_exc + 2]) | (u64(ex[4 * my_exc + 3]) << 32);
           double z;
 #if MB_DEVICE_BUILD
           z = __longlong_as_double(static_cast<long long>(zb));
@@ -1856,7 +1824,8 @@ struct CellSimT {
 #endif
           store(i, z);
         } else {
-          store(i, unit_normal_fast_value(cur.r));
+          const u64 r = my_shift == shift_spec ? r_spec : raw(base + my_shift + i);
+          store(i, unit_normal_fast_value(r));
         }
       }
       if (over) S.move_bound_hit = 1;
