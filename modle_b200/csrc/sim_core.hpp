@@ -1284,6 +1284,7 @@ struct CellSimT {
     u64 i = 0;
     if (n > 1) {
       // bucket * (range + 1) <= 2^64 - 1: range + 1 serves as the reciprocal of the bucket
+      // (short of the quotient by (range + 1) / bucket at most: nothing for ranges below 2^32)
       const u64 range = n - 1;
       const InvU64 bucket{uniform_int_bucket(range), range + 1};
       do {

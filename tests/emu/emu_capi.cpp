@@ -399,6 +399,12 @@ u64 emu_ctr_draw(const u64* state, u64 epoch, u32 phase, u32 item, u32 k) {
   return sim.raw(ctr_pack(epoch, phase, item) + k);
 }
 u64 emu_mix64(u64 x) { return mix64(x); }
+// The kernel's division by a per-interval constant (sim_core.hpp div_u64); magic == 0: the
+// general reciprocal of inv_u64, else the caller's (uniform_int: range + 1 for the bucket).
+u64 emu_div_u64(u64 x, u64 d, u64 magic) {
+  return div_u64(x, magic ? InvU64{d, magic} : inv_u64(d));
+}
+u64 emu_uniform_int_bucket(u64 range) { return uniform_int_bucket(range); }
 
 // The kernel's collision-word helpers (sim_types.hpp), for the reference's encoding KATs.
 u32 emu_collision_word(u64 idx, u32 event) { return coll_make(static_cast<u32>(idx), event); }

@@ -276,3 +276,36 @@ def test_lef_bar_walk_without_the_barrier_lookup_table(name):
     finally:
         emu_lib.lib().emu_set_barrier_lut(1)
     assert results_equal(a, b) == []
+
+
+def test_division_by_a_per_interval_constant_is_exact():
+    """sim_core.hpp div_u64 (bind, contact sampling: draw / bucket of boost's uniform_int, which the
+    reference computes with a plain 64-bit division, uniform_int_distribution.hpp) against Python
+    integers: the general reciprocal, and range + 1 standing in for the reciprocal of the bucket."""
+    import ctypes as C
+    import random
+
+    L = emu_lib.lib()
+    L.emu_div_u64.restype = C.c_uint64
+    L.emu_div_u64.argtypes = [C.c_uint64] * 3
+    L.emu_uniform_int_bucket.restype = C.c_uint64
+    L.emu_uniform_int_bucket.argtypes = [C.c_uint64]
+    rnd = random.Random(7)
+    top = (1 << 64) - 1
+    xs = [0, 1, 2, top, top - 1, 1 << 63, (1 << 63) - 1, (1 << 32), (1 << 32) - 1] + \
+        [rnd.getrandbits(64) for _ in range(200)] + [rnd.getrandbits(rnd.randrange(1, 65)) for _ in range(200)]
+    ds = [1, 2, 3, 5, 7, 1 << 31, (1 << 32) - 1, 1 << 32, (1 << 32) + 1, 1 << 63, (1 << 63) + 1, top, top - 1] + \
+        [rnd.getrandbits(rnd.randrange(1, 65)) | 1 for _ in range(100)]
+    for d in ds:
+        for x in xs + [d - 1, d, d + 1 if d < top else d, (top // d) * d, max((top // d) * d - 1, 0)]:
+            assert int(L.emu_div_u64(x, d, 0)) == x // d, (x, d)
+    # uniform_int over [0, range]: bucket = (2^64 - 1) / (range + 1) (+1 when the remainder is range)
+    # (ranges are LEF counts and distances on a chromosome: below 2^32, where range + 1 is within
+    # one unit of the exact reciprocal; the kernel keeps positions in 32 bits)
+    ranges = [1, 2, 3, 10, 1288, 4978, 248_956_421, (1 << 28) - 1, (1 << 32) - 2] + \
+        [rnd.getrandbits(rnd.randrange(1, 33)) + 1 for _ in range(100)]
+    for r in ranges:
+        bucket = top // (r + 1) + (1 if top % (r + 1) == r else 0)
+        assert int(L.emu_uniform_int_bucket(r)) == bucket
+        for x in xs + [bucket - 1, bucket, bucket * r, bucket * (r + 1) - 1 if bucket * (r + 1) - 1 <= top else top]:
+            assert int(L.emu_div_u64(x, bucket, r + 1)) == x // bucket, (x, r)
