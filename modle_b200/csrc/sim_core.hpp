@@ -1526,7 +1526,8 @@ struct CellSimT {
   // One Normal(speed, sd) per item, items in stream order: the first n_rev items are the rev
   // moves of LEFs 0..n_rev-1, the others the fwd moves (generate_moves, simulation.cpp:299-330,
   // draws all rev moves and then all fwd moves). The fast ziggurat path uses exactly one draw;
-  // the rare slow paths are evaluated speculatively and stitched into the stream by the leader.
+  // the rare slow paths are evaluated speculatively, every one at its own offset, and stitched
+  // into the stream (which of them start an item, by how much each shifts the items behind it).
   MB_FN void draw_normal_moves(u32 items, u32 n_rev, double rev_speed, double fwd_speed) {
     if constexpr (kCtr) {
       // One ziggurat sampler per item on the item's own sequence. Some 98 % of the items are
