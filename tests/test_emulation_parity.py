@@ -44,6 +44,11 @@ CASES = {
                               max_burnin_epochs=150),
     "tiny_interval": dict(size=120_000, ncells=3, nbar=3, target_contact_density=0.002),
     "no_barriers": dict(size=2_000_000, ncells=2, nbar=0, target_contact_density=0.01),
+    # 480 contacts + 480 1D events per epoch against a scratch area that holds 62 events: the
+    # pooled sampling pass runs 16 batches per epoch (plus the rounds its off-stride events end)
+    "dense_sampling_many_batches": dict(size=3_000_000, ncells=2, nbar=40,
+                                        contact_sampling_interval=1000,
+                                        target_contact_density=0.2),
 }
 
 
