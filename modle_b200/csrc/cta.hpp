@@ -533,6 +533,14 @@ inline int& emu_thread_order() {
   return mode;
 }
 
+// Tests only: make bind_lefs take its sequential redo (the path a uniform_int rejection -- one
+// draw in 2^36 on a human chromosome -- sends it down) in every epoch although nothing was
+// rejected; the results must not change.
+inline int& emu_force_bind_redo() {
+  static thread_local int on = 0;
+  return on;
+}
+
 #ifdef MODLE_B200_EMU_MT  // ----------------------------------------------- SPMD emulation
 
 // Collectives go through per-thread slots of the shared scratch (at most kMaxWarps = 32 virtual

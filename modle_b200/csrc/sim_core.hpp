@@ -884,6 +884,9 @@ struct CellSimT {
       chunk(tid, n, &lo, &hi);
       u64 o = S.rng_pos + cnt[tid];
       bool rejected = false;
+#if !MB_DEVICE_BUILD
+      rejected = emu_force_bind_redo() != 0;  // (tests: the redo without a rejection)
+#endif
       for (u32 i = lo; i < hi; ++i) {
         if (A.ep[i] != kUnbound) continue;
         const u64 r = div_u64(raw(o++), bucket);

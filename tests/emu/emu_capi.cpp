@@ -99,6 +99,8 @@ const char* emu_last_error() { return g_emu_error.c_str(); }
 
 // 0 ascending, 1 descending, 2 shuffled per region (cta.hpp: emu_thread_order)
 void emu_set_thread_order(int mode) { emu_thread_order() = mode; }
+// bind_lefs takes its sequential redo in every epoch (cta.hpp: emu_force_bind_redo)
+void emu_set_force_bind_redo(int on) { emu_force_bind_redo() = on; }
 // CTA barriers the device build would have executed in this thread's calls so far (cta.hpp)
 u64 emu_barrier_count_get(int reset) {
   const u64 n = emu_barrier_count();

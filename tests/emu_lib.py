@@ -63,6 +63,12 @@ def set_thread_order(mode):
     lib().emu_set_thread_order(int(mode))
 
 
+def set_force_bind_redo(on):
+    """bind_lefs takes its sequential redo (the uniform_int rejection path) in every epoch of the
+    calling thread's later calls, although nothing was rejected."""
+    lib().emu_set_force_bind_redo(1 if on else 0)
+
+
 def set_rng_mode(mode):
     """0: deterministic mode (reference draw order), 1: throughput mode (counter-based draws);
     see modle_b200_set_rng_mode. Applies to the calling thread's later calls."""

@@ -314,3 +314,22 @@ def test_division_by_a_per_interval_constant_is_exact():
         assert int(L.emu_uniform_int_bucket(r)) == bucket
         for x in xs + [bucket - 1, bucket, bucket * r, bucket * (r + 1) - 1 if bucket * (r + 1) - 1 <= top else top]:
             assert int(L.emu_div_u64(x, bucket, r + 1)) == x // bucket, (x, r)
+
+
+@pytest.mark.parametrize("name", ["defaults_small", "skip_burnin", "sub_interval", "tiny_interval"])
+def test_bind_redo_path_gives_the_same_cells(name):
+    """A uniform_int rejection while binding (one draw in 2^36 on a human chromosome: a few per
+    cent of genome-wide runs see one) sends bind_lefs down a sequential redo that no input can
+    trigger in a test; with the emulation's switch every epoch takes it. Nothing was rejected, so
+    the result must still be the oracle's."""
+    kw = dict(CASES[name])
+    vt = kw.pop("_vt", 64)
+    staging = kw.pop("_staging", 0)
+    p, iv, bars, tasks = make_case(**kw)
+    a = pyoracle.simulate_interval(p, iv, bars, tasks, nthreads=4)
+    emu_lib.set_force_bind_redo(True)
+    try:
+        b = emu_lib.simulate_interval(p, iv, bars, tasks, virtual_threads=vt, staging=staging)
+    finally:
+        emu_lib.set_force_bind_redo(False)
+    assert results_equal(a, b) == []
